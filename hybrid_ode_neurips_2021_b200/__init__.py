@@ -1,0 +1,13 @@
+"""hybrid_ode_neurips_2021_b200 -- B200 (sm_100a) implementation of the hybrid-ODE hot path of
+ZhaozhiQIAN/Hybrid-ODE-NeurIPS-2021: fused fixed-step / dopri5 integration (forward + discrete backprop) of the
+expert PK/PD + latent-MLP vector field, and the fused read-out + masked-SSE reduction.
+
+Importing this package does not load CUDA; the shared library is loaded on first solver call and its absence is a
+hard error (there is no CPU fallback).
+"""
+from .solver import odeint, last_solve_info, fixed_grid_points  # noqa: F401
+from .model import RocheODE, NeuralODE, RocheExpertDecoder, RochConfig  # noqa: F401
+from .loss import masked_sse, decode_sse_loss  # noqa: F401
+from .integrate import install_as_torchdiffeq, patch_model  # noqa: F401
+
+__version__ = "0.1.0"

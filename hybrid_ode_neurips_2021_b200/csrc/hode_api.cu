@@ -1,0 +1,222 @@
+// hode_api.cu -- the C ABI of include/hode.h: argument checking and dispatch to the per-(field, D) launchers.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "hode_bodies.cuh"
+
+namespace hode {
+template <class F> int launch_fixed_fwd(const hode_cfg&, const SolveArgs&, cudaStream_t);
+template <class F> int launch_fixed_bwd(const hode_cfg&, const SolveArgs&, cudaStream_t);
+template <class F> int launch_dopri5_fwd(const hode_cfg&, const SolveArgs&, cudaStream_t);
+template <class F> int launch_dopri5_bwd(const hode_cfg&, const SolveArgs&, cudaStream_t);
+int launch_dose_schedule(const float*, int64_t, int64_t, int32_t, int64_t, float*, int32_t*, int32_t*, cudaStream_t);
+int launch_decode_sse(int32_t, int32_t, int32_t, int64_t, double, const float*, const float*, const float*,
+                      const float*, const float*, int64_t, int64_t, int64_t, float*, float*, float*, float*,
+                      cudaStream_t);
+}  // namespace hode
+
+using namespace hode;
+
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, const char* a = "", long long b = 0) {
+    snprintf(g_err, sizeof(g_err), fmt, a, b);
+    return code;
+}
+
+enum Op { OP_FIXED_FWD, OP_FIXED_BWD, OP_DOPRI5_FWD, OP_DOPRI5_BWD };
+
+template <class F>
+static int run(Op op, const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) {
+    switch (op) {
+        case OP_FIXED_FWD: return launch_fixed_fwd<F>(cfg, a, st);
+        case OP_FIXED_BWD: return launch_fixed_bwd<F>(cfg, a, st);
+        case OP_DOPRI5_FWD: return launch_dopri5_fwd<F>(cfg, a, st);
+        case OP_DOPRI5_BWD: return launch_dopri5_bwd<F>(cfg, a, st);
+    }
+    return -1;
+}
+
+static bool roche_dim_ok(int d) { return d == 4 || d == 6 || d == 8 || d == 12; }
+
+static int dispatch(Op op, const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) {
+    int rc = -1;
+    if (cfg.field == HODE_FIELD_ROCHE) {
+        switch (cfg.latent_dim) {
+            case 4: rc = run<Roche<4>>(op, cfg, a, st); break;
+            case 6: rc = run<Roche<6>>(op, cfg, a, st); break;
+            case 8: rc = run<Roche<8>>(op, cfg, a, st); break;
+            case 12: rc = run<Roche<12>>(op, cfg, a, st); break;
+            default: return fail(HODE_ERR_UNSUPPORTED, "RocheODE latent_dim %s%lld is not compiled in (4, 6, 8, 12)", "", cfg.latent_dim);
+        }
+    } else {
+        return fail(HODE_ERR_UNSUPPORTED, "field %s%lld is not compiled in", "", cfg.field);
+    }
+    if (rc == 0) return HODE_OK;
+    if (rc == -2) return fail(HODE_ERR_UNSUPPORTED, "batch-coupled dopri5 group larger than %s%lld trajectories", "", hode_dopri5_max_batch(&cfg));
+    if (rc == -1) return fail(HODE_ERR_UNSUPPORTED, "method %s%lld is not valid for this entry point", "", cfg.method);
+    if (rc == (int)cudaErrorNoKernelImageForDevice || rc == (int)cudaErrorNoDevice || rc == (int)cudaErrorInsufficientDriver)
+        return fail(HODE_ERR_NO_DEVICE, "%s (libhode_b200 holds sm_100a code only)", cudaGetErrorString((cudaError_t)rc));
+    return fail(HODE_ERR_CUDA, "CUDA error: %s (%lld)", cudaGetErrorString((cudaError_t)rc), rc);
+}
+
+extern "C" {
+
+int32_t hode_abi_version(void) { return HODE_ABI_VERSION; }
+const char* hode_last_error(void) { return g_err; }
+
+int64_t hode_param_count(const hode_cfg* cfg) {
+    if (!cfg) return -1;
+    const int64_t d = cfg->latent_dim;
+    if (cfg->field == HODE_FIELD_ROCHE) return d >= 4 ? 13 + (d - 4) * d + (d - 4) : -1;
+    if (cfg->field == HODE_FIELD_NEURAL) return d >= 1 ? 1 + 10 * d * (d + 1) + 10 * d + d * 10 * d + d : -1;
+    return -1;
+}
+
+int32_t hode_supported(const hode_cfg* cfg) {
+    if (!cfg) return 0;
+    if (cfg->method < HODE_EULER || cfg->method > HODE_DOPRI5) return 0;
+    if (cfg->field == HODE_FIELD_ROCHE) return roche_dim_ok(cfg->latent_dim) ? 1 : 0;
+    return 0;
+}
+
+int64_t hode_dopri5_max_batch(const hode_cfg* cfg) {
+    (void)cfg;
+    return 512;
+}
+
+size_t hode_fixed_tape_bytes(const hode_cfg* cfg, int64_t n_traj, int32_t n_grid) {
+    if (!cfg || n_traj < 0 || n_grid < 1) return 0;
+    return (size_t)(n_grid - 1) * (size_t)n_traj * (size_t)cfg->latent_dim * sizeof(float);
+}
+
+static int check_common(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const void* dose_amt, const void* dose_t,
+                        int64_t dose_t_stride, const void* params, int32_t n_t) {
+    if (!cfg) return fail(HODE_ERR_ARG, "cfg is NULL");
+    if (n_groups < 0 || batch < 0) return fail(HODE_ERR_ARG, "negative n_groups/batch");
+    if (n_groups * batch > 0 && (!dose_amt || !params)) return fail(HODE_ERR_ARG, "NULL dose_amt/params");
+    if (cfg->n_dose < 0 || (cfg->n_dose > 0 && (!dose_t || dose_t_stride < cfg->n_dose)))
+        return fail(HODE_ERR_ARG, "bad dose_t / dose_t_stride / n_dose");
+    if (n_t < 1) return fail(HODE_ERR_ARG, "n_t must be >= 1");
+    if (n_groups > 0x7fffffffLL) return fail(HODE_ERR_ARG, "too many groups");
+    return HODE_OK;
+}
+
+static void fill_common(SolveArgs& a, const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,
+                        const float* dose_t, int64_t dose_t_stride, const float* params, const int32_t* pset) {
+    memset(&a, 0, sizeof(a));
+    a.n_groups = n_groups; a.batch = batch;
+    a.dose_amt = dose_amt; a.dose_t = dose_t; a.dose_t_stride = dose_t_stride; a.n_dose = cfg->n_dose;
+    a.params = params; a.pset = pset; a.perturb = cfg->perturb;
+    a.rtol_f = (float)cfg->rtol; a.atol_f = (float)cfg->atol;
+    a.safety = cfg->safety; a.ifactor = cfg->ifactor; a.dfactor = cfg->dfactor; a.first_step = cfg->first_step;
+    a.max_num_steps = cfg->max_num_steps; a.attempt_cap = cfg->attempt_cap;
+    a.per_traj = cfg->controller == HODE_CTRL_TRAJ;
+}
+
+int32_t hode_dose_schedule(const float* action, int64_t stride_t, int64_t stride_b, int32_t T, int64_t n_traj,
+                           float* dose_amt, int32_t* dose_idx, int32_t* dose_count, void* stream) {
+    if (T < 1 || n_traj < 0) return fail(HODE_ERR_ARG, "bad T / n_traj");
+    if (n_traj == 0) return HODE_OK;
+    if (!action || !dose_amt || !dose_idx || !dose_count) return fail(HODE_ERR_ARG, "NULL pointer");
+    const int rc = launch_dose_schedule(action, stride_t, stride_b, T, n_traj, dose_amt, dose_idx, dose_count,
+                                        (cudaStream_t)stream);
+    if (rc != 0) return fail(HODE_ERR_CUDA, "CUDA error: %s (%lld)", cudaGetErrorString((cudaError_t)rc), rc);
+    return HODE_OK;
+}
+
+int32_t hode_fixed_fwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* y0, const float* dose_amt,
+                       const float* dose_t, int64_t dose_t_stride, const float* params,
+                       const int32_t* param_set_of_group, const float* grid, int32_t n_grid, const float* t_eval,
+                       int32_t n_t, float* h_out, float* tape, void* stream) {
+    int rc = check_common(cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, n_t);
+    if (rc) return rc;
+    if (cfg->method == HODE_DOPRI5) return fail(HODE_ERR_ARG, "hode_fixed_fwd called with method dopri5");
+    if (n_grid < 1 || !grid || !t_eval) return fail(HODE_ERR_ARG, "bad grid / t_eval");
+    if (n_groups * batch == 0) return HODE_OK;
+    if (!y0 || !h_out) return fail(HODE_ERR_ARG, "NULL y0 / h_out");
+    SolveArgs a;
+    fill_common(a, cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, param_set_of_group);
+    a.y0 = y0; a.grid = grid; a.n_grid = n_grid; a.t_eval_f = t_eval; a.n_t = n_t; a.h_out = h_out; a.tape_y = tape;
+    return dispatch(OP_FIXED_FWD, *cfg, a, (cudaStream_t)stream);
+}
+
+int32_t hode_fixed_bwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,
+                       const float* dose_t, int64_t dose_t_stride, const float* params,
+                       const int32_t* param_set_of_group, int32_t n_param_sets, const float* grid, int32_t n_grid,
+                       const float* t_eval, int32_t n_t, const float* grad_h, const float* tape, float* grad_y0,
+                       float* grad_params, void* stream) {
+    int rc = check_common(cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, n_t);
+    if (rc) return rc;
+    if (cfg->method == HODE_DOPRI5) return fail(HODE_ERR_ARG, "hode_fixed_bwd called with method dopri5");
+    if (n_grid < 1 || !grid || !t_eval || n_param_sets < 1 || !grad_params) return fail(HODE_ERR_ARG, "bad grid / t_eval / grad_params");
+    const int64_t P = hode_param_count(cfg);
+    cudaError_t e = cudaMemsetAsync(grad_params, 0, sizeof(float) * (size_t)P * (size_t)n_param_sets, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(HODE_ERR_CUDA, "CUDA error: %s (%lld)", cudaGetErrorString(e), (long long)e);
+    if (n_groups * batch == 0) return HODE_OK;
+    if (!grad_h || !grad_y0 || (n_grid > 1 && !tape)) return fail(HODE_ERR_ARG, "NULL grad_h / grad_y0 / tape");
+    SolveArgs a;
+    fill_common(a, cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, param_set_of_group);
+    a.n_param_sets = n_param_sets;
+    a.grid = grid; a.n_grid = n_grid; a.t_eval_f = t_eval; a.n_t = n_t;
+    a.grad_h = grad_h; a.tape_y = const_cast<float*>(tape); a.grad_y0 = grad_y0; a.grad_params = grad_params;
+    return dispatch(OP_FIXED_BWD, *cfg, a, (cudaStream_t)stream);
+}
+
+int32_t hode_dopri5_fwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* y0,
+                        const float* dose_amt, const float* dose_t, int64_t dose_t_stride, const float* params,
+                        const int32_t* param_set_of_group, const double* t_eval, int32_t n_t, float* h_out,
+                        double* tape_t, float* tape_y, int32_t tape_capacity, hode_stats* stats, void* stream) {
+    int rc = check_common(cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, n_t);
+    if (rc) return rc;
+    if (cfg->method != HODE_DOPRI5) return fail(HODE_ERR_ARG, "hode_dopri5_fwd called with a fixed-grid method");
+    if (!t_eval || !stats) return fail(HODE_ERR_ARG, "NULL t_eval / stats");
+    if ((tape_y == nullptr) != (tape_t == nullptr)) return fail(HODE_ERR_ARG, "tape_t and tape_y must both be given or both be NULL");
+    if (tape_y && tape_capacity < 1) return fail(HODE_ERR_ARG, "tape_capacity must be >= 1");
+    if (n_groups * batch == 0) return HODE_OK;
+    if (!y0 || !h_out) return fail(HODE_ERR_ARG, "NULL y0 / h_out");
+    SolveArgs a;
+    fill_common(a, cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, param_set_of_group);
+    a.y0 = y0; a.t_eval_d = t_eval; a.n_t = n_t; a.h_out = h_out;
+    a.tape_t = tape_t; a.tape_y = tape_y; a.tape_cap = tape_capacity; a.stats = stats;
+    return dispatch(OP_DOPRI5_FWD, *cfg, a, (cudaStream_t)stream);
+}
+
+int32_t hode_dopri5_bwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,
+                        const float* dose_t, int64_t dose_t_stride, const float* params,
+                        const int32_t* param_set_of_group, int32_t n_param_sets, const double* t_eval, int32_t n_t,
+                        const float* grad_h, const double* tape_t, const float* tape_y, int32_t tape_capacity,
+                        const hode_stats* stats, float* grad_y0, float* grad_params, void* stream) {
+    int rc = check_common(cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, n_t);
+    if (rc) return rc;
+    if (cfg->method != HODE_DOPRI5) return fail(HODE_ERR_ARG, "hode_dopri5_bwd called with a fixed-grid method");
+    if (!t_eval || !stats || !tape_t || !tape_y || n_param_sets < 1 || !grad_params || tape_capacity < 1)
+        return fail(HODE_ERR_ARG, "NULL / bad t_eval, stats, tape or grad_params");
+    const int64_t P = hode_param_count(cfg);
+    cudaError_t e = cudaMemsetAsync(grad_params, 0, sizeof(float) * (size_t)P * (size_t)n_param_sets, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(HODE_ERR_CUDA, "CUDA error: %s (%lld)", cudaGetErrorString(e), (long long)e);
+    if (n_groups * batch == 0) return HODE_OK;
+    if (!grad_h || !grad_y0) return fail(HODE_ERR_ARG, "NULL grad_h / grad_y0");
+    SolveArgs a;
+    fill_common(a, cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, param_set_of_group);
+    a.n_param_sets = n_param_sets;
+    a.t_eval_d = t_eval; a.n_t = n_t; a.grad_h = grad_h;
+    a.tape_t = const_cast<double*>(tape_t); a.tape_y = const_cast<float*>(tape_y); a.tape_cap = tape_capacity;
+    a.stats = const_cast<hode_stats*>(stats); a.grad_y0 = grad_y0; a.grad_params = grad_params;
+    return dispatch(OP_DOPRI5_BWD, *cfg, a, (cudaStream_t)stream);
+}
+
+int32_t hode_decode_sse(int32_t D, int32_t obs, int32_t n_t, int64_t n_traj, double n_norm, const float* h,
+                        const float* W, const float* b, const float* x, const float* mask, int64_t st, int64_t sb,
+                        int64_t so, float* loss, float* grad_h, float* grad_w, float* grad_b, void* stream) {
+    if (D < 1 || D > 64 || obs < 1 || n_t < 1 || n_traj < 0) return fail(HODE_ERR_ARG, "bad D / obs / n_t / n_traj");
+    if (!loss || !W || !b) return fail(HODE_ERR_ARG, "NULL loss / W / b");
+    if (n_traj > 0 && (!h || !x || !mask)) return fail(HODE_ERR_ARG, "NULL h / x / mask");
+    const int rc = launch_decode_sse(D, obs, n_t, n_traj, n_norm, h, W, b, x, mask, st, sb, so, loss, grad_h, grad_w,
+                                     grad_b, (cudaStream_t)stream);
+    if (rc == -1) return fail(HODE_ERR_UNSUPPORTED, "decode_sse: obs*D too large for one CTA's shared memory");
+    if (rc != 0) return fail(HODE_ERR_CUDA, "CUDA error: %s (%lld)", cudaGetErrorString((cudaError_t)rc), rc);
+    return HODE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,196 @@
+// hode_aux.cu -- the two streaming kernels either side of the solve:
+//   * dose_schedule_kernel : RocheODE/NeuralODE.set_action (model.py:495-507, 1001-1013) without the O(B) Python loop
+//   * decode_sse_kernel    : output_function (model.py:1120) + masked SSE (model.py:1179) + their gradients, one pass
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace hode {
+
+// ---------------------------------------------------------------------------------------------------------------
+// one thread per patient: max over time, indices of the non-zero actions in ascending order
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dose_schedule_kernel(const float* __restrict__ action, int64_t stride_t,
+                                                            int64_t stride_b, int32_t T, int64_t n_traj,
+                                                            float* __restrict__ dose_amt,
+                                                            int32_t* __restrict__ dose_idx,
+                                                            int32_t* __restrict__ dose_count) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_traj) return;
+    const float* p = action + b * stride_b;
+    float mx = p[0];
+    int cnt = 0;
+    for (int t = 0; t < T; ++t) {
+        const float v = p[(int64_t)t * stride_t];
+        mx = (v > mx || v != v) ? v : mx;  // torch.max propagates NaN
+        if (v != 0.0f) dose_idx[b * T + cnt++] = t;
+    }
+    for (int c = cnt; c < T; ++c) dose_idx[b * T + c] = -1;
+    dose_amt[b] = mx;
+    dose_count[b] = cnt;
+}
+
+int launch_dose_schedule(const float* action, int64_t stride_t, int64_t stride_b, int32_t T, int64_t n_traj,
+                         float* dose_amt, int32_t* dose_idx, int32_t* dose_count, cudaStream_t st) {
+    const int threads = 256;
+    const int64_t blocks = (n_traj + threads - 1) / threads;
+    dose_schedule_kernel<<<(unsigned)blocks, threads, 0, st>>>(action, stride_t, stride_b, T, n_traj, dose_amt,
+                                                               dose_idx, dose_count);
+    return (int)cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// decode + masked SSE.  HBM-bound: per (t, trajectory) it reads obs x + obs mask + D h floats and writes D grad_h.
+//
+// Persistent CTAs walk tiles of TR trajectories at one observation time.  Per tile:
+//   load   x / mask tile -> shared memory, consecutive lanes on consecutive addresses (coalesced when so == 1)
+//   pass 1 thread = trajectory: x_hat = W h + b, c = -2/n (x - x_hat) mask, loss += (x - x_hat)^2 mask,
+//          grad_h = W^T c (registers), c written back over the x tile
+//   pass 2 thread = (observation o, row subset): grad_W[o,:] += c[r,o] h[r,:], grad_b[o] += c[r,o] -- the contraction over
+//          trajectories stays in registers across ALL tiles of the CTA, so global atomics happen once per CTA.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kTR = 128;       // trajectories per tile == threads per CTA
+constexpr int kThreads = 128;
+
+template <int D>
+__global__ void __launch_bounds__(kThreads) decode_sse_kernel(
+    int32_t obs, int32_t n_t, int64_t n_traj, float scale /* -2/n_norm */, float inv_norm, const float* __restrict__ h,
+    const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ x,
+    const float* __restrict__ mask, int64_t st, int64_t sb, int64_t so, float* __restrict__ loss,
+    float* __restrict__ grad_h, float* __restrict__ grad_w, float* __restrict__ grad_b) {
+    extern __shared__ float smem[];
+    const int ld = obs | 1;  // odd row stride: thread-per-row accesses hit 32 distinct banks
+    float* sW = smem;                    // [obs][D]
+    float* sB = sW + obs * D;            // [obs]
+    float* sH = sB + obs;                // [kTR][D]
+    float* sX = sH + kTR * D;            // [kTR][ld]
+    float* sM = sX + kTR * ld;           // [kTR][ld]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < obs * D; i += kThreads) sW[i] = W[i];
+    for (int i = tid; i < obs; i += kThreads) sB[i] = bias[i];
+
+    // pass-2 ownership: column o2, row subset sub2 of nsub
+    const int nsub = kThreads / obs > 0 ? kThreads / obs : 1;
+    const int o2 = tid % obs;  // obs <= kThreads is enforced by the launcher
+    const int sub2 = tid / obs;
+    const bool act2 = sub2 < nsub;
+    float gw[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) gw[d] = 0.0f;
+    float gb = 0.0f, lsum = 0.0f;
+
+    const int64_t tiles_per_t = (n_traj + kTR - 1) / kTR;
+    const int64_t n_tiles = tiles_per_t * n_t;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t t = tile / tiles_per_t;
+        const int64_t b0 = (tile % tiles_per_t) * kTR;
+        const int rows = (int)((n_traj - b0) < kTR ? (n_traj - b0) : kTR);
+        __syncthreads();  // previous tile's pass 2 is done with sX / sH (and the W staging on the first trip)
+        // ---- tile load (no integer division in the loop: (r, o) advance by a fixed step with carry) ---------------
+        {
+            int r = tid / obs, o = tid % obs;
+            const int dr = kThreads / obs, dor = kThreads % obs;
+            const float* xb = x + t * st + b0 * sb;
+            const float* mb = mask + t * st + b0 * sb;
+            while (r < rows) {
+                const int64_t off = (int64_t)r * sb + (int64_t)o * so;
+                sX[r * ld + o] = xb[off];
+                sM[r * ld + o] = mb[off];
+                r += dr; o += dor;
+                if (o >= obs) { o -= obs; ++r; }
+            }
+        }
+        // ---- pass 1 -------------------------------------------------------------------------------------------
+        float hv[D], gh[D];
+        const bool act1 = tid < rows;
+        if (act1) {
+            const float* hp = h + ((int64_t)t * n_traj + b0 + tid) * D;
+#pragma unroll
+            for (int d = 0; d < D; ++d) { hv[d] = hp[d]; sH[tid * D + d] = hv[d]; gh[d] = 0.0f; }
+        }
+        __syncthreads();
+        if (act1) {
+            float* xr = sX + tid * ld;
+            const float* mr = sM + tid * ld;
+            for (int o = 0; o < obs; ++o) {
+                float xh = sB[o];
+#pragma unroll
+                for (int d = 0; d < D; ++d) xh = fmaf(sW[o * D + d], hv[d], xh);
+                const float diff = xr[o] - xh;
+                const float m = mr[o];
+                lsum = fmaf(diff * diff, m, lsum);
+                const float c = scale * diff * m;
+#pragma unroll
+                for (int d = 0; d < D; ++d) gh[d] = fmaf(c, sW[o * D + d], gh[d]);
+                xr[o] = c;
+            }
+            if (grad_h != nullptr) {
+                float* gp = grad_h + ((int64_t)t * n_traj + b0 + tid) * D;
+#pragma unroll
+                for (int d = 0; d < D; ++d) gp[d] = gh[d];
+            }
+        }
+        __syncthreads();
+        // ---- pass 2 -------------------------------------------------------------------------------------------
+        if (act2 && grad_w != nullptr) {
+            for (int r = sub2; r < rows; r += nsub) {
+                const float c = sX[r * ld + o2];
+                gb += c;
+#pragma unroll
+                for (int d = 0; d < D; ++d) gw[d] = fmaf(c, sH[r * D + d], gw[d]);
+            }
+        }
+    }
+    // ---- CTA epilogue: one global atomic per (o, d) per row subset, one per warp for the loss ----------------------
+    if (act2 && grad_w != nullptr) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) atomicAdd(&grad_w[o2 * D + d], gw[d]);
+        if (grad_b != nullptr) atomicAdd(&grad_b[o2], gb);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    if ((tid & 31) == 0) atomicAdd(loss, lsum * inv_norm);
+}
+
+template <int D>
+static int launch_decode_sse_d(int32_t obs, int32_t n_t, int64_t n_traj, double n_norm, const float* h, const float* W,
+                               const float* b, const float* x, const float* mask, int64_t st, int64_t sb, int64_t so,
+                               float* loss, float* grad_h, float* grad_w, float* grad_b, cudaStream_t stream) {
+    const int ld = obs | 1;
+    const size_t sh = sizeof(float) * ((size_t)obs * D + obs + (size_t)kTR * D + 2 * (size_t)kTR * ld);
+    if (obs > kThreads || sh > 227 * 1024) return -1;
+    cudaError_t e = cudaFuncSetAttribute(decode_sse_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_sse_kernel<D>, kThreads, sh);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t n_tiles = ((n_traj + kTR - 1) / kTR) * n_t;
+    int64_t grid = (int64_t)sms * per_sm;  // persistent: a whole number of CTAs per SM
+    if (grid > n_tiles) grid = n_tiles;
+    if (grid < 1) grid = 1;
+    decode_sse_kernel<D><<<(unsigned)grid, kThreads, sh, stream>>>(obs, n_t, n_traj, (float)(-2.0 / n_norm),
+                                                                  (float)(1.0 / n_norm), h, W, b, x, mask, st, sb, so,
+                                                                  loss, grad_h, grad_w, grad_b);
+    return (int)cudaGetLastError();
+}
+
+int launch_decode_sse(int32_t D, int32_t obs, int32_t n_t, int64_t n_traj, double n_norm, const float* h,
+                      const float* W, const float* b, const float* x, const float* mask, int64_t st, int64_t sb,
+                      int64_t so, float* loss, float* grad_h, float* grad_w, float* grad_b, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), stream);
+    if (e != cudaSuccess) return (int)e;
+    if (grad_w) { e = cudaMemsetAsync(grad_w, 0, sizeof(float) * (size_t)obs * D, stream); if (e != cudaSuccess) return (int)e; }
+    if (grad_b) { e = cudaMemsetAsync(grad_b, 0, sizeof(float) * (size_t)obs, stream); if (e != cudaSuccess) return (int)e; }
+    if (n_traj == 0) return 0;
+#define HODE_DS(DD) \
+    case DD: return launch_decode_sse_d<DD>(obs, n_t, n_traj, n_norm, h, W, b, x, mask, st, sb, so, loss, grad_h, grad_w, grad_b, stream)
+    switch (D) {
+        HODE_DS(4); HODE_DS(6); HODE_DS(8); HODE_DS(12);
+        default: return -1;
+    }
+#undef HODE_DS
+}
+
+}  // namespace hode

@@ -1,0 +1,430 @@
+// hode_core.cuh -- per-trajectory arithmetic of the hybrid-ODE hot path: vector fields (+ hand-derived VJPs),
+// fixed-grid step functions, the dopri5 attempt, dense output, and their reverse sweeps.
+//
+// Everything here is written per trajectory ("one thread = one patient, state in registers") and is shared by the
+// sm_100a kernels in hode_kernels.cu.  It also compiles as plain C++ (HODE_HOSTSIM) for tests/hostsim, a TEST-ONLY
+// thread-emulation used to debug the derivations in a container that has no GPU; the product never loads that.
+//
+// Reference semantics followed (file:line into the reference; "tde" = torchdiffeq 0.2.2, restated in oracle/odeint.py):
+//   RocheODE.forward / dose_at_time     model.py:509-555
+//   NeuralODE.forward / dose_at_time    model.py:1015-1026
+//   tde fixed_grid.py step functions, solvers.py FixedGridODESolver.integrate, rk_common.py _runge_kutta_step,
+//   misc.py _select_initial_step/_compute_error_ratio/_optimal_step_size, interp.py _interp_fit/_interp_evaluate
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__) && !defined(HODE_HOSTSIM)
+#define HODE_HD __host__ __device__ __forceinline__
+#define HODE_D __device__ __forceinline__
+#define HODE_DEVICE_BUILD 1
+#else
+#define HODE_HD inline
+#define HODE_D inline
+#define HODE_DEVICE_BUILD 0
+#endif
+
+#ifndef HODE_FAST_TANH
+#define HODE_FAST_TANH 0
+#endif
+
+namespace hode {
+
+// ------------------------------------------------------------------------------------------------------------
+// exactly-rounded fp32 primitives for TIME arithmetic.  PyTorch evaluates `t0 + alpha*dt` as two separately rounded
+// float32 ops; a contracted FMA would move stage times by an ulp and flip `t >= dose_time` (model.py:512).
+// ------------------------------------------------------------------------------------------------------------
+#if HODE_DEVICE_BUILD && defined(__CUDA_ARCH__)
+HODE_D float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+HODE_D float add_rn(float a, float b) { return __fadd_rn(a, b); }
+HODE_D float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+HODE_D float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+#else
+// host build is compiled with -ffp-contract=off
+HODE_HD float mul_rn(float a, float b) { volatile float r = a * b; return r; }
+HODE_HD float add_rn(float a, float b) { volatile float r = a + b; return r; }
+HODE_HD float sub_rn(float a, float b) { volatile float r = a - b; return r; }
+HODE_HD float div_rn(float a, float b) { volatile float r = a / b; return r; }
+#endif
+
+// tde _nextafter(t, t+1) / _nextafter(t, t-1)
+HODE_HD float t_next(float t) { return nextafterf(t, t + 1.0f); }
+HODE_HD float t_prev(float t) { return nextafterf(t, t - 1.0f); }
+
+HODE_HD float tanh_f(float x) {
+#if HODE_FAST_TANH && HODE_DEVICE_BUILD && defined(__CUDA_ARCH__)
+    // 1 - 2/(exp(2x)+1): 2 MUFU + 3 FMA-pipe ops, abs error ~1.2e-7 ("tanh")
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+#else
+    return tanhf(x);
+#endif
+}
+
+// x ** p with a float32 tensor exponent (model.py:529, 537-538).  p == 2 (RochConfig default) is a multiply.
+HODE_HD float pow_hill(float x, float p) { return (p == 2.0f) ? x * x : powf(x, p); }
+// d/dx x**p = p * x**(p-1)   (autograd pow_backward_self; zero where p == 0)
+HODE_HD float dpow_hill(float x, float p) {
+    if (p == 2.0f) return 2.0f * x;
+    if (p == 0.0f) return 0.0f;
+    return p * powf(x, p - 1.0f);
+}
+// d/dp x**p = x**p * log(x)  (autograd pow_backward_exponent; zero where x == 0 and p >= 0)
+HODE_HD float dpow_hill_exp(float x, float xp, float p) {
+    if (x == 0.0f && p >= 0.0f) return 0.0f;
+    return xp * logf(x);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// dose schedules (set_action output): one amount + n_dose times per patient
+// ------------------------------------------------------------------------------------------------------------
+template <int ND>
+struct DoseReg {  // times held in registers
+    float amt;
+    float tau[ND];
+    static constexpr int kStatic = ND;
+    HODE_HD int n() const { return ND; }
+    HODE_HD float at(int j) const { return tau[j]; }
+};
+struct DoseMem {  // times read from memory (any n_dose)
+    float amt;
+    const float* tau;
+    int nd;
+    HODE_HD int n() const { return nd; }
+    HODE_HD float at(int j) const { return tau[j]; }
+};
+
+// RocheODE.dose_at_time (model.py:509-513): amt * sum_j exp(kel*(tau_j - t) * [t>=tau_j]) * [t>=tau_j]
+template <class Dose>
+HODE_HD float roche_dose(const Dose& ds, float t, float kel) {
+    float s = 0.0f;
+    const int n = ds.n();
+    for (int j = 0; j < n; ++j) {
+        const float tau = ds.at(j);
+        if (t >= tau) s += expf(mul_rn(kel, sub_rn(tau, t)));
+    }
+    return ds.amt * s;
+}
+// d Dose / d kel = amt * sum_j (tau_j - t) exp(kel (tau_j - t)) [t >= tau_j]
+template <class Dose>
+HODE_HD float roche_dose_dkel(const Dose& ds, float t, float kel) {
+    float s = 0.0f;
+    const int n = ds.n();
+    for (int j = 0; j < n; ++j) {
+        const float tau = ds.at(j);
+        if (t >= tau) {
+            const float d = sub_rn(tau, t);
+            s += d * expf(mul_rn(kel, d));
+        }
+    }
+    return ds.amt * s;
+}
+// NeuralODE.dose_at_time (model.py:1015-1017): amt * #{j : tau_j == t}
+template <class Dose>
+HODE_HD float neural_dose(const Dose& ds, float t) {
+    int c = 0;
+    const int n = ds.n();
+    for (int j = 0; j < n; ++j) c += (ds.at(j) == t) ? 1 : 0;
+    return ds.amt * (float)c;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// RocheODE: 4 expert states (Disease, ImmuneReact, Immunity, Dose2) + ML latents  (model.py:515-555)
+// packed parameters: 13 scalars (named_parameters order), W [ML][D], b [ML]; staged copy appends ec50**HillPatho
+// ------------------------------------------------------------------------------------------------------------
+enum RocheIdx {
+    R_HC = 0, R_HP, R_EC50, R_EMAX, R_KDEXA, R_KDCIR, R_KDCI, R_KDISPROG, R_KID, R_KFB, R_KOFF, R_KIM, R_KEL,
+    R_NSCALAR
+};
+
+template <int D_>
+struct Roche {
+    static constexpr int D = D_;
+    static constexpr int ML = D_ - 4;
+    static constexpr int P = R_NSCALAR + ML * D_ + ML;  // packed parameter count
+    static constexpr int SP = P + 1;                     // staged: + ec50**hp
+    static constexpr int OFF_W = R_NSCALAR;
+    static constexpr int OFF_B = R_NSCALAR + ML * D_;
+    static constexpr int OFF_ECP = P;
+    static constexpr int EVALS_FLOPS = 29 + 2 * D_ * ML + ML + 3 + ML;  // SURVEY.md 8(d) algorithmic count
+
+    HODE_HD static void prepare(float* sp) { sp[OFF_ECP] = pow_hill(sp[R_EC50], sp[R_HP]); }
+
+    template <class Dose>
+    HODE_HD static void eval(const float* __restrict__ sp, float t, const Dose& ds, const float (&y)[D_],
+                             float (&dy)[D_]) {
+        const float dis = y[0], react = y[1], imm = y[2], dose2 = y[3];
+        const float kel = sp[R_KEL];
+        const float dose = roche_dose(ds, t, kel);
+        const float ip = pow_hill(imm, sp[R_HC]);
+        const float rp = pow_hill(react, sp[R_HP]);
+        dy[0] = dis * sp[R_KDISPROG] - dis * ip * sp[R_KDCI] - dis * react * sp[R_KDCIR];
+        dy[1] = dis * sp[R_KID] - react * sp[R_KOFF] + dis * react * sp[R_KFB] +
+                (rp * sp[R_EMAX]) / (sp[OFF_ECP] + rp) - dose2 * react * sp[R_KDEXA];
+        dy[2] = react * sp[R_KIM];
+        dy[3] = kel * dose - kel * dose2;
+#pragma unroll
+        for (int j = 0; j < ML; ++j) {
+            float a = sp[OFF_B + j];
+#pragma unroll
+            for (int d = 0; d < D_; ++d) a = fmaf(sp[OFF_W + j * D_ + d], y[d], a);
+            dy[4 + j] = tanh_f(a);
+        }
+    }
+
+    // gy = J^T l ; acc += d<l, f>/dtheta.  `k` (may be null) is f(t, y) if the caller already has it: its ML part is
+    // tanh(W y + b), which is all the MLP backward needs.  EG: also accumulate the 13 expert scalars.
+    template <bool EG, class Dose>
+    HODE_HD static void vjp(const float* __restrict__ sp, float t, const Dose& ds, const float (&y)[D_],
+                            const float* k, const float (&l)[D_], float (&gy)[D_], float* acc) {
+        const float dis = y[0], react = y[1], imm = y[2], dose2 = y[3];
+        const float hc = sp[R_HC], hp = sp[R_HP], em = sp[R_EMAX], ecp = sp[OFF_ECP];
+        const float kdci = sp[R_KDCI], kdcir = sp[R_KDCIR], kfb = sp[R_KFB], kdexa = sp[R_KDEXA];
+        const float kel = sp[R_KEL];
+        const float ip = pow_hill(imm, hc);
+        const float rp = pow_hill(react, hp);
+        const float den = ecp + rp;
+        const float inv_den = 1.0f / den;
+        const float l0 = l[0], l1 = l[1], l2 = l[2], l3 = l[3];
+        const float drp = dpow_hill(react, hp);
+        gy[0] = l0 * (sp[R_KDISPROG] - ip * kdci - react * kdcir) + l1 * (sp[R_KID] + react * kfb);
+        gy[1] = l0 * (-dis * kdcir) +
+                l1 * (-sp[R_KOFF] + dis * kfb + em * drp * ecp * inv_den * inv_den - dose2 * kdexa) + l2 * sp[R_KIM];
+        gy[2] = l0 * (-dis * kdci * dpow_hill(imm, hc));
+        gy[3] = l1 * (-react * kdexa) - l3 * kel;
+#pragma unroll
+        for (int d = 4; d < D_; ++d) gy[d] = 0.0f;
+        if (EG) {
+            const float ec50 = sp[R_EC50];
+            acc[R_KDISPROG] += l0 * dis;
+            acc[R_KDCI] -= l0 * dis * ip;
+            acc[R_KDCIR] -= l0 * dis * react;
+            acc[R_HC] -= l0 * dis * kdci * dpow_hill_exp(imm, ip, hc);
+            acc[R_KID] += l1 * dis;
+            acc[R_KOFF] -= l1 * react;
+            acc[R_KFB] += l1 * dis * react;
+            acc[R_EMAX] += l1 * rp * inv_den;
+            // d/d ec50 and d/d hp of  em*rp/(ec50**hp + rp)
+            acc[R_EC50] -= l1 * em * rp * dpow_hill(ec50, hp) * inv_den * inv_den;
+            acc[R_HP] += l1 * em * (dpow_hill_exp(react, rp, hp) * ecp - rp * dpow_hill_exp(ec50, ecp, hp)) * inv_den *
+                         inv_den;
+            acc[R_KDEXA] -= l1 * dose2 * react;
+            acc[R_KIM] += l2 * react;
+            const float dose = roche_dose(ds, t, kel);
+            acc[R_KEL] += l3 * (dose - dose2 + kel * roche_dose_dkel(ds, t, kel));
+        }
+#pragma unroll
+        for (int j = 0; j < ML; ++j) {
+            float s;
+            if (k != nullptr) {
+                s = k[4 + j];
+            } else {
+                float a = sp[OFF_B + j];
+#pragma unroll
+                for (int d = 0; d < D_; ++d) a = fmaf(sp[OFF_W + j * D_ + d], y[d], a);
+                s = tanh_f(a);
+            }
+            const float u = l[4 + j] * (1.0f - s * s);
+#pragma unroll
+            for (int d = 0; d < D_; ++d) {
+                gy[d] = fmaf(sp[OFF_W + j * D_ + d], u, gy[d]);
+                acc[OFF_W + j * D_ + d] = fmaf(u, y[d], acc[OFF_W + j * D_ + d]);
+            }
+            acc[OFF_B + j] += u;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// fixed-grid step functions (tde fixed_grid.py): dy such that y1 = y0 + dy.  Time arithmetic in float32.
+// ------------------------------------------------------------------------------------------------------------
+enum Method { M_EULER = 0, M_MIDPOINT = 1, M_RK4_38 = 2, M_DOPRI5 = 3 };
+
+#define HODE_ONE_THIRD ((float)(1.0 / 3.0))
+#define HODE_TWO_THIRDS ((float)(2.0 / 3.0))
+
+template <class F, int METHOD, class Dose>
+HODE_HD void fixed_step(const float* __restrict__ sp, const Dose& ds, float t0, float t1, float dt, bool perturb,
+                        const float (&y0)[F::D], float (&y1)[F::D]) {
+    constexpr int D = F::D;
+    float k1[D];
+    F::eval(sp, perturb ? t_next(t0) : t0, ds, y0, k1);
+    if (METHOD == M_EULER) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) y1[d] = y0[d] + dt * k1[d];
+    } else if (METHOD == M_MIDPOINT) {
+        const float half_dt = mul_rn(0.5f, dt);
+        float ym[D], k2[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) ym[d] = y0[d] + k1[d] * half_dt;
+        F::eval(sp, add_rn(t0, half_dt), ds, ym, k2);
+#pragma unroll
+        for (int d = 0; d < D; ++d) y1[d] = y0[d] + dt * k2[d];
+    } else {  // 3/8 rule (tde rk4_alt_step_func)
+        float yi[D], k2[D], k3[D], k4[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) yi[d] = y0[d] + dt * k1[d] * HODE_ONE_THIRD;
+        F::eval(sp, add_rn(t0, mul_rn(dt, HODE_ONE_THIRD)), ds, yi, k2);
+#pragma unroll
+        for (int d = 0; d < D; ++d) yi[d] = y0[d] + dt * (k2[d] - k1[d] * HODE_ONE_THIRD);
+        F::eval(sp, add_rn(t0, mul_rn(dt, HODE_TWO_THIRDS)), ds, yi, k3);
+#pragma unroll
+        for (int d = 0; d < D; ++d) yi[d] = y0[d] + dt * (k1[d] - k2[d] + k3[d]);
+        F::eval(sp, perturb ? t_prev(t1) : t1, ds, yi, k4);
+#pragma unroll
+        for (int d = 0; d < D; ++d) y1[d] = y0[d] + (k1[d] + 3.0f * (k2[d] + k3[d]) + k4[d]) * dt * 0.125f;
+    }
+}
+
+// reverse of one fixed-grid step:  lam0 = lam1 + (d dy/d y0)^T lam1 ; acc += (d dy/d theta)^T lam1.
+// Stages are recomputed from y0 (the tape holds only the state at the start of the step).
+template <class F, int METHOD, bool EG, class Dose>
+HODE_HD void fixed_step_vjp(const float* __restrict__ sp, const Dose& ds, float t0, float t1, float dt, bool perturb,
+                            const float (&y0)[F::D], const float (&lam1)[F::D], float (&lam0)[F::D], float* acc) {
+    constexpr int D = F::D;
+    const float ta = perturb ? t_next(t0) : t0;
+    float kb[D], g[D];
+    if (METHOD == M_EULER) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) kb[d] = dt * lam1[d];
+        F::template vjp<EG>(sp, ta, ds, y0, nullptr, kb, g, acc);
+#pragma unroll
+        for (int d = 0; d < D; ++d) lam0[d] = lam1[d] + g[d];
+    } else if (METHOD == M_MIDPOINT) {
+        const float half_dt = mul_rn(0.5f, dt);
+        float k1[D], ym[D];
+        F::eval(sp, ta, ds, y0, k1);
+#pragma unroll
+        for (int d = 0; d < D; ++d) ym[d] = y0[d] + k1[d] * half_dt;
+#pragma unroll
+        for (int d = 0; d < D; ++d) kb[d] = dt * lam1[d];
+        F::template vjp<EG>(sp, add_rn(t0, half_dt), ds, ym, nullptr, kb, g, acc);  // g = adjoint of ym
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            lam0[d] = lam1[d] + g[d];
+            kb[d] = half_dt * g[d];  // adjoint of k1
+        }
+        F::template vjp<EG>(sp, ta, ds, y0, k1, kb, g, acc);
+#pragma unroll
+        for (int d = 0; d < D; ++d) lam0[d] += g[d];
+    } else {
+        // Butcher form of the 3/8 rule: A = [[],[1/3],[-1/3,1],[1,-1,1]], b = [1/8,3/8,3/8,1/8]
+        const float tb = add_rn(t0, mul_rn(dt, HODE_ONE_THIRD));
+        const float tc = add_rn(t0, mul_rn(dt, HODE_TWO_THIRDS));
+        const float td = perturb ? t_prev(t1) : t1;
+        float k1[D], k2[D], k3[D], Y2[D], Y3[D], Y4[D];
+        F::eval(sp, ta, ds, y0, k1);
+#pragma unroll
+        for (int d = 0; d < D; ++d) Y2[d] = y0[d] + dt * k1[d] * HODE_ONE_THIRD;
+        F::eval(sp, tb, ds, Y2, k2);
+#pragma unroll
+        for (int d = 0; d < D; ++d) Y3[d] = y0[d] + dt * (k2[d] - k1[d] * HODE_ONE_THIRD);
+        F::eval(sp, tc, ds, Y3, k3);
+#pragma unroll
+        for (int d = 0; d < D; ++d) Y4[d] = y0[d] + dt * (k1[d] - k2[d] + k3[d]);
+        const float w1 = dt * 0.125f, w3 = dt * 0.375f, third = dt * HODE_ONE_THIRD;
+        float kb1[D], kb2[D];
+        // stage 4
+#pragma unroll
+        for (int d = 0; d < D; ++d) kb[d] = w1 * lam1[d];
+        F::template vjp<EG>(sp, td, ds, Y4, nullptr, kb, g, acc);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            lam0[d] = lam1[d] + g[d];
+            kb[d] = w3 * lam1[d] + dt * g[d];   // k3 adjoint
+            kb2[d] = w3 * lam1[d] - dt * g[d];  // k2 adjoint (partial)
+            kb1[d] = w1 * lam1[d] + dt * g[d];  // k1 adjoint (partial)
+        }
+        // stage 3
+        F::template vjp<EG>(sp, tc, ds, Y3, k3, kb, g, acc);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            lam0[d] += g[d];
+            kb2[d] += dt * g[d];
+            kb1[d] -= third * g[d];
+        }
+        // stage 2
+        F::template vjp<EG>(sp, tb, ds, Y2, k2, kb2, g, acc);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            lam0[d] += g[d];
+            kb1[d] += third * g[d];
+        }
+        // stage 1
+        F::template vjp<EG>(sp, ta, ds, y0, k1, kb1, g, acc);
+#pragma unroll
+        for (int d = 0; d < D; ++d) lam0[d] += g[d];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// dopri5 (tde dopri5.py tableau, cast to float32 like `tableau.to(y0.dtype)`)
+// ------------------------------------------------------------------------------------------------------------
+struct Dopri5Tab {
+    float alpha[6];
+    float beta[6][6];
+    float c_err[7];
+    float c_mid[7];
+};
+HODE_HD Dopri5Tab dopri5_tab() {
+    Dopri5Tab T = {
+        {(float)(1.0 / 5), (float)(3.0 / 10), (float)(4.0 / 5), (float)(8.0 / 9), 1.0f, 1.0f},
+        {{(float)(1.0 / 5), 0, 0, 0, 0, 0},
+         {(float)(3.0 / 40), (float)(9.0 / 40), 0, 0, 0, 0},
+         {(float)(44.0 / 45), (float)(-56.0 / 15), (float)(32.0 / 9), 0, 0, 0},
+         {(float)(19372.0 / 6561), (float)(-25360.0 / 2187), (float)(64448.0 / 6561), (float)(-212.0 / 729), 0, 0},
+         {(float)(9017.0 / 3168), (float)(-355.0 / 33), (float)(46732.0 / 5247), (float)(49.0 / 176),
+          (float)(-5103.0 / 18656), 0},
+         {(float)(35.0 / 384), 0.0f, (float)(500.0 / 1113), (float)(125.0 / 192), (float)(-2187.0 / 6784),
+          (float)(11.0 / 84)}},
+        {(float)(35.0 / 384 - 1951.0 / 21600), 0.0f, (float)(500.0 / 1113 - 22642.0 / 50085),
+         (float)(125.0 / 192 - 451.0 / 720), (float)(-2187.0 / 6784 - -12231.0 / 42400),
+         (float)(11.0 / 84 - 649.0 / 6300), (float)(-1.0 / 60.0)},
+        {(float)(6025192743.0 / 30085553152.0 / 2), 0.0f, (float)(51252292925.0 / 65400821598.0 / 2),
+         (float)(-2691868925.0 / 45128329728.0 / 2), (float)(187940372067.0 / 1594534317056.0 / 2),
+         (float)(-1776094331.0 / 19743644256.0 / 2), (float)(11237099.0 / 235043384.0 / 2)}};
+    return T;
+}
+
+// torch.max / torch.min propagate NaN
+HODE_HD double nan_max(double a, double b) { return (a != a || b != b) ? (a + b) : (a > b ? a : b); }
+HODE_HD double nan_min(double a, double b) { return (a != a || b != b) ? (a + b) : (a < b ? a : b); }
+
+// tde misc.py _optimal_step_size (order = 5): float64 arithmetic on a float32 error ratio
+HODE_HD double optimal_step(double last, float ratio, double safety, double ifactor, double dfactor) {
+    if (ratio == 0.0f) return last * ifactor;
+    if (ratio < 1.0f) dfactor = 1.0;
+    const double r = (double)ratio;
+    const double factor = nan_min(ifactor, nan_max(safety / pow(r, 0.2), dfactor));
+    return last * factor;
+}
+
+// The 7 stages of one attempt.  k[0] must hold f0 on entry.  On exit k[1..6] are filled and y1 is the last stage input.
+template <class F, class Dose>
+HODE_HD void dopri5_stages(const float* __restrict__ sp, const Dose& ds, const Dopri5Tab& T, float t0f, float dtf,
+                           float t1f, const float (&y0)[F::D], float (&k)[7][F::D], float (&y1)[F::D]) {
+    constexpr int D = F::D;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        float ti;
+        if (T.alpha[i] == 1.0f) ti = t_prev(t1f);
+        else ti = add_rn(t0f, mul_rn(T.alpha[i], dtf));
+        float yi[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            float a = 0.0f;
+#pragma unroll
+            for (int j = 0; j <= i; ++j) a = fmaf(k[j][d], mul_rn(T.beta[i][j], dtf), a);
+            yi[d] = y0[d] + a;
+        }
+        F::eval(sp, ti, ds, yi, k[i + 1]);
+        if (i == 5) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) y1[d] = yi[d];
+        }
+    }
+}
+
+}  // namespace hode

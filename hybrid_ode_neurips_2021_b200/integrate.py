@@ -1,0 +1,33 @@
+"""Hooks for running the reference's UNMODIFIED experiment code on top of this package.
+
+``install_as_torchdiffeq()`` registers a module named ``torchdiffeq`` whose ``odeint`` is the fused solver, so that
+``from torchdiffeq import odeint as dto`` (``/root/reference/model.py:10``) binds to it: the reference's own
+``RocheODE`` / ``NeuralODE`` instances are recognised by structure and integrated by the sm_100a kernels.
+``patch_model(module)`` additionally swaps the three hot-path classes of an imported reference ``model`` module for
+the drop-ins (vectorised ``set_action``).
+"""
+from __future__ import annotations
+
+import sys
+import types
+
+from . import model as _model
+from .solver import odeint
+
+
+def install_as_torchdiffeq(force: bool = False):
+    if "torchdiffeq" in sys.modules and not force and not getattr(sys.modules["torchdiffeq"], "__hode_shim__", False):
+        raise RuntimeError("a real torchdiffeq is already imported; pass force=True to shadow it")
+    m = types.ModuleType("torchdiffeq")
+    m.odeint = odeint
+    m.__hode_shim__ = True
+    sys.modules["torchdiffeq"] = m
+    return m
+
+
+def patch_model(module):
+    module.dto = odeint
+    module.RocheODE = _model.RocheODE
+    module.NeuralODE = _model.NeuralODE
+    module.RocheExpertDecoder = _model.RocheExpertDecoder
+    return module

@@ -1,0 +1,155 @@
+"""Thin tensor-level wrappers over the C ABI: allocate outputs with torch, pass raw pointers, check return codes.
+
+Every function takes the :class:`HodeLib` to call, so the same wrappers drive the CUDA library in the product and the
+test-only host emulation in ``tests/`` (CPU tensors).  No arithmetic of the hot path happens in this file.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+
+ATTEMPT_CAP_DEFAULT = 1 << 22
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream(t: torch.Tensor):
+    if t.is_cuda:
+        return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+    return None
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    assert t.dtype == torch.float32, "float32 expected, got {}".format(t.dtype)
+    return t.contiguous()
+
+
+def make_cfg(field, latent_dim, method, *, controller=L.CTRL_BATCH, perturb=False, n_dose=1, expert_grads=True,
+             rtol=1e-7, atol=1e-9, safety=0.9, ifactor=10.0, dfactor=0.2, first_step=None,
+             max_num_steps=2 ** 31 - 1, attempt_cap=ATTEMPT_CAP_DEFAULT) -> L.HodeCfg:
+    cfg = L.HodeCfg()
+    cfg.field, cfg.latent_dim, cfg.method, cfg.controller = int(field), int(latent_dim), int(method), int(controller)
+    cfg.perturb, cfg.n_dose, cfg.expert_grads = int(bool(perturb)), int(n_dose), int(bool(expert_grads))
+    cfg.rtol, cfg.atol, cfg.safety, cfg.ifactor, cfg.dfactor = float(rtol), float(atol), float(safety), float(ifactor), float(dfactor)
+    cfg.first_step = -1.0 if first_step is None else float(first_step)
+    cfg.max_num_steps, cfg.attempt_cap = int(max_num_steps), int(attempt_cap)
+    return cfg
+
+
+def dose_schedule(lib, action: torch.Tensor):
+    """``action [T, B, 1]`` (any strides) -> ``dose_amt [B]`` f32, ``dose_idx [B, T]`` i32, ``dose_count [B]`` i32."""
+    assert action.dim() == 3 and action.shape[2] == 1 and action.dtype == torch.float32
+    T, B = action.shape[0], action.shape[1]
+    dev = action.device
+    amt = torch.empty(B, dtype=torch.float32, device=dev)
+    idx = torch.empty(B, T, dtype=torch.int32, device=dev)
+    cnt = torch.empty(B, dtype=torch.int32, device=dev)
+    rc = lib.hode_dose_schedule(_ptr(action), action.stride(0), action.stride(1), T, B, _ptr(amt), _ptr(idx), _ptr(cnt),
+                                _stream(action))
+    lib.check(rc, "hode_dose_schedule")
+    return amt, idx, cnt
+
+
+@dataclass
+class Problem:
+    """Device-resident inputs shared by forward and backward of one solve."""
+
+    cfg: L.HodeCfg
+    n_groups: int
+    batch: int
+    dose_amt: torch.Tensor  # [n_traj] f32
+    dose_t: torch.Tensor  # [n_traj, stride] f32
+    params: torch.Tensor  # [n_sets, P] f32
+    pset: Optional[torch.Tensor]  # [n_groups] i32 or None
+
+    @property
+    def n_traj(self):
+        return self.n_groups * self.batch
+
+
+def fixed_fwd(lib, pb: Problem, y0, grid, t_eval, want_tape):
+    D = pb.cfg.latent_dim
+    y0 = _f32c(y0)
+    n_t, n_grid = t_eval.numel(), grid.numel()
+    h = torch.empty(n_t, pb.n_traj, D, dtype=torch.float32, device=y0.device)
+    tape = torch.empty(max(n_grid - 1, 0), pb.n_traj, D, dtype=torch.float32, device=y0.device) if want_tape else None
+    rc = lib.hode_fixed_fwd(C.byref(pb.cfg), pb.n_groups, pb.batch, _ptr(y0), _ptr(pb.dose_amt), _ptr(pb.dose_t),
+                            pb.dose_t.stride(0), _ptr(pb.params), _ptr(pb.pset), _ptr(grid), n_grid, _ptr(t_eval), n_t,
+                            _ptr(h), _ptr(tape), _stream(y0))
+    lib.check(rc, "hode_fixed_fwd")
+    return h, tape
+
+
+def fixed_bwd(lib, pb: Problem, grid, t_eval, grad_h, tape):
+    D = pb.cfg.latent_dim
+    grad_h = _f32c(grad_h)
+    dev = grad_h.device
+    gy0 = torch.empty(pb.n_traj, D, dtype=torch.float32, device=dev)
+    gp = torch.empty_like(pb.params)
+    rc = lib.hode_fixed_bwd(C.byref(pb.cfg), pb.n_groups, pb.batch, _ptr(pb.dose_amt), _ptr(pb.dose_t),
+                            pb.dose_t.stride(0), _ptr(pb.params), _ptr(pb.pset), pb.params.shape[0], _ptr(grid),
+                            grid.numel(), _ptr(t_eval), t_eval.numel(), _ptr(grad_h), _ptr(tape), _ptr(gy0), _ptr(gp),
+                            _stream(grad_h))
+    lib.check(rc, "hode_fixed_bwd")
+    return gy0, gp
+
+
+def dopri5_fwd(lib, pb: Problem, y0, t_eval64, tape_capacity):
+    """Returns ``h, stats [n_ctrl, 4] i32, (tape_t, tape_y) or None``."""
+    D = pb.cfg.latent_dim
+    y0 = _f32c(y0)
+    dev = y0.device
+    n_t = t_eval64.numel()
+    n_ctrl = pb.n_traj if pb.cfg.controller == L.CTRL_TRAJ else pb.n_groups
+    h = torch.empty(n_t, pb.n_traj, D, dtype=torch.float32, device=dev)
+    stats = torch.zeros(n_ctrl, 4, dtype=torch.int32, device=dev)
+    tape_t = tape_y = None
+    if tape_capacity:
+        tape_t = torch.empty(n_ctrl, tape_capacity, 2, dtype=torch.float64, device=dev)
+        tape_y = torch.empty(tape_capacity, pb.n_traj, D, dtype=torch.float32, device=dev)
+    rc = lib.hode_dopri5_fwd(C.byref(pb.cfg), pb.n_groups, pb.batch, _ptr(y0), _ptr(pb.dose_amt), _ptr(pb.dose_t),
+                             pb.dose_t.stride(0), _ptr(pb.params), _ptr(pb.pset), _ptr(t_eval64), n_t, _ptr(h),
+                             _ptr(tape_t), _ptr(tape_y), int(tape_capacity or 0), _ptr(stats), _stream(y0))
+    lib.check(rc, "hode_dopri5_fwd")
+    return h, stats, (tape_t, tape_y) if tape_capacity else None
+
+
+def dopri5_bwd(lib, pb: Problem, t_eval64, grad_h, tape, stats):
+    D = pb.cfg.latent_dim
+    grad_h = _f32c(grad_h)
+    dev = grad_h.device
+    tape_t, tape_y = tape
+    gy0 = torch.empty(pb.n_traj, D, dtype=torch.float32, device=dev)
+    gp = torch.empty_like(pb.params)
+    rc = lib.hode_dopri5_bwd(C.byref(pb.cfg), pb.n_groups, pb.batch, _ptr(pb.dose_amt), _ptr(pb.dose_t),
+                             pb.dose_t.stride(0), _ptr(pb.params), _ptr(pb.pset), pb.params.shape[0], _ptr(t_eval64),
+                             t_eval64.numel(), _ptr(grad_h), _ptr(tape_t), _ptr(tape_y), tape_t.shape[1], _ptr(stats),
+                             _ptr(gy0), _ptr(gp), _stream(grad_h))
+    lib.check(rc, "hode_dopri5_bwd")
+    return gy0, gp
+
+
+def decode_sse(lib, h, W, b, x, mask, n_norm, want_grads=True):
+    """Fused ``output_function`` + masked SSE.  Returns ``loss [1]`` and (grad_h, grad_W, grad_b) unit gradients."""
+    n_t, n_traj, D = h.shape
+    obs = W.shape[0]
+    assert x.shape == (n_t, n_traj, obs) and mask.shape == x.shape and x.stride() == mask.stride()
+    h, W, b = _f32c(h), _f32c(W), _f32c(b)
+    dev = h.device
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    gh = gw = gb = None
+    if want_grads:
+        gh = torch.empty_like(h)
+        gw = torch.empty(obs, D, dtype=torch.float32, device=dev)
+        gb = torch.empty(obs, dtype=torch.float32, device=dev)
+    rc = lib.hode_decode_sse(D, obs, n_t, n_traj, float(n_norm), _ptr(h), _ptr(W), _ptr(b), _ptr(x), _ptr(mask),
+                             x.stride(0), x.stride(1), x.stride(2), _ptr(loss), _ptr(gh), _ptr(gw), _ptr(gb), _stream(h))
+    lib.check(rc, "hode_decode_sse")
+    return loss, gh, gw, gb

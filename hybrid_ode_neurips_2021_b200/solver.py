@@ -1,0 +1,309 @@
+"""``odeint`` with torchdiffeq's call signature, executed by the fused sm_100a kernels of ``libhode_b200.so``.
+
+Replaces, for the reference's two vector fields, what ``from torchdiffeq import odeint as dto`` provides at
+``/root/reference/model.py:10`` (call sites ``model.py:837, 842, 1116``): the whole solve is ONE kernel launch
+(forward) plus ONE launch for the reverse sweep, exposed to autograd as a custom ``torch.autograd.Function``.
+
+Semantics kept from torchdiffeq 0.2.2: ``odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None,
+event_fn=None) -> Tensor[len(t), *y0.shape]``; default method ``dopri5``; fixed-grid options ``step_size`` /
+``perturb``; adaptive options ``first_step, safety, ifactor, dfactor, max_num_steps``; unknown option keys warn;
+solver failures raise ``AssertionError`` with torchdiffeq's messages.  Gradients are the discrete backprop through
+the accepted steps (what autograd gives through torchdiffeq's ``odeint``), with constant step sizes.
+
+There is no generic path: ``func`` must be one of the hybrid-ODE vector fields (``TypeError`` otherwise) and ``y0``
+must live on a CUDA device (``RuntimeError`` otherwise).  Extensions (all optional, in ``options``):
+``controller='batch'|'trajectory'``, ``n_groups`` (several independent odeint calls in one launch),
+``tape_capacity``, ``expert_grads``.
+"""
+from __future__ import annotations
+
+import warnings
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+__all__ = ["odeint", "SolveInfo", "last_solve_info", "fixed_grid_points"]
+
+EXPERT_NAMES = (
+    "HillCure", "HillPatho", "ec50_patho", "emax_patho", "k_dexa", "k_discure_immunereact", "k_discure_immunity",
+    "k_disprog", "k_immune_disease", "k_immune_feedback", "k_immune_off", "k_immunity", "kel",
+)
+
+
+class SolveInfo:
+    """Counters of the most recent dopri5 solve (per controller): accepted, rejected, nfe, status."""
+
+    def __init__(self, stats: Optional[torch.Tensor], n_steps_fixed: int = 0):
+        self.stats = stats
+        self.n_steps_fixed = n_steps_fixed
+
+    @property
+    def accepted(self):
+        return None if self.stats is None else self.stats[:, 0]
+
+    @property
+    def rejected(self):
+        return None if self.stats is None else self.stats[:, 1]
+
+    @property
+    def nfe(self):
+        return None if self.stats is None else self.stats[:, 2]
+
+    @property
+    def attempts_total(self) -> int:
+        if self.stats is None:
+            return self.n_steps_fixed
+        return int((self.stats[:, 0] + self.stats[:, 1]).sum())
+
+
+_last_info: Optional[SolveInfo] = None
+
+
+def last_solve_info() -> Optional[SolveInfo]:
+    return _last_info
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# recognising the vector field (ours, or the reference's own classes by structure) and packing its parameters
+# ------------------------------------------------------------------------------------------------------------------
+def _is_roche(func) -> bool:
+    return all(hasattr(func, n) for n in EXPERT_NAMES) and hasattr(func, "ml_net") and hasattr(func, "dose_at_time")
+
+
+def _is_neural(func) -> bool:
+    return (
+        hasattr(func, "ml_net") and hasattr(func, "kel") and not hasattr(func, "HillCure")
+        and isinstance(func.ml_net, torch.nn.Sequential) and len(func.ml_net) == 4
+    )
+
+
+def field_kind(func):
+    if isinstance(func, torch.nn.Module):
+        if _is_roche(func):
+            if getattr(func, "ablate", False):
+                raise NotImplementedError("RocheODE(ablate=True) has no fused kernel")
+            return L.FIELD_ROCHE
+        if _is_neural(func):
+            return L.FIELD_NEURAL
+    raise TypeError(
+        "hybrid_ode odeint only integrates the hybrid-ODE vector fields (RocheODE / NeuralODE); got {}. "
+        "There is no generic fallback.".format(type(func).__name__)
+    )
+
+
+def pack_params(func, kind) -> torch.Tensor:
+    """Differentiable packed parameter vector, layout of include/hode.h."""
+    if kind == L.FIELD_ROCHE:
+        parts = [getattr(func, n).reshape(1) for n in EXPERT_NAMES]
+        if int(func.latent_dim) > 4:
+            lin = func.ml_net[0]
+            parts += [lin.weight.reshape(-1), lin.bias.reshape(-1)]
+    else:
+        l1, l2 = func.ml_net[0], func.ml_net[2]
+        parts = [func.kel.reshape(1), l1.weight.reshape(-1), l1.bias.reshape(-1), l2.weight.reshape(-1), l2.bias.reshape(-1)]
+    return torch.cat(parts).to(torch.float32)
+
+
+def fixed_grid_points(t: torch.Tensor, step_size) -> torch.Tensor:
+    """torchdiffeq's fixed grid, computed in ``t.dtype`` exactly as ``_grid_constructor_from_step_size`` does."""
+    if step_size is None:
+        return t
+    start, end = t[0], t[-1]
+    niters = torch.ceil((end - start) / step_size + 1).item()
+    grid = torch.arange(0, niters, dtype=t.dtype, device=t.device) * step_size + start
+    grid[-1] = t[-1]
+    return grid
+
+
+_time_cache = {}
+
+
+def _times_for(t: torch.Tensor, step_size, device, fixed: bool):
+    """Device copies of the output times / solver grid, cached per (t storage, version, step_size)."""
+    key = (t.data_ptr(), t._version, t.numel(), str(t.dtype), str(t.device), step_size, str(device), fixed)
+    hit = _time_cache.get(key)
+    if hit is not None:
+        return hit
+    t_host = t.detach().cpu()
+    assert t_host.dim() == 1 and torch.is_floating_point(t_host), "t must be a one dimensional floating point Tensor"
+    if t_host.numel() > 1:
+        inc = bool((t_host[1:] > t_host[:-1]).all())
+        dec = bool((t_host[1:] < t_host[:-1]).all())
+        assert inc or dec, "t must be strictly increasing or decreasing"
+        if dec:
+            raise NotImplementedError("decreasing t (reverse-time solve) is not used by the reference and not built")
+    if fixed:
+        if t_host.dtype != torch.float32:
+            raise NotImplementedError("fixed-grid solvers do their time arithmetic in t.dtype; only float32 t is built")
+        grid = fixed_grid_points(t_host, step_size)
+        assert grid[0] == t_host[0] and grid[-1] == t_host[-1]
+        out = (t_host.to(device).contiguous(), grid.to(device).contiguous())
+    else:
+        out = (t_host.to(torch.float64).to(device).contiguous(), None)
+    if len(_time_cache) > 64:
+        _time_cache.clear()
+    _time_cache[key] = out
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+class _FixedSolve(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y0, packed, pb, grid, t_eval, need_grad):
+        lib = L.get_lib()
+        pb.params = packed.detach().reshape(pb.params_shape).contiguous()
+        h, tape = ops.fixed_fwd(lib, pb, y0.detach(), grid, t_eval, need_grad)
+        ctx.pb, ctx.grid, ctx.t_eval, ctx.tape = pb, grid, t_eval, tape
+        return h
+
+    @staticmethod
+    def backward(ctx, grad_h):
+        if ctx.tape is None:
+            raise RuntimeError("backward through a solve that was run without a tape")
+        gy0, gp = ops.fixed_bwd(L.get_lib(), ctx.pb, ctx.grid, ctx.t_eval, grad_h, ctx.tape)
+        return gy0, gp.reshape(-1), None, None, None, None
+
+
+class _Dopri5Solve(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y0, packed, pb, t_eval, tape_capacity, need_grad, holder):
+        lib = L.get_lib()
+        pb.params = packed.detach().reshape(pb.params_shape).contiguous()
+        cap = int(tape_capacity) if need_grad else 0
+        while True:
+            h, stats, tape = ops.dopri5_fwd(lib, pb, y0.detach(), t_eval, cap)
+            st = stats.cpu()
+            status = st[:, 3]
+            if need_grad and bool((status == L.SOLVE_TAPE_FULL).any()) and cap < (1 << 20):
+                cap *= 4  # the tape was too short for this solve: rerun with a larger one
+                continue
+            break
+        holder.append(st)
+        _raise_on_failure(st)
+        ctx.pb, ctx.t_eval, ctx.tape, ctx.stats = pb, t_eval, tape, stats
+        return h
+
+    @staticmethod
+    def backward(ctx, grad_h):
+        if ctx.tape is None:
+            raise RuntimeError("backward through a solve that was run without a tape")
+        gy0, gp = ops.dopri5_bwd(L.get_lib(), ctx.pb, ctx.t_eval, grad_h, ctx.tape, ctx.stats)
+        return gy0, gp.reshape(-1), None, None, None, None, None
+
+
+def _raise_on_failure(st: torch.Tensor):
+    status = st[:, 3]
+    if bool((status == L.SOLVE_OK).all()):
+        return
+    bad = int(torch.nonzero(status != L.SOLVE_OK)[0])
+    code = int(status[bad])
+    # torchdiffeq raises these with `assert` (rk_common.py); callers such as training_utils.py:45 rely on the type
+    if code == L.SOLVE_DT_UNDERFLOW:
+        raise AssertionError("underflow in dt (controller {})".format(bad))
+    if code == L.SOLVE_NONFINITE:
+        raise AssertionError("non-finite values in state `y` (controller {})".format(bad))
+    if code == L.SOLVE_MAX_STEPS:
+        raise AssertionError("max_num_steps exceeded (controller {})".format(bad))
+    raise RuntimeError("dopri5 tape capacity exceeded (controller {})".format(bad))
+
+
+_FIXED_KEYS = {"step_size", "perturb", "grid_constructor", "interp"}
+_ADAPTIVE_KEYS = {"first_step", "step_t", "jump_t", "safety", "ifactor", "dfactor", "max_num_steps", "dtype", "norm"}
+_OUR_KEYS = {"controller", "n_groups", "tape_capacity", "expert_grads", "attempt_cap", "param_sets", "param_set_of_group"}
+_NAMES = {"euler": "Euler", "midpoint": "Midpoint", "rk4": "RK4", "dopri5": "Dopri5Solver"}
+
+
+def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None):
+    global _last_info
+    if event_fn is not None:
+        raise NotImplementedError("event_fn is not used by the reference and has no fused kernel")
+    kind = field_kind(func)
+    if not isinstance(y0, torch.Tensor):
+        raise NotImplementedError("tuple states are not used by the reference and have no fused kernel")
+    if not y0.is_cuda:
+        raise RuntimeError(
+            "hybrid_ode odeint runs on CUDA (sm_100a) only; y0 is on {}. There is no CPU fallback.".format(y0.device)
+        )
+    if y0.dtype != torch.float32:
+        raise NotImplementedError("only float32 states (the reference's DTYPE, global_config.py:3) have kernels")
+    assert y0.dim() == 2, "y0 must be [batch, latent_dim]"
+    for name, tol in (("rtol", rtol), ("atol", atol)):
+        if isinstance(tol, torch.Tensor):
+            assert not tol.requires_grad, name + " cannot require gradient"
+    method = "dopri5" if method is None else method
+    if method not in L.METHODS:
+        raise ValueError('Invalid method "{}". Must be one of {}'.format(method, "{" + ", ".join(L.METHODS) + "}"))
+    options = {} if options is None else dict(options)
+    fixed = method != "dopri5"
+    known = (_FIXED_KEYS if fixed else _ADAPTIVE_KEYS) | _OUR_KEYS
+    unused = {k: v for k, v in options.items() if k not in known}
+    if unused:
+        warnings.warn("{}: Unexpected arguments {}".format(_NAMES[method], unused))
+
+    B, D = y0.shape
+    if D != int(func.latent_dim):
+        raise ValueError("y0 has {} columns but the vector field has latent_dim {}".format(D, func.latent_dim))
+    n_groups = int(options.get("n_groups", 1))
+    if n_groups < 1 or B % n_groups != 0:
+        raise ValueError("n_groups must divide the batch")
+    batch = B // n_groups
+    if func.dosage is None or func.times is None:
+        raise RuntimeError("set_action must be called before integrating (model.py:1113)")
+    dose_amt = func.dosage.detach().to(device=y0.device, dtype=torch.float32).contiguous()
+    dose_t = getattr(func, "_dose_t_f32", None)
+    if dose_t is None or dose_t.shape[0] != B:
+        dose_t = func.times.detach().to(device=y0.device, dtype=torch.float32).contiguous()
+    if dose_amt.shape[0] != B or dose_t.shape[0] != B:
+        raise RuntimeError("dose schedule has {} patients but y0 has {}".format(dose_amt.shape[0], B))
+    n_dose = dose_t.shape[1] if dose_t.dim() == 2 else 0
+
+    ctrl_name = options.get("controller", "batch")
+    if ctrl_name not in ("batch", "trajectory"):
+        raise ValueError("controller must be 'batch' or 'trajectory'")
+    need_grad = torch.is_grad_enabled() and (
+        y0.requires_grad or any(p.requires_grad for p in func.parameters())
+    )
+    cfg = ops.make_cfg(
+        kind, D, L.METHODS[method],
+        controller=L.CTRL_TRAJ if ctrl_name == "trajectory" else L.CTRL_BATCH,
+        perturb=bool(options.get("perturb", False)), n_dose=n_dose,
+        expert_grads=bool(options.get("expert_grads", True)),
+        rtol=float(rtol), atol=float(atol), safety=float(options.get("safety", 0.9)),
+        ifactor=float(options.get("ifactor", 10.0)), dfactor=float(options.get("dfactor", 0.2)),
+        first_step=options.get("first_step", None), max_num_steps=int(options.get("max_num_steps", 2 ** 31 - 1)),
+        attempt_cap=int(options.get("attempt_cap", ops.ATTEMPT_CAP_DEFAULT)),
+    )
+    packed = pack_params(func, kind)
+    pb = ops.Problem(cfg, n_groups, batch, dose_amt, dose_t, None, None)
+    pb.params_shape = (1, packed.numel())
+
+    if fixed:
+        if options.get("grid_constructor") is not None:
+            raise NotImplementedError("grid_constructor is not used by the reference; pass step_size")
+        if options.get("interp", "linear") != "linear":
+            raise ValueError("Unknown interpolation method {}".format(options.get("interp")))
+        t_dev, grid = _times_for(t, options.get("step_size"), y0.device, True)
+        h = _FixedSolve.apply(y0, packed, pb, grid, t_dev, need_grad)
+        _last_info = SolveInfo(None, (grid.numel() - 1) * B)
+        return h
+
+    for key in ("step_t", "jump_t"):
+        v = options.get(key)
+        if v is not None and len(v) > 0:
+            raise NotImplementedError("dopri5 option {} has no fused kernel (the reference only passes it to fixed-grid "
+                                      "solvers, which ignore it)".format(key))
+    if ctrl_name == "batch":
+        mb = int(L.get_lib().hode_dopri5_max_batch(cfg))
+        if batch > mb:
+            raise NotImplementedError(
+                "batch-coupled dopri5 integrates one group per CTA (<= {} trajectories); got {}. Use "
+                "options={{'n_groups': g}} or options={{'controller': 'trajectory'}}.".format(mb, batch)
+            )
+    t_dev, _ = _times_for(t, None, y0.device, False)
+    holder = []
+    h = _Dopri5Solve.apply(y0, packed, pb, t_dev, int(options.get("tape_capacity", 1024)), need_grad, holder)
+    _last_info = SolveInfo(holder[0] if holder else None)
+    return h

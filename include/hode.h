@@ -1,0 +1,155 @@
+/*
+ * hode.h -- C ABI of libhode_b200.so: the B200 (sm_100a) implementation of the hybrid-ODE hot path of
+ * ZhaozhiQIAN/Hybrid-ODE-NeurIPS-2021.
+ *
+ * The reference is pure Python; the interface each entry point replaces is cited as reference file:line
+ * (paths relative to the reference root; "torchdiffeq" = the un-vendored torchdiffeq==0.2.2 of requirements.txt:9).
+ * The Python binding a maintainer adds on the reference side is a ctypes stub, shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer on the current CUDA device unless named host_*; the library never
+ *    allocates, frees or retains memory; work is enqueued on `stream` (a cudaStream_t passed as void*) and the call
+ *    returns without synchronising;
+ *  - return value: HODE_OK, or a negative hode_status; hode_last_error() gives a per-thread message;
+ *    solver failures (torchdiffeq's assertions) are reported per controller group in `stats`, not by return value;
+ *  - trajectories are independent patients.  n_traj = n_groups * batch.  A "group" is what ONE reference odeint
+ *    call integrates (model.py:1116): it shares a parameter set and -- for the batch-coupled dopri5 controller --
+ *    one step-size sequence.  Trajectory index = group * batch + b.
+ *  - layouts are the reference's own: y0 [n_traj, D] row-major (model.py:1112 `init`), solution h
+ *    [n_t, n_traj, D] time-major (what torchdiffeq.odeint returns), observations x/mask [n_t, n_traj, obs]
+ *    (model.py:1151-1153) with arbitrary element strides.
+ *  - packed parameter vector of one parameter set (float32, length hode_param_count()):
+ *      ROCHE : 13 expert scalars in named_parameters() order (model.py:468-481: HillCure, HillPatho, ec50_patho,
+ *              emax_patho, k_dexa, k_discure_immunereact, k_discure_immunity, k_disprog, k_immune_disease,
+ *              k_immune_feedback, k_immune_off, k_immunity, kel), then ml_net[0].weight [D-4, D] row-major, then
+ *              ml_net[0].bias [D-4]  (model.py:488)
+ *      NEURAL: kel, ml_net[0].weight [10D, D+1], ml_net[0].bias [10D], ml_net[2].weight [D, 10D],
+ *              ml_net[2].bias [D]  (model.py:989-996)
+ */
+#ifndef HODE_H_
+#define HODE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HODE_ABI_VERSION 1
+
+typedef enum hode_status {
+    HODE_OK = 0,
+    HODE_ERR_ARG = -1,         /* bad argument (null pointer, negative size, ...) */
+    HODE_ERR_UNSUPPORTED = -2, /* latent_dim / method / field combination not compiled in */
+    HODE_ERR_CUDA = -3,        /* CUDA launch or runtime error */
+    HODE_ERR_NO_DEVICE = -4    /* no sm_100 device / no kernel image for this device */
+} hode_status;
+
+/* vector field: model.py:446-555 (RocheODE, ablate=False) / model.py:969-1026 (NeuralODE) */
+typedef enum hode_field { HODE_FIELD_ROCHE = 0, HODE_FIELD_NEURAL = 1 } hode_field;
+
+/* torchdiffeq SOLVERS keys used by the reference: 'euler', 'midpoint', 'rk4' (= 3/8 rule), 'dopri5' */
+typedef enum hode_method { HODE_EULER = 0, HODE_MIDPOINT = 1, HODE_RK4_38 = 2, HODE_DOPRI5 = 3 } hode_method;
+
+/* dopri5 step-size control.  BATCH = torchdiffeq semantics: one RMS error norm, one dt, one accept/reject per
+ * group (per odeint call).  TRAJ = every trajectory is its own controller (== B calls of batch 1). */
+typedef enum hode_controller { HODE_CTRL_BATCH = 0, HODE_CTRL_TRAJ = 1 } hode_controller;
+
+/* per-group solver status (stats[g].status); 1..3 are torchdiffeq's assertion failures */
+typedef enum hode_solve_status {
+    HODE_SOLVE_OK = 0,
+    HODE_SOLVE_DT_UNDERFLOW = 1, /* 'underflow in dt {}' */
+    HODE_SOLVE_NONFINITE = 2,    /* 'non-finite values in state `y`: {}' */
+    HODE_SOLVE_MAX_STEPS = 3,    /* 'max_num_steps exceeded ({}>={})' */
+    HODE_SOLVE_TAPE_FULL = 4     /* accepted steps exceeded tape_capacity (retry with a larger tape) */
+} hode_solve_status;
+
+typedef struct hode_stats {
+    int32_t accepted; /* accepted steps (== tape length) */
+    int32_t rejected; /* rejected attempts */
+    int32_t nfe;      /* vector-field evaluations, torchdiffeq accounting: 2 + 6*(accepted+rejected) */
+    int32_t status;   /* hode_solve_status */
+} hode_stats;
+
+typedef struct hode_cfg {
+    int32_t field;        /* hode_field */
+    int32_t latent_dim;   /* D */
+    int32_t method;       /* hode_method */
+    int32_t controller;   /* hode_controller (dopri5 only) */
+    int32_t perturb;      /* fixed-grid option 'perturb' (model.py:825): first/last stage times moved by one ulp */
+    int32_t n_dose;       /* doses per patient, columns of dose_t (model.py:507 `times [B, n_dose]`) */
+    int32_t expert_grads; /* backward also accumulates the 13 expert-scalar gradients (Roche) */
+    int32_t reserved0;
+    double rtol, atol;                /* model.py:1079-1080 */
+    double safety, ifactor, dfactor;  /* torchdiffeq defaults 0.9, 10, 0.2 */
+    double first_step;                /* <= 0: automatic selection (torchdiffeq `_select_initial_step`) */
+    int64_t max_num_steps;            /* torchdiffeq default 2**31-1, counted per output interval */
+    int64_t attempt_cap;              /* hard cap on attempts per group for the whole solve (GPU watchdog) */
+} hode_cfg;
+
+/* ---- introspection ------------------------------------------------------------------------------------- */
+int32_t hode_abi_version(void);
+const char* hode_last_error(void);
+/* number of floats in one packed parameter set; <0 on unsupported cfg */
+int64_t hode_param_count(const hode_cfg* cfg);
+/* 1 if (field, latent_dim, method) has a compiled kernel */
+int32_t hode_supported(const hode_cfg* cfg);
+
+/* ---- dose schedule: RocheODE.set_action / NeuralODE.set_action (model.py:495-507, 1001-1013) -------------
+ * action[t, b] at action + t*stride_t + b*stride_b (element strides, float32).
+ * dose_amt[b] = max_t action[t,b];  dose_idx[b, 0..count-1] = indices t with action != 0, ascending, row stride T;
+ * dose_count[b] = number of non-zero actions.  (The host checks that all counts are equal, like torch.stack.) */
+int32_t hode_dose_schedule(const float* action, int64_t stride_t, int64_t stride_b, int32_t T, int64_t n_traj,
+                           float* dose_amt, int32_t* dose_idx, int32_t* dose_count, void* stream);
+
+/* ---- fixed-grid solvers: torchdiffeq FixedGridODESolver.integrate + Euler/Midpoint/RK4 step functions --------
+ * (called from model.py:837, 842, 1116 with method in {'euler','midpoint','rk4'}).
+ * grid[n_grid]: the solver grid in float32 (host-built exactly like torchdiffeq: `t` itself or
+ * arange(niters)*step_size + t[0] with the last point clamped); t_eval[n_t]: output times, float32.
+ * dose_t [n_traj, dose_t_stride] float32 dose times (only the first cfg->n_dose columns are read).
+ * params [n_param_sets, P]; param_set_of_group[n_groups] (NULL: every group uses set 0).
+ * tape (NULL for forward-only): [n_grid-1, n_traj, D] float32, state at the start of every grid step.       */
+size_t hode_fixed_tape_bytes(const hode_cfg* cfg, int64_t n_traj, int32_t n_grid);
+int32_t hode_fixed_fwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* y0, const float* dose_amt,
+                       const float* dose_t, int64_t dose_t_stride, const float* params,
+                       const int32_t* param_set_of_group, const float* grid, int32_t n_grid, const float* t_eval,
+                       int32_t n_t, float* h_out, float* tape, void* stream);
+/* backward (autograd through every step, training_utils.py:50 `loss.backward()`):
+ * grad_h [n_t, n_traj, D] -> grad_y0 [n_traj, D] (overwritten), grad_params [n_param_sets, P] (overwritten). */
+int32_t hode_fixed_bwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,
+                       const float* dose_t, int64_t dose_t_stride, const float* params,
+                       const int32_t* param_set_of_group, int32_t n_param_sets, const float* grid, int32_t n_grid,
+                       const float* t_eval, int32_t n_t, const float* grad_h, const float* tape, float* grad_y0,
+                       float* grad_params, void* stream);
+
+/* ---- dopri5: torchdiffeq Dopri5Solver (RKAdaptiveStepsizeODESolver.integrate), model.py:1116 ------------------
+ * t_eval is float64 (torchdiffeq casts `t` to float64).  controller BATCH: one controller per group
+ * (batch <= hode_dopri5_max_batch()); TRAJ: one per trajectory.  n_ctrl = n_groups (BATCH) or n_traj (TRAJ).
+ * tape (NULL for forward-only): accepted steps, capacity tape_capacity per controller:
+ *     tape_t  [n_ctrl, tape_capacity, 2] float64 (t0, dt);  tape_y [tape_capacity, n_traj, D] float32.
+ * stats [n_ctrl].                                                                                            */
+int64_t hode_dopri5_max_batch(const hode_cfg* cfg);
+int32_t hode_dopri5_fwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* y0,
+                        const float* dose_amt, const float* dose_t, int64_t dose_t_stride, const float* params,
+                        const int32_t* param_set_of_group, const double* t_eval, int32_t n_t, float* h_out,
+                        double* tape_t, float* tape_y, int32_t tape_capacity, hode_stats* stats, void* stream);
+int32_t hode_dopri5_bwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,
+                        const float* dose_t, int64_t dose_t_stride, const float* params,
+                        const int32_t* param_set_of_group, int32_t n_param_sets, const double* t_eval, int32_t n_t,
+                        const float* grad_h, const double* tape_t, const float* tape_y, int32_t tape_capacity,
+                        const hode_stats* stats, float* grad_y0, float* grad_params, void* stream);
+
+/* ---- decode + masked SSE: output_function (model.py:1097-1100, 1120) and the likelihood of
+ * VariationalInference.loss (model.py:1179): loss = sum_{t,b,o} (x - (W h + b))^2 mask / n_norm.
+ * x, mask: element strides (st, sb, so).  One pass also produces the unit gradients:
+ *   grad_h [n_t, n_traj, D], grad_w [obs, D], grad_b [obs]  (d loss / d .), any of which may be NULL.
+ * loss: one float32 (overwritten).  W [obs, D] row-major, b [obs]. */
+int32_t hode_decode_sse(int32_t D, int32_t obs, int32_t n_t, int64_t n_traj, double n_norm, const float* h,
+                        const float* W, const float* b, const float* x, const float* mask, int64_t st, int64_t sb,
+                        int64_t so, float* loss, float* grad_h, float* grad_w, float* grad_b, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HODE_H_ */

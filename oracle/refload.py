@@ -1,0 +1,56 @@
+"""Import the reference's own ``model.py`` UNMODIFIED, with the two missing third-party modules injected.
+
+TEST INFRASTRUCTURE ONLY.  Works only where ``/root/reference`` exists (this container, never the GPU box).
+``model.py:10`` needs ``torchdiffeq`` and ``training_utils.py:4`` needs ``properscoring``; neither is installable
+offline, so ``oracle.odeint`` stands in for the former and a minimal ``crps_ensemble`` for the latter.
+"""
+from __future__ import annotations
+
+import importlib
+import os
+import sys
+import types
+
+REFERENCE_ROOT = os.environ.get("HODE_REFERENCE_ROOT", "/root/reference")
+
+
+def available() -> bool:
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "model.py"))
+
+
+def _crps_ensemble(observations, forecasts):
+    """CRPS of an ensemble forecast, ``E|X - y| - 0.5 E|X - X'|`` (what properscoring.crps_ensemble computes)."""
+    import numpy as np
+
+    obs = np.asarray(observations, dtype=float)
+    fc = np.asarray(forecasts, dtype=float)
+    if fc.ndim == obs.ndim:
+        fc = fc[..., None]
+    term1 = np.abs(fc - obs[..., None]).mean(axis=-1)
+    term2 = np.abs(fc[..., :, None] - fc[..., None, :]).mean(axis=(-2, -1))
+    return term1 - 0.5 * term2
+
+
+def install_shims():
+    from . import odeint as oi
+
+    if "torchdiffeq" not in sys.modules:
+        m = types.ModuleType("torchdiffeq")
+        m.odeint = oi.odeint
+        m.__oracle_shim__ = True
+        sys.modules["torchdiffeq"] = m
+    if "properscoring" not in sys.modules:
+        p = types.ModuleType("properscoring")
+        p.crps_ensemble = _crps_ensemble
+        p.__oracle_shim__ = True
+        sys.modules["properscoring"] = p
+
+
+def load(name: str = "model"):
+    """Return the reference module ``name`` (``model``, ``training_utils``, ``dataloader``, ``sim_config`` ...)."""
+    if not available():
+        raise FileNotFoundError("reference tree not present at " + REFERENCE_ROOT)
+    install_shims()
+    if REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, REFERENCE_ROOT)
+    return importlib.import_module(name)

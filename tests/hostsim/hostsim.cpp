@@ -1,0 +1,213 @@
+// hostsim.cpp -- TEST-ONLY thread emulation of the solver kernels (never loaded by the product package).
+//
+// This container has no GPU, so the per-trajectory bodies of csrc/hode_bodies.cuh (the exact source the sm_100a
+// kernels are built from) are also compiled here as plain C++ and driven by host loops / std::thread groups.  It lets
+// tests/test_hostsim_*.py check the hand-derived reverse sweeps, tape logic and dense-output emission against the
+// oracle without a GPU.  It exports the solver subset of the include/hode.h ABI, taking HOST pointers.
+#define HODE_HOSTSIM 1
+#include <barrier>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../../hybrid_ode_neurips_2021_b200/csrc/hode_bodies.cuh"
+
+using namespace hode;
+
+namespace {
+struct CommNone {
+    void sum2(float&, float&) {}
+};
+struct CommThreads {
+    std::barrier<>* bar;
+    float* buf;
+    int n, tid;
+    void sum2(float& a, float& b) {
+        buf[2 * tid] = a;
+        buf[2 * tid + 1] = b;
+        bar->arrive_and_wait();
+        float sa = 0.f, sb = 0.f;
+        for (int i = 0; i < n; ++i) { sa += buf[2 * i]; sb += buf[2 * i + 1]; }
+        bar->arrive_and_wait();
+        a = sa; b = sb;
+    }
+};
+
+void fill(SolveArgs& a, const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,
+          const float* dose_t, int64_t stride, const float* params, const int32_t* pset) {
+    memset(&a, 0, sizeof(a));
+    a.n_groups = n_groups; a.batch = batch; a.dose_amt = dose_amt; a.dose_t = dose_t; a.dose_t_stride = stride;
+    a.n_dose = cfg->n_dose; a.params = params; a.pset = pset; a.perturb = cfg->perturb;
+    a.rtol_f = (float)cfg->rtol; a.atol_f = (float)cfg->atol; a.safety = cfg->safety; a.ifactor = cfg->ifactor;
+    a.dfactor = cfg->dfactor; a.first_step = cfg->first_step; a.max_num_steps = cfg->max_num_steps;
+    a.attempt_cap = cfg->attempt_cap; a.per_traj = cfg->controller == HODE_CTRL_TRAJ;
+}
+
+template <class F>
+std::vector<float> stage(const SolveArgs& a, int64_t g) {
+    std::vector<float> sp(F::SP);
+    const int set = a.pset ? a.pset[g] : 0;
+    for (int i = 0; i < F::P; ++i) sp[i] = a.params[(int64_t)set * F::P + i];
+    F::prepare(sp.data());
+    return sp;
+}
+DoseMem dose(const SolveArgs& a, int64_t idx) {
+    DoseMem d; d.amt = a.dose_amt[idx]; d.tau = a.dose_t + idx * a.dose_t_stride; d.nd = a.n_dose; return d;
+}
+
+template <class F, int M>
+void fixed_fwd(const SolveArgs& a) {
+    for (int64_t g = 0; g < a.n_groups; ++g) {
+        auto sp = stage<F>(a, g);
+        for (int64_t b = 0; b < a.batch; ++b) { const int64_t idx = g * a.batch + b; fixed_fwd_traj<F, M>(a, sp.data(), dose(a, idx), idx); }
+    }
+}
+template <class F, int M>
+void fixed_bwd(const SolveArgs& a, bool eg) {
+    for (int64_t g = 0; g < a.n_groups; ++g) {
+        auto sp = stage<F>(a, g);
+        std::vector<float> acc(F::P, 0.f);
+        for (int64_t b = 0; b < a.batch; ++b) {
+            const int64_t idx = g * a.batch + b;
+            if (eg) fixed_bwd_traj<F, M, true>(a, sp.data(), dose(a, idx), idx, acc.data());
+            else fixed_bwd_traj<F, M, false>(a, sp.data(), dose(a, idx), idx, acc.data());
+        }
+        const int set = a.pset ? a.pset[g] : 0;
+        for (int i = 0; i < F::P; ++i) a.grad_params[(int64_t)set * F::P + i] += acc[i];
+    }
+}
+template <class F>
+void dopri5_fwd(const SolveArgs& a) {
+    for (int64_t g = 0; g < a.n_groups; ++g) {
+        auto sp = stage<F>(a, g);
+        if (a.per_traj) {
+            for (int64_t b = 0; b < a.batch; ++b) {
+                const int64_t idx = g * a.batch + b;
+                CommNone cm;
+                dopri5_fwd_traj<F>(a, cm, sp.data(), dose(a, idx), idx, true, idx, true, (float)F::D);
+            }
+        } else {
+            const int n = (int)a.batch;
+            std::barrier<> bar(n);
+            std::vector<float> buf(2 * n);
+            std::vector<std::thread> th;
+            for (int b = 0; b < n; ++b)
+                th.emplace_back([&, b]() {
+                    const int64_t idx = g * a.batch + b;
+                    CommThreads cm{&bar, buf.data(), n, b};
+                    dopri5_fwd_traj<F>(a, cm, sp.data(), dose(a, idx), idx, true, g, b == 0, (float)(a.batch * F::D));
+                });
+            for (auto& t : th) t.join();
+        }
+    }
+}
+template <class F>
+void dopri5_bwd(const SolveArgs& a, bool eg) {
+    for (int64_t g = 0; g < a.n_groups; ++g) {
+        auto sp = stage<F>(a, g);
+        std::vector<float> acc(F::P, 0.f);
+        for (int64_t b = 0; b < a.batch; ++b) {
+            const int64_t idx = g * a.batch + b;
+            const int64_t ctrl = a.per_traj ? idx : g;
+            if (eg) dopri5_bwd_traj<F, true>(a, sp.data(), dose(a, idx), idx, ctrl, acc.data());
+            else dopri5_bwd_traj<F, false>(a, sp.data(), dose(a, idx), idx, ctrl, acc.data());
+        }
+        const int set = a.pset ? a.pset[g] : 0;
+        for (int i = 0; i < F::P; ++i) a.grad_params[(int64_t)set * F::P + i] += acc[i];
+    }
+}
+
+enum Op { FF, FB, DF, DB };
+template <class F>
+int run(Op op, const hode_cfg& cfg, const SolveArgs& a) {
+    const bool eg = cfg.expert_grads != 0;
+    switch (op) {
+        case FF:
+            if (cfg.method == HODE_EULER) fixed_fwd<F, M_EULER>(a);
+            else if (cfg.method == HODE_MIDPOINT) fixed_fwd<F, M_MIDPOINT>(a);
+            else fixed_fwd<F, M_RK4_38>(a);
+            return 0;
+        case FB:
+            if (cfg.method == HODE_EULER) fixed_bwd<F, M_EULER>(a, eg);
+            else if (cfg.method == HODE_MIDPOINT) fixed_bwd<F, M_MIDPOINT>(a, eg);
+            else fixed_bwd<F, M_RK4_38>(a, eg);
+            return 0;
+        case DF: dopri5_fwd<F>(a); return 0;
+        case DB: dopri5_bwd<F>(a, eg); return 0;
+    }
+    return -1;
+}
+int dispatch(Op op, const hode_cfg& cfg, const SolveArgs& a) {
+    if (cfg.field == HODE_FIELD_ROCHE) {
+        switch (cfg.latent_dim) {
+            case 4: return run<Roche<4>>(op, cfg, a);
+            case 6: return run<Roche<6>>(op, cfg, a);
+            case 8: return run<Roche<8>>(op, cfg, a);
+            case 12: return run<Roche<12>>(op, cfg, a);
+        }
+    }
+#ifdef HODE_HAVE_NEURAL
+    if (cfg.field == HODE_FIELD_NEURAL) {
+        switch (cfg.latent_dim) {
+            case 4: return run<Neural<4>>(op, cfg, a);
+            case 6: return run<Neural<6>>(op, cfg, a);
+            case 8: return run<Neural<8>>(op, cfg, a);
+            case 12: return run<Neural<12>>(op, cfg, a);
+        }
+    }
+#endif
+    return HODE_ERR_UNSUPPORTED;
+}
+int64_t pcount(const hode_cfg* cfg) {
+    const int64_t d = cfg->latent_dim;
+    if (cfg->field == HODE_FIELD_ROCHE) return 13 + (d - 4) * d + (d - 4);
+    return 1 + 10 * d * (d + 1) + 10 * d + d * 10 * d + d;
+}
+}  // namespace
+
+extern "C" {
+int32_t hode_abi_version(void) { return HODE_ABI_VERSION; }
+const char* hode_last_error(void) { return "hostsim"; }
+int64_t hode_param_count(const hode_cfg* cfg) { return pcount(cfg); }
+int64_t hode_dopri5_max_batch(const hode_cfg*) { return 256; }
+
+int32_t hode_fixed_fwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* y0, const float* dose_amt,
+                       const float* dose_t, int64_t dose_t_stride, const float* params, const int32_t* pset,
+                       const float* grid, int32_t n_grid, const float* t_eval, int32_t n_t, float* h_out, float* tape,
+                       void*) {
+    SolveArgs a; fill(a, cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, pset);
+    a.y0 = y0; a.grid = grid; a.n_grid = n_grid; a.t_eval_f = t_eval; a.n_t = n_t; a.h_out = h_out; a.tape_y = tape;
+    return dispatch(FF, *cfg, a);
+}
+int32_t hode_fixed_bwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,
+                       const float* dose_t, int64_t dose_t_stride, const float* params, const int32_t* pset,
+                       int32_t n_param_sets, const float* grid, int32_t n_grid, const float* t_eval, int32_t n_t,
+                       const float* grad_h, const float* tape, float* grad_y0, float* grad_params, void*) {
+    SolveArgs a; fill(a, cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, pset);
+    a.n_param_sets = n_param_sets; a.grid = grid; a.n_grid = n_grid; a.t_eval_f = t_eval; a.n_t = n_t;
+    a.grad_h = grad_h; a.tape_y = const_cast<float*>(tape); a.grad_y0 = grad_y0; a.grad_params = grad_params;
+    memset(grad_params, 0, sizeof(float) * pcount(cfg) * n_param_sets);
+    return dispatch(FB, *cfg, a);
+}
+int32_t hode_dopri5_fwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* y0, const float* dose_amt,
+                        const float* dose_t, int64_t dose_t_stride, const float* params, const int32_t* pset,
+                        const double* t_eval, int32_t n_t, float* h_out, double* tape_t, float* tape_y,
+                        int32_t tape_capacity, hode_stats* stats, void*) {
+    SolveArgs a; fill(a, cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, pset);
+    a.y0 = y0; a.t_eval_d = t_eval; a.n_t = n_t; a.h_out = h_out; a.tape_t = tape_t; a.tape_y = tape_y;
+    a.tape_cap = tape_capacity; a.stats = stats;
+    return dispatch(DF, *cfg, a);
+}
+int32_t hode_dopri5_bwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,
+                        const float* dose_t, int64_t dose_t_stride, const float* params, const int32_t* pset,
+                        int32_t n_param_sets, const double* t_eval, int32_t n_t, const float* grad_h,
+                        const double* tape_t, const float* tape_y, int32_t tape_capacity, const hode_stats* stats,
+                        float* grad_y0, float* grad_params, void*) {
+    SolveArgs a; fill(a, cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, pset);
+    a.n_param_sets = n_param_sets; a.t_eval_d = t_eval; a.n_t = n_t; a.grad_h = grad_h;
+    a.tape_t = const_cast<double*>(tape_t); a.tape_y = const_cast<float*>(tape_y); a.tape_cap = tape_capacity;
+    a.stats = const_cast<hode_stats*>(stats); a.grad_y0 = grad_y0; a.grad_params = grad_params;
+    memset(grad_params, 0, sizeof(float) * pcount(cfg) * n_param_sets);
+    return dispatch(DB, *cfg, a);
+}
+}
