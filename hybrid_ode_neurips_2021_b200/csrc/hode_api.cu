@@ -49,6 +49,14 @@ static int dispatch(Op op, const hode_cfg& cfg, const SolveArgs& a, cudaStream_t
             case 12: rc = run<Roche<12>>(op, cfg, a, st); break;
             default: return fail(HODE_ERR_UNSUPPORTED, "RocheODE latent_dim %s%lld is not compiled in (4, 6, 8, 12)", "", cfg.latent_dim);
         }
+    } else if (cfg.field == HODE_FIELD_NEURAL) {
+        switch (cfg.latent_dim) {
+            case 4: rc = run<Neural<4>>(op, cfg, a, st); break;
+            case 6: rc = run<Neural<6>>(op, cfg, a, st); break;
+            case 8: rc = run<Neural<8>>(op, cfg, a, st); break;
+            case 12: rc = run<Neural<12>>(op, cfg, a, st); break;
+            default: return fail(HODE_ERR_UNSUPPORTED, "NeuralODE latent_dim %s%lld is not compiled in (4, 6, 8, 12)", "", cfg.latent_dim);
+        }
     } else {
         return fail(HODE_ERR_UNSUPPORTED, "field %s%lld is not compiled in", "", cfg.field);
     }
@@ -76,7 +84,7 @@ int64_t hode_param_count(const hode_cfg* cfg) {
 int32_t hode_supported(const hode_cfg* cfg) {
     if (!cfg) return 0;
     if (cfg->method < HODE_EULER || cfg->method > HODE_DOPRI5) return 0;
-    if (cfg->field == HODE_FIELD_ROCHE) return roche_dim_ok(cfg->latent_dim) ? 1 : 0;
+    if (cfg->field == HODE_FIELD_ROCHE || cfg->field == HODE_FIELD_NEURAL) return roche_dim_ok(cfg->latent_dim) ? 1 : 0;
     return 0;
 }
 

@@ -150,6 +150,12 @@ struct Roche {
     static constexpr int OFF_ECP = P;
     static constexpr int EVALS_FLOPS = 29 + 2 * D_ * ML + ML + 3 + ML;  // SURVEY.md 8(d) algorithmic count
 
+    static constexpr bool kAccInRegs = true;             // per-thread gradient accumulators fit in registers
+
+    // cooperative copy of one packed parameter set into the staged layout (thread `tid` of `nthr`)
+    HODE_HD static void stage(const float* __restrict__ src, float* sp, int tid, int nthr) {
+        for (int i = tid; i < P; i += nthr) sp[i] = src[i];
+    }
     HODE_HD static void prepare(float* sp) { sp[OFF_ECP] = pow_hill(sp[R_EC50], sp[R_HP]); }
 
     template <class Dose>
@@ -233,6 +239,103 @@ struct Roche {
                 acc[OFF_W + j * D_ + d] = fmaf(u, y[d], acc[OFF_W + j * D_ + d]);
             }
             acc[OFF_B + j] += u;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// NeuralODE: dy = tanh(W2 tanh(W1 [y, Dose] + b1) + b2), hidden width 10*D  (model.py:969-1026)
+// packed parameters: kel (unused by the field but a state_dict key), W1 [H][D+1], b1 [H], W2 [D][H], b2 [D].
+// staged layout: one 16-byte aligned record per hidden unit j: {W1[j][0..D], b1[j], W2[0..D-1][j], pad}, then b2 --
+// every weight the j-th unit needs is contiguous, so the broadcast reads are LDS.128.
+// ------------------------------------------------------------------------------------------------------------
+template <int D_>
+struct Neural {
+    static constexpr int D = D_;
+    static constexpr int H = 10 * D_;
+    static constexpr int IN = D_ + 1;
+    static constexpr int P = 1 + H * IN + H + D_ * H + D_;
+    static constexpr int R = ((2 * D_ + 2 + 3) / 4) * 4;  // record length
+    static constexpr int SP = H * R + ((D_ + 3) / 4) * 4;
+    static constexpr int OFF_W1 = 1;
+    static constexpr int OFF_B1 = 1 + H * IN;
+    static constexpr int OFF_W2 = OFF_B1 + H;
+    static constexpr int OFF_B2 = OFF_W2 + D_ * H;
+    static constexpr bool kAccInRegs = false;  // P is 846..3132: accumulators live in local memory
+
+    HODE_HD static void stage(const float* __restrict__ src, float* sp, int tid, int nthr) {
+        for (int e = tid; e < H * R; e += nthr) {
+            const int j = e / R, c = e % R;
+            float v = 0.0f;
+            if (c < IN) v = src[OFF_W1 + j * IN + c];
+            else if (c == IN) v = src[OFF_B1 + j];
+            else if (c < IN + 1 + D_) v = src[OFF_W2 + (c - IN - 1) * H + j];
+            sp[e] = v;
+        }
+        for (int d = tid; d < D_; d += nthr) sp[H * R + d] = src[OFF_B2 + d];
+    }
+    HODE_HD static void prepare(float*) {}
+
+    template <class Dose>
+    HODE_HD static void eval(const float* __restrict__ sp, float t, const Dose& ds, const float (&y)[D_],
+                             float (&dy)[D_]) {
+        float in[IN], out[D_];
+#pragma unroll
+        for (int i = 0; i < D_; ++i) in[i] = y[i];
+        in[D_] = neural_dose(ds, t);
+#pragma unroll
+        for (int d = 0; d < D_; ++d) out[d] = sp[H * R + d];
+#pragma unroll 2
+        for (int j = 0; j < H; ++j) {
+            const float* rec = sp + j * R;
+            float a = rec[IN];
+#pragma unroll
+            for (int i = 0; i < IN; ++i) a = fmaf(rec[i], in[i], a);
+            a = tanh_f(a);
+#pragma unroll
+            for (int d = 0; d < D_; ++d) out[d] = fmaf(rec[IN + 1 + d], a, out[d]);
+        }
+#pragma unroll
+        for (int d = 0; d < D_; ++d) dy[d] = tanh_f(out[d]);
+    }
+
+    template <bool EG, class Dose>
+    HODE_HD static void vjp(const float* __restrict__ sp, float t, const Dose& ds, const float (&y)[D_],
+                            const float* k, const float (&l)[D_], float (&gy)[D_], float* acc) {
+        float in[IN], u[D_];
+#pragma unroll
+        for (int i = 0; i < D_; ++i) in[i] = y[i];
+        in[D_] = neural_dose(ds, t);
+        if (k != nullptr) {
+#pragma unroll
+            for (int d = 0; d < D_; ++d) u[d] = l[d] * (1.0f - k[d] * k[d]);
+        } else {
+            float s2[D_];
+            eval(sp, t, ds, y, s2);
+#pragma unroll
+            for (int d = 0; d < D_; ++d) u[d] = l[d] * (1.0f - s2[d] * s2[d]);
+        }
+#pragma unroll
+        for (int d = 0; d < D_; ++d) { acc[OFF_B2 + d] += u[d]; gy[d] = 0.0f; }
+#pragma unroll 1
+        for (int j = 0; j < H; ++j) {
+            const float* rec = sp + j * R;
+            float a = rec[IN];
+#pragma unroll
+            for (int i = 0; i < IN; ++i) a = fmaf(rec[i], in[i], a);
+            a = tanh_f(a);
+            float c = 0.0f;
+#pragma unroll
+            for (int d = 0; d < D_; ++d) {
+                c = fmaf(rec[IN + 1 + d], u[d], c);
+                acc[OFF_W2 + d * H + j] = fmaf(u[d], a, acc[OFF_W2 + d * H + j]);
+            }
+            const float del = c * (1.0f - a * a);
+#pragma unroll
+            for (int i = 0; i < D_; ++i) gy[i] = fmaf(rec[i], del, gy[i]);
+#pragma unroll
+            for (int i = 0; i < IN; ++i) acc[OFF_W1 + j * IN + i] = fmaf(del, in[i], acc[OFF_W1 + j * IN + i]);
+            acc[OFF_B1 + j] += del;
         }
     }
 };

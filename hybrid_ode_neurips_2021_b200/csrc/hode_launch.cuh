@@ -44,7 +44,7 @@ template <class F>
 __device__ __forceinline__ void stage_params(const SolveArgs& a, int64_t group, float* sp) {
     const int set = a.pset ? a.pset[group] : 0;
     const float* src = a.params + (int64_t)set * F::P;
-    for (int i = threadIdx.x; i < F::P; i += blockDim.x) sp[i] = src[i];
+    F::stage(src, sp, (int)threadIdx.x, (int)blockDim.x);
     __syncthreads();
     if (threadIdx.x == 0) F::prepare(sp);
     __syncthreads();
@@ -57,17 +57,38 @@ __device__ __forceinline__ void reduce_param_grads(const SolveArgs& a, int64_t g
     const int lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < F::P; i += blockDim.x) sred[i] = 0.0f;
     __syncthreads();
+    if constexpr (F::kAccInRegs) {
 #pragma unroll
-    for (int p = 0; p < F::P; ++p) {
-        float v = acc[p];
+        for (int p = 0; p < F::P; ++p) {
+            float v = acc[p];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) atomicAdd(&sred[p], v);
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) atomicAdd(&sred[p], v);
+        }
+    } else {
+#pragma unroll 1
+        for (int p = 0; p < F::P; ++p) {
+            float v = acc[p];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            if (lane == 0) atomicAdd(&sred[p], v);
+        }
     }
     __syncthreads();
     const int set = a.pset ? a.pset[group] : 0;
     float* dst = a.grad_params + (int64_t)set * F::P;
     for (int i = threadIdx.x; i < F::P; i += blockDim.x) atomicAdd(&dst[i], sred[i]);
+}
+
+template <class F>
+__device__ __forceinline__ void zero_acc(float* acc) {
+    if constexpr (F::kAccInRegs) {
+#pragma unroll
+        for (int p = 0; p < F::P; ++p) acc[p] = 0.0f;
+    } else {
+#pragma unroll 1
+        for (int p = 0; p < F::P; ++p) acc[p] = 0.0f;
+    }
 }
 
 template <int ND>
@@ -123,8 +144,7 @@ __global__ void __launch_bounds__(128) fixed_bwd_kernel(const SolveArgs a, int t
     const Tile tl = tile_of(a, tiles_per_group);
     stage_params<F>(a, tl.group, sp);
     float acc[F::P];
-#pragma unroll
-    for (int p = 0; p < F::P; ++p) acc[p] = 0.0f;
+    zero_acc<F>(acc);
     if (tl.b < a.batch) {
         const int64_t idx = tl.group * a.batch + tl.b;
         if (ND > 0) {
@@ -173,8 +193,7 @@ __global__ void __launch_bounds__(128) dopri5_bwd_kernel(const SolveArgs a, int 
     const Tile tl = tile_of(a, tiles_per_group);
     stage_params<F>(a, tl.group, sp);
     float acc[F::P];
-#pragma unroll
-    for (int p = 0; p < F::P; ++p) acc[p] = 0.0f;
+    zero_acc<F>(acc);
     if (tl.b < a.batch) {
         const int64_t idx = tl.group * a.batch + tl.b;
         const int64_t ctrl = a.per_traj ? idx : tl.group;

@@ -299,7 +299,7 @@ class AdaptiveRK:
         else:
             first = self.first_step
         if self.trace is not None:
-            self.trace.first_step = float(first)
+            self.trace.first_step = float(first.detach())
         # (y1, f1, t0, t1, dt, interp_coeff)
         self.state = (self.y0, f0, t0, t0, first, [self.y0] * 5)
 
@@ -341,7 +341,7 @@ class AdaptiveRK:
         ratio = _compute_error_ratio(y1_error, self.rtol, self.atol, y0, y1, self.norm)
         accept = bool(ratio <= 1)
         if self.trace is not None:
-            self.trace.attempts.append((float(t0), float(dt), float(ratio), accept))
+            self.trace.attempts.append((float(t0), float(dt.detach()), float(ratio.detach()), accept))
             if accept:
                 self.trace.accepted += 1
             else:

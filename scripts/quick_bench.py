@@ -7,7 +7,6 @@ import torch
 
 sys.path.insert(0, ".")
 import hybrid_ode_neurips_2021_b200 as H  # noqa: E402
-from tests._util import make_cohort  # noqa: E402
 
 dev = "cuda:0"
 

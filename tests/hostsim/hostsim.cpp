@@ -5,6 +5,7 @@
 // tests/test_hostsim_*.py check the hand-derived reverse sweeps, tape logic and dense-output emission against the
 // oracle without a GPU.  It exports the solver subset of the include/hode.h ABI, taking HOST pointers.
 #define HODE_HOSTSIM 1
+#define HODE_HAVE_NEURAL 1
 #include <barrier>
 #include <cstring>
 #include <thread>
@@ -47,7 +48,7 @@ template <class F>
 std::vector<float> stage(const SolveArgs& a, int64_t g) {
     std::vector<float> sp(F::SP);
     const int set = a.pset ? a.pset[g] : 0;
-    for (int i = 0; i < F::P; ++i) sp[i] = a.params[(int64_t)set * F::P + i];
+    F::stage(a.params + (int64_t)set * F::P, sp.data(), 0, 1);
     F::prepare(sp.data());
     return sp;
 }

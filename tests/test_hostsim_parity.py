@@ -1,0 +1,202 @@
+"""CPU-side check of the kernel SOURCE: csrc/hode_core.cuh + hode_bodies.cuh (what the sm_100a kernels are compiled
+from) built as plain C++ by tests/hostsim (a thread emulation, test infrastructure only) and compared with the oracle.
+Covers the hand-derived reverse sweeps, the tape, dense-output emission and the controller without a GPU."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from hybrid_ode_neurips_2021_b200 import _lib as L
+from hybrid_ode_neurips_2021_b200 import ops
+from oracle import fields as OF
+from oracle import odeint as OI
+
+from _util import EXPERT_NAMES, make_cohort, oracle_roche, relerr
+
+HS_DIR = os.path.join(os.path.dirname(__file__), "hostsim")
+HS = os.path.join(HS_DIR, "libhode_hostsim.so")
+SYMS = ["hode_abi_version", "hode_last_error", "hode_param_count", "hode_fixed_fwd", "hode_fixed_bwd", "hode_dopri5_fwd",
+        "hode_dopri5_bwd", "hode_dopri5_max_batch"]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    subprocess.run(["make", "-C", HS_DIR], check=True, capture_output=True)
+    return L.HodeLib(HS, required=SYMS)
+
+
+def pack_roche(o):
+    ps = [getattr(o, n).detach().reshape(1) for n in EXPERT_NAMES]
+    if o.ml_dim > 0:
+        ps += [o.ml_net[0].weight.detach().reshape(-1), o.ml_net[0].bias.detach().reshape(-1)]
+    return torch.cat(ps).float()[None].contiguous()
+
+
+def pack_neural(o):
+    l1, l2 = o.ml_net[0], o.ml_net[2]
+    return torch.cat([o.kel.detach().reshape(1), l1.weight.detach().reshape(-1), l1.bias.detach().reshape(-1),
+                      l2.weight.detach().reshape(-1), l2.bias.detach().reshape(-1)]).float()[None].contiguous()
+
+
+def grads_vec(o, neural):
+    if neural:
+        return torch.cat([torch.zeros(1), o.ml_net[0].weight.grad.reshape(-1), o.ml_net[0].bias.grad.reshape(-1),
+                          o.ml_net[2].weight.grad.reshape(-1), o.ml_net[2].bias.grad.reshape(-1)])
+    g = [getattr(o, n).grad.reshape(1) for n in EXPERT_NAMES]
+    if o.ml_dim > 0:
+        g += [o.ml_net[0].weight.grad.reshape(-1), o.ml_net[0].bias.grad.reshape(-1)]
+    return torch.cat(g)
+
+
+def problem(o, cfg, B, n_groups=1, neural=False):
+    return ops.Problem(cfg, n_groups, B // n_groups, o.dosage.float().contiguous(), o.times.float().contiguous(),
+                       pack_neural(o) if neural else pack_roche(o), None)
+
+
+@pytest.mark.parametrize("D", [4, 6, 8, 12])
+@pytest.mark.parametrize("method,opts", [("rk4", {"step_size": 0.0625}), ("rk4", {"step_size": 0.3, "perturb": True}),
+                                         ("midpoint", {"step_size": 0.125, "perturb": True}), ("euler", {"step_size": 0.0625})])
+def test_fixed_grid_forward_and_reverse_sweep(lib, D, method, opts):
+    B = 6
+    o = oracle_roche(D, 1, True)
+    y0, a, _, _ = make_cohort(B, D, seed=D)
+    o.set_action(a)
+    t = torch.arange(0, 15.0)
+    W = torch.randn(15, B, D, generator=torch.Generator().manual_seed(0))
+    z = y0.clone().requires_grad_(True)
+    ref = OI.odeint(o, z, t, method=method, options=opts)
+    (ref * W).sum().backward()
+    grid = OI.fixed_grid_points(t, opts.get("step_size")).contiguous()
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.METHODS[method], perturb=opts.get("perturb", False), n_dose=1)
+    pb = problem(o, cfg, B)
+    h, tape = ops.fixed_fwd(lib, pb, y0, grid, t, True)
+    gy0, gp = ops.fixed_bwd(lib, pb, grid, t, W, tape)
+    assert relerr(h, ref) < 2e-6
+    assert relerr(gy0, z.grad) < 5e-6
+    gref = grads_vec(o, False)
+    ok = ~torch.isnan(gref)
+    assert torch.equal(torch.isnan(gp[0]), ~ok)
+    assert relerr(gp[0][ok], gref[ok]) < 5e-5
+
+
+@pytest.mark.parametrize("D", [4, 6, 8, 12])
+@pytest.mark.parametrize("ctrl", ["batch", "trajectory"])
+def test_dopri5_forward_and_reverse_sweep(lib, D, ctrl):
+    B = 5 if ctrl == "batch" else 1
+    o = oracle_roche(D, 2, True)
+    y0, a, _, _ = make_cohort(B, D, seed=20 + D)
+    o.set_action(a)
+    t = torch.arange(0, 15.0)
+    W = torch.randn(15, B, D, generator=torch.Generator().manual_seed(1))
+    z = y0.clone().requires_grad_(True)
+    tr = OI.SolveTrace()
+    ref = OI.odeint(o, z, t, rtol=1e-7, atol=1e-8, method="dopri5", options={"trace": tr, "differentiable_first_step": False})
+    (ref * W).sum().backward()
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.DOPRI5, n_dose=1, rtol=1e-7, atol=1e-8,
+                       controller=L.CTRL_TRAJ if ctrl == "trajectory" else L.CTRL_BATCH)
+    pb = problem(o, cfg, B)
+    h, stats, tape = ops.dopri5_fwd(lib, pb, y0, t.double(), 1024)
+    assert stats[0, 3] == 0 and stats[0, 2] == 2 + 6 * (stats[0, 0] + stats[0, 1])
+    n_ref, n_out = tr.accepted + tr.rejected, int(stats[0, 0] + stats[0, 1])
+    assert abs(n_out - n_ref) <= 0.3 * n_ref
+    assert tape[0][0, 0, 0] == 0.0 and abs(tape[0][0, 0, 1].item() - tr.first_step) < 1e-5 * tr.first_step
+    gy0, gp = ops.dopri5_bwd(lib, pb, t.double(), W, tape, stats)
+    assert relerr(h, ref) < 5e-5
+    assert relerr(gy0, z.grad) < 5e-5
+    if D > 4:
+        assert relerr(gp[0][13:], grads_vec(o, False)[13:]) < 5e-5
+
+
+def test_dopri5_first_attempt_is_exactly_the_oracle_attempt(lib):
+    D, B, h = 6, 4, 0.25
+    o = oracle_roche(D, 3, True)
+    y0, a, _, _ = make_cohort(B, D, seed=3)
+    y0 = y0 * 20
+    o.set_action(a)
+    t = torch.tensor([0.0, 0.05, 0.125, 0.25, 0.3])
+    tr = OI.SolveTrace()
+    with torch.no_grad():
+        ref = OI.odeint(o, y0, t, rtol=1e-4, atol=1e-5, options={"first_step": h, "trace": tr})
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.DOPRI5, n_dose=1, rtol=1e-4, atol=1e-5, first_step=h)
+    out, stats, tape = ops.dopri5_fwd(lib, problem(o, cfg, B), y0, t.double(), 16)
+    assert relerr(out[:4], ref[:4]) < 1e-6
+    assert tr.attempts[0][3] and tr.attempts[1][3]
+    assert abs(tape[0][0, 1, 1].item() - tr.attempts[1][1]) <= 1e-3 * tr.attempts[1][1]
+
+
+def test_failure_statuses(lib):
+    D, B = 6, 3
+    o = oracle_roche(D, 4, False)
+    y0, a, _, _ = make_cohort(B, D, seed=4)
+    o.set_action(a)
+    t = torch.arange(0, 15.0).double()
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.DOPRI5, n_dose=1, rtol=1e-7, atol=1e-8, max_num_steps=3)
+    _, stats, _ = ops.dopri5_fwd(lib, problem(o, cfg, B), y0, t, 0)
+    assert stats[0, 3] == L.SOLVE_MAX_STEPS
+    bad = y0.clone()
+    bad[1, 1] = float("nan")
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.DOPRI5, n_dose=1, rtol=1e-7, atol=1e-8)
+    _, stats, _ = ops.dopri5_fwd(lib, problem(o, cfg, B), bad, t, 0)
+    assert stats[0, 3] == L.SOLVE_DT_UNDERFLOW  # NaN first step -> torchdiffeq's 'underflow in dt nan'
+    bad[1, 1] = float("inf")
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.DOPRI5, n_dose=1, rtol=1e-7, atol=1e-8, first_step=0.01)
+    _, stats, _ = ops.dopri5_fwd(lib, problem(o, cfg, B), bad, t, 0)
+    assert stats[0, 3] == L.SOLVE_NONFINITE
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.DOPRI5, n_dose=1, rtol=1e-7, atol=1e-8)
+    _, stats, _ = ops.dopri5_fwd(lib, problem(o, cfg, B), y0, t, 5)
+    assert stats[0, 3] == L.SOLVE_TAPE_FULL
+
+
+@pytest.mark.parametrize("D", [4, 6, 12])
+def test_neural_field_all_solvers(lib, D):
+    B = 4
+    torch.manual_seed(D)
+    o = OF.OracleNeuralODE(D)
+    y0, a, _, _ = make_cohort(B, D, seed=D)
+    y0 = y0 * 30
+    o.set_action(a)
+    t = torch.arange(0, 15.0)
+    W = torch.randn(15, B, D, generator=torch.Generator().manual_seed(2))
+    for method, opts in (("rk4", {"step_size": 0.5}), ("midpoint", {}), ("euler", {"step_size": 0.25})):
+        o.zero_grad()
+        z = y0.clone().requires_grad_(True)
+        ref = OI.odeint(o, z, t, method=method, options=opts)
+        (ref * W).sum().backward()
+        grid = OI.fixed_grid_points(t, opts.get("step_size")).contiguous()
+        cfg = ops.make_cfg(L.FIELD_NEURAL, D, L.METHODS[method], n_dose=1)
+        pb = problem(o, cfg, B, neural=True)
+        h, tape = ops.fixed_fwd(lib, pb, y0, grid, t, True)
+        gy0, gp = ops.fixed_bwd(lib, pb, grid, t, W, tape)
+        assert relerr(h, ref) < 2e-6 and relerr(gy0, z.grad) < 5e-6 and relerr(gp[0], grads_vec(o, True)) < 1e-5
+    o.zero_grad()
+    z = y0.clone().requires_grad_(True)
+    ref = OI.odeint(o, z, t, rtol=1e-5, atol=1e-6, options={"differentiable_first_step": False})
+    (ref * W).sum().backward()
+    cfg = ops.make_cfg(L.FIELD_NEURAL, D, L.DOPRI5, n_dose=1, rtol=1e-5, atol=1e-6)
+    pb = problem(o, cfg, B, neural=True)
+    h, stats, tape = ops.dopri5_fwd(lib, pb, y0, t.double(), 256)
+    gy0, gp = ops.dopri5_bwd(lib, pb, t.double(), W, tape, stats)
+    assert relerr(h, ref) < 5e-5 and relerr(gy0, z.grad) < 2e-4 and relerr(gp[0], grads_vec(o, True)) < 2e-4
+
+
+def test_parameter_sets_per_group(lib):
+    """Ensemble members: groups with different weights in one call (config 4)."""
+    D, B, G = 6, 3, 2
+    os_ = [oracle_roche(D, 10 + g, True) for g in range(G)]
+    y0, a, _, _ = make_cohort(B * G, D, seed=9)
+    t = torch.arange(0, 15.0)
+    grid = OI.fixed_grid_points(t, 0.125).contiguous()
+    refs = []
+    for g, o in enumerate(os_):
+        o.set_action(a[:, g * B:(g + 1) * B])
+        with torch.no_grad():
+            refs.append(OI.odeint(o, y0[g * B:(g + 1) * B], t, method="rk4", options={"step_size": 0.125}))
+    full = OF.OracleRocheODE(D)
+    full.set_action(a)
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.RK4_38, n_dose=1)
+    pb = ops.Problem(cfg, G, B, full.dosage.float().contiguous(), full.times.float().contiguous(),
+                     torch.cat([pack_roche(o) for o in os_]).contiguous(), torch.arange(G, dtype=torch.int32))
+    h, _ = ops.fixed_fwd(lib, pb, y0, grid, t, False)
+    assert relerr(h, torch.cat(refs, dim=1)) < 2e-6
