@@ -63,6 +63,7 @@ SIGNATURES = {
         _I32,
         [_CFG, _I64, _I64, _P, _P, _I64, _P, _P, _I32, _P, _I32, _P, _P, _P, _I32, _P, _P, _P, _P],
     ),
+    "hode_bench_ffma": (_I64, [_I32, _I32, _P, _P]),
     "hode_decode_sse": (_I32, [_I32, _I32, _I32, _I64, _F64, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P]),
 }
 

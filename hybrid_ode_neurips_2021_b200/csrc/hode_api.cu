@@ -14,6 +14,7 @@ int launch_dose_schedule(const float*, int64_t, int64_t, int32_t, int64_t, float
 int launch_decode_sse(int32_t, int32_t, int32_t, int64_t, double, const float*, const float*, const float*,
                       const float*, const float*, int64_t, int64_t, int64_t, float*, float*, float*, float*,
                       cudaStream_t);
+int launch_ffma_probe(int, int, float*, cudaStream_t);
 }  // namespace hode
 
 using namespace hode;
@@ -225,6 +226,13 @@ int32_t hode_decode_sse(int32_t D, int32_t obs, int32_t n_t, int64_t n_traj, dou
     if (rc == -1) return fail(HODE_ERR_UNSUPPORTED, "decode_sse: obs*D too large for one CTA's shared memory");
     if (rc != 0) return fail(HODE_ERR_CUDA, "CUDA error: %s (%lld)", cudaGetErrorString((cudaError_t)rc), rc);
     return HODE_OK;
+}
+
+int64_t hode_bench_ffma(int32_t blocks, int32_t iters, float* out, void* stream) {
+    if (blocks < 1 || iters < 1 || !out) return fail(HODE_ERR_ARG, "bad blocks / iters / out");
+    const int rc = launch_ffma_probe(blocks, iters, out, (cudaStream_t)stream);
+    if (rc != 0) return fail(HODE_ERR_CUDA, "CUDA error: %s (%lld)", cudaGetErrorString((cudaError_t)rc), rc);
+    return (int64_t)2 * 16 * (int64_t)iters * 256 * (int64_t)blocks;
 }
 
 }  // extern "C"

@@ -193,4 +193,28 @@ int launch_decode_sse(int32_t D, int32_t obs, int32_t n_t, int64_t n_traj, doubl
 #undef HODE_DS
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// FP32 FMA peak probe for the roofline denominator (MEASURED_PEAKS.json has HBM and bf16 figures only):
+// 16 independent FFMA chains per thread, no memory traffic.  flops = 2 * 16 * iters * threads.
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ffma_probe_kernel(int iters, float seed, float* __restrict__ out) {
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = seed + (float)(threadIdx.x + i) * 1e-3f;
+    const float m = 1.0f - 1e-6f * seed, c = 1e-7f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], m, c);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 123.456f) out[0] = s;  // never true; keeps the chains alive
+}
+
+int launch_ffma_probe(int blocks, int iters, float* out, cudaStream_t st) {
+    ffma_probe_kernel<<<blocks, 256, 0, st>>>(iters, 1.0f, out);
+    return (int)cudaGetLastError();
+}
+
 }  // namespace hode

@@ -18,6 +18,7 @@ must live on a CUDA device (``RuntimeError`` otherwise).  Extensions (all option
 from __future__ import annotations
 
 import warnings
+import weakref
 from typing import Optional
 
 import torch
@@ -122,11 +123,14 @@ _time_cache = {}
 
 
 def _times_for(t: torch.Tensor, step_size, device, fixed: bool):
-    """Device copies of the output times / solver grid, cached per (t storage, version, step_size)."""
-    key = (t.data_ptr(), t._version, t.numel(), str(t.dtype), str(t.device), step_size, str(device), fixed)
+    """Device copies of the output times / solver grid.  Cached per tensor OBJECT (weak reference + version counter),
+    so a decoder's persistent ``self.t`` costs one host read in its lifetime; a fresh tensor is always re-read."""
+    key = (id(t), step_size, str(device), fixed)
     hit = _time_cache.get(key)
     if hit is not None:
-        return hit
+        ref, version, out = hit
+        if ref() is t and version == t._version:
+            return out
     t_host = t.detach().cpu()
     assert t_host.dim() == 1 and torch.is_floating_point(t_host), "t must be a one dimensional floating point Tensor"
     if t_host.numel() > 1:
@@ -145,7 +149,7 @@ def _times_for(t: torch.Tensor, step_size, device, fixed: bool):
         out = (t_host.to(torch.float64).to(device).contiguous(), None)
     if len(_time_cache) > 64:
         _time_cache.clear()
-    _time_cache[key] = out
+    _time_cache[key] = (weakref.ref(t), t._version, out)
     return out
 
 

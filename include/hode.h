@@ -149,6 +149,11 @@ int32_t hode_decode_sse(int32_t D, int32_t obs, int32_t n_t, int64_t n_traj, dou
                         const float* W, const float* b, const float* x, const float* mask, int64_t st, int64_t sb,
                         int64_t so, float* loss, float* grad_h, float* grad_w, float* grad_b, void* stream);
 
+/* ---- measurement aid: FP32 FMA peak probe (the roofline denominator of the solver kernels; bench.py times it).
+ * Launches `blocks` CTAs of 256 threads running 16 independent FFMA chains for `iters` iterations.
+ * Returns the number of floating-point operations the launch performs (FMA = 2), or a negative hode_status. */
+int64_t hode_bench_ffma(int32_t blocks, int32_t iters, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

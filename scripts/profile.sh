@@ -1,0 +1,14 @@
+#!/bin/bash
+# ncu evidence for bench.py (run under gpurun, one GPU).  Usage: scripts/profile.sh <tag>
+# 1) plain run (must exit 0), 2) launch list with per-launch device time, 3) --set full on the three hot kernels.
+set -u
+TAG=${1:-r01}
+OUT=gpurun_out/prof_$TAG
+mkdir -p $OUT
+CMD="python bench.py --steps 2 --warmup 3 --cpu-patients 512"
+$CMD > $OUT/plain.json 2> $OUT/plain.err || { echo "plain run failed"; tail -5 $OUT/plain.err; exit 1; }
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv $CMD > $OUT/ncu_launches.log 2>&1
+for K in fixed_fwd_kernel fixed_bwd_kernel decode_sse_kernel; do
+  ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 1 -o $OUT/$K $CMD > $OUT/ncu_$K.log 2>&1
+done
+ls -la $OUT
