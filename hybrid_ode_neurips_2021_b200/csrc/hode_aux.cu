@@ -151,10 +151,165 @@ __global__ void __launch_bounds__(kThreads) decode_sse_kernel(
     if ((tid & 31) == 0) atomicAdd(loss, lsum * inv_norm);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fast path of decode + masked SSE for contiguous x / mask [n_t, n_traj, obs] with obs % 4 == 0 (the layout a training
+// loop keeps on the device).  Same two passes as above, but
+//   * the x / mask tiles are fetched with 16-byte cp.async (LDGSTS): 2 * TR * obs * 4 bytes in flight per CTA, several
+//     CTAs per SM, so HBM latency is covered without register staging (the scalar version was latency-bound: ~1 TB/s);
+//   * rows are padded to an odd number of 16-byte chunks: thread-per-row LDS.128 / STS.128 are bank-conflict free.
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+
+template <int D, int TR>
+__global__ void __launch_bounds__(TR) decode_sse_fast_kernel(
+    int32_t obs, int32_t ldx, int32_t n_t, int64_t n_traj, float scale, float inv_norm, const float* __restrict__ h,
+    const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ x,
+    const float* __restrict__ mask, float* __restrict__ loss, float* __restrict__ grad_h, float* __restrict__ grad_w,
+    float* __restrict__ grad_b) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int DP = (D + 3) / 4 * 4;  // W rows padded to 16 bytes
+    const int obs4 = obs / 4;
+    float* sW = smem;                      // [obs][DP]
+    float* sB = sW + obs * DP;             // [obs]
+    float* sH = sB + obs;                  // [TR][DP]
+    float* sX = sH + TR * DP;              // [TR][ldx]
+    float* sM = sX + TR * ldx;             // [TR][ldx]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < obs * DP; i += TR) {
+        const int o = i / DP, d = i % DP;
+        sW[i] = d < D ? W[o * D + d] : 0.0f;
+    }
+    for (int i = tid; i < obs; i += TR) sB[i] = bias[i];
+
+    const int nsub = TR / obs > 0 ? TR / obs : 1;
+    const int o2 = tid % obs, sub2 = tid / obs;
+    const bool act2 = sub2 < nsub && grad_w != nullptr;
+    float gw[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) gw[d] = 0.0f;
+    float gb = 0.0f, lsum = 0.0f;
+
+    const int64_t tiles_per_t = (n_traj + TR - 1) / TR;
+    const int64_t n_tiles = tiles_per_t * n_t;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t t = tile / tiles_per_t;
+        const int64_t b0 = (tile % tiles_per_t) * TR;
+        const int rows = (int)((n_traj - b0) < TR ? (n_traj - b0) : TR);
+        __syncthreads();
+        {   // tile load: chunk c of the tile is 16 contiguous bytes; consecutive lanes take consecutive chunks
+            const float* xb = x + ((int64_t)t * n_traj + b0) * obs;
+            const float* mb = mask + ((int64_t)t * n_traj + b0) * obs;
+            int r = tid / obs4, c4 = tid % obs4;
+            const int dr = TR / obs4, dc = TR % obs4;
+            while (r < rows) {
+                const int src = (r * obs4 + c4) * 4, dst = r * ldx + c4 * 4;
+                cp_async16(sX + dst, xb + src);
+                cp_async16(sM + dst, mb + src);
+                r += dr; c4 += dc;
+                if (c4 >= obs4) { c4 -= obs4; ++r; }
+            }
+        }
+        const bool act1 = tid < rows;
+        float hv[D], gh[D];
+        if (act1) {
+            const float* hp = h + ((int64_t)t * n_traj + b0 + tid) * D;
+#pragma unroll
+            for (int d = 0; d < D; ++d) { hv[d] = hp[d]; sH[tid * DP + d] = hv[d]; gh[d] = 0.0f; }
+        }
+        cp_async_wait_all();
+        __syncthreads();
+        if (act1) {
+            float4* xr = reinterpret_cast<float4*>(sX + tid * ldx);
+            const float4* mr = reinterpret_cast<const float4*>(sM + tid * ldx);
+            for (int q = 0; q < obs4; ++q) {
+                const float4 xv = xr[q], mv = mr[q];
+                const float4 bv = reinterpret_cast<const float4*>(sB)[q];
+                const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ms[4] = {mv.x, mv.y, mv.z, mv.w};
+                const float bs[4] = {bv.x, bv.y, bv.z, bv.w};
+                float cs[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float* w = sW + (q * 4 + i) * DP;
+                    float xh = bs[i];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) xh = fmaf(w[d], hv[d], xh);
+                    const float diff = xs[i] - xh;
+                    const float dm = diff * ms[i];
+                    lsum = fmaf(diff, dm, lsum);
+                    const float c = scale * dm;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) gh[d] = fmaf(c, w[d], gh[d]);
+                    cs[i] = c;
+                }
+                xr[q] = make_float4(cs[0], cs[1], cs[2], cs[3]);
+            }
+            if (grad_h != nullptr) {
+                float* gp = grad_h + ((int64_t)t * n_traj + b0 + tid) * D;
+#pragma unroll
+                for (int d = 0; d < D; ++d) gp[d] = gh[d];
+            }
+        }
+        __syncthreads();
+        if (act2) {
+            for (int r = sub2; r < rows; r += nsub) {
+                const float c = sX[r * ldx + o2];
+                gb += c;
+#pragma unroll
+                for (int d = 0; d < D; ++d) gw[d] = fmaf(c, sH[r * DP + d], gw[d]);
+            }
+        }
+    }
+    if (act2) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) atomicAdd(&grad_w[o2 * D + d], gw[d]);
+        if (grad_b != nullptr) atomicAdd(&grad_b[o2], gb);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
+    if ((tid & 31) == 0) atomicAdd(loss, lsum * inv_norm);
+}
+
+template <int D, int TR>
+static int launch_decode_fast(int32_t obs, int32_t n_t, int64_t n_traj, double n_norm, const float* h, const float* W,
+                              const float* b, const float* x, const float* mask, float* loss, float* grad_h,
+                              float* grad_w, float* grad_b, cudaStream_t stream) {
+    constexpr int DP = (D + 3) / 4 * 4;
+    const int obs4 = obs / 4;
+    const int ldx = (obs4 % 2 == 0) ? obs + 4 : obs;
+    const size_t sh = sizeof(float) * ((size_t)obs * DP + obs + (size_t)TR * DP + 2 * (size_t)TR * ldx);
+    if (sh > 227 * 1024) return -1;
+    cudaError_t e = cudaFuncSetAttribute(decode_sse_fast_kernel<D, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    if (e != cudaSuccess) return (int)e;
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_sse_fast_kernel<D, TR>, TR, sh);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t n_tiles = ((n_traj + TR - 1) / TR) * n_t;
+    int64_t grid = (int64_t)sms * per_sm;
+    if (grid > n_tiles) grid = n_tiles;
+    decode_sse_fast_kernel<D, TR><<<(unsigned)grid, TR, sh, stream>>>(obs, ldx, n_t, n_traj, (float)(-2.0 / n_norm),
+                                                                     (float)(1.0 / n_norm), h, W, b, x, mask, loss,
+                                                                     grad_h, grad_w, grad_b);
+    return (int)cudaGetLastError();
+}
+
 template <int D>
 static int launch_decode_sse_d(int32_t obs, int32_t n_t, int64_t n_traj, double n_norm, const float* h, const float* W,
                                const float* b, const float* x, const float* mask, int64_t st, int64_t sb, int64_t so,
                                float* loss, float* grad_h, float* grad_w, float* grad_b, cudaStream_t stream) {
+    const bool contiguous = so == 1 && sb == obs && (n_t == 1 || st == n_traj * (int64_t)obs);
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(mask)) & 15) == 0;
+    if (contiguous && aligned && obs % 4 == 0 && obs >= 4) {
+        if (obs <= 48) return launch_decode_fast<D, 128>(obs, n_t, n_traj, n_norm, h, W, b, x, mask, loss, grad_h, grad_w, grad_b, stream);
+        if (obs <= 64) return launch_decode_fast<D, 64>(obs, n_t, n_traj, n_norm, h, W, b, x, mask, loss, grad_h, grad_w, grad_b, stream);
+        if (obs <= 128) return launch_decode_fast<D, 128>(obs, n_t, n_traj, n_norm, h, W, b, x, mask, loss, grad_h, grad_w, grad_b, stream);
+    }
     const int ld = obs | 1;
     const size_t sh = sizeof(float) * ((size_t)obs * D + obs + (size_t)kTR * D + 2 * (size_t)kTR * ld);
     if (obs > kThreads || sh > 227 * 1024) return -1;

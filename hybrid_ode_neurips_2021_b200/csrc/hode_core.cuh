@@ -24,8 +24,8 @@
 #define HODE_DEVICE_BUILD 0
 #endif
 
-#ifndef HODE_FAST_TANH
-#define HODE_FAST_TANH 0
+#ifndef HODE_FAST_MATH
+#define HODE_FAST_MATH 1
 #endif
 
 namespace hode {
@@ -51,17 +51,22 @@ HODE_HD float div_rn(float a, float b) { volatile float r = a / b; return r; }
 HODE_HD float t_next(float t) { return nextafterf(t, t + 1.0f); }
 HODE_HD float t_prev(float t) { return nextafterf(t, t - 1.0f); }
 
-HODE_HD float tanh_f(float x) {
-#if HODE_FAST_TANH && HODE_DEVICE_BUILD && defined(__CUDA_ARCH__)
-    // 1 - 2/(exp(2x)+1): 2 MUFU + 3 FMA-pipe ops, abs error ~1.2e-7 ("tanh")
-    float e, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
-    return fmaf(-2.0f, r, 1.0f);
+// ---- transcendental primitives ----------------------------------------------------------------------------------
+// HODE_FAST_MATH=1 (device default): MUFU-based forms with ~1e-7 absolute error (DESIGN.md "math"): the kernels are
+// issue-bound, and libm's tanhf/expf/division cost 4-5x the instructions.  HODE_FAST_MATH=0 keeps the libm calls.
+#if HODE_FAST_MATH && HODE_DEVICE_BUILD && defined(__CUDA_ARCH__)
+HODE_D float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+HODE_D float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// tanh(x) = 1 - 2/(2^(2x log2 e) + 1): 2 MUFU + 3 FMA-pipe ops; saturates correctly at +-inf, NaN propagates
+HODE_D float tanh_f(float x) { return fmaf(-2.0f, rcp_approx(ex2_approx(x * 2.8853900817779268f) + 1.0f), 1.0f); }
+// exp(kel * d) with kl2 = kel * log2(e) pre-multiplied
+HODE_D float exp_scaled(float kl2, float /*kel*/, float d) { return ex2_approx(kl2 * d); }
+HODE_D float rcp_f(float x) { return rcp_approx(x); }
 #else
-    return tanhf(x);
+HODE_HD float tanh_f(float x) { return tanhf(x); }
+HODE_HD float exp_scaled(float /*kl2*/, float kel, float d) { return expf(mul_rn(kel, d)); }
+HODE_HD float rcp_f(float x) { return 1.0f / x; }
 #endif
-}
 
 // x ** p with a float32 tensor exponent (model.py:529, 537-538).  p == 2 (RochConfig default) is a multiply.
 HODE_HD float pow_hill(float x, float p) { return (p == 2.0f) ? x * x : powf(x, p); }
@@ -98,26 +103,26 @@ struct DoseMem {  // times read from memory (any n_dose)
 
 // RocheODE.dose_at_time (model.py:509-513): amt * sum_j exp(kel*(tau_j - t) * [t>=tau_j]) * [t>=tau_j]
 template <class Dose>
-HODE_HD float roche_dose(const Dose& ds, float t, float kel) {
+HODE_HD float roche_dose(const Dose& ds, float t, float kel, float kl2) {
     float s = 0.0f;
     const int n = ds.n();
     for (int j = 0; j < n; ++j) {
         const float tau = ds.at(j);
-        if (t >= tau) s += expf(mul_rn(kel, sub_rn(tau, t)));
+        const float e = exp_scaled(kl2, kel, sub_rn(tau, t));
+        s += (t >= tau) ? e : 0.0f;
     }
     return ds.amt * s;
 }
 // d Dose / d kel = amt * sum_j (tau_j - t) exp(kel (tau_j - t)) [t >= tau_j]
 template <class Dose>
-HODE_HD float roche_dose_dkel(const Dose& ds, float t, float kel) {
+HODE_HD float roche_dose_dkel(const Dose& ds, float t, float kel, float kl2) {
     float s = 0.0f;
     const int n = ds.n();
     for (int j = 0; j < n; ++j) {
         const float tau = ds.at(j);
-        if (t >= tau) {
-            const float d = sub_rn(tau, t);
-            s += d * expf(mul_rn(kel, d));
-        }
+        const float d = sub_rn(tau, t);
+        const float e = d * exp_scaled(kl2, kel, d);
+        s += (t >= tau) ? e : 0.0f;
     }
     return ds.amt * s;
 }
@@ -144,33 +149,36 @@ struct Roche {
     static constexpr int D = D_;
     static constexpr int ML = D_ - 4;
     static constexpr int P = R_NSCALAR + ML * D_ + ML;  // packed parameter count
-    static constexpr int SP = P + 1;                     // staged: + ec50**hp
     static constexpr int OFF_W = R_NSCALAR;
     static constexpr int OFF_B = R_NSCALAR + ML * D_;
-    static constexpr int OFF_ECP = P;
-    static constexpr int EVALS_FLOPS = 29 + 2 * D_ * ML + ML + 3 + ML;  // SURVEY.md 8(d) algorithmic count
-
-    static constexpr bool kAccInRegs = true;             // per-thread gradient accumulators fit in registers
+    // staged copy appends derived constants
+    static constexpr int OFF_ECP = P;       // ec50 ** HillPatho
+    static constexpr int OFF_KL2 = P + 1;   // kel * log2(e)
+    static constexpr int SP = P + 2;
+    static constexpr bool kAccInRegs = true;  // per-thread gradient accumulators fit in registers
 
     // cooperative copy of one packed parameter set into the staged layout (thread `tid` of `nthr`)
     HODE_HD static void stage(const float* __restrict__ src, float* sp, int tid, int nthr) {
         for (int i = tid; i < P; i += nthr) sp[i] = src[i];
     }
-    HODE_HD static void prepare(float* sp) { sp[OFF_ECP] = pow_hill(sp[R_EC50], sp[R_HP]); }
+    HODE_HD static void prepare(float* sp) {
+        sp[OFF_ECP] = pow_hill(sp[R_EC50], sp[R_HP]);
+        sp[OFF_KL2] = sp[R_KEL] * 1.4426950408889634f;
+    }
 
+    // f(t, y).  Same terms as model.py:527-544, factored to minimise issue slots (the kernels are issue-bound):
+    //   dx1 = D (kp - I^hc kdi - R kdr);  dx2 = D (kid + R kfb) - R (koff + Q kdexa) + R^hp emax / (ec50^hp + R^hp)
     template <class Dose>
     HODE_HD static void eval(const float* __restrict__ sp, float t, const Dose& ds, const float (&y)[D_],
                              float (&dy)[D_]) {
         const float dis = y[0], react = y[1], imm = y[2], dose2 = y[3];
-        const float kel = sp[R_KEL];
-        const float dose = roche_dose(ds, t, kel);
         const float ip = pow_hill(imm, sp[R_HC]);
         const float rp = pow_hill(react, sp[R_HP]);
-        dy[0] = dis * sp[R_KDISPROG] - dis * ip * sp[R_KDCI] - dis * react * sp[R_KDCIR];
-        dy[1] = dis * sp[R_KID] - react * sp[R_KOFF] + dis * react * sp[R_KFB] +
-                (rp * sp[R_EMAX]) / (sp[OFF_ECP] + rp) - dose2 * react * sp[R_KDEXA];
+        dy[0] = dis * fmaf(-react, sp[R_KDCIR], fmaf(-ip, sp[R_KDCI], sp[R_KDISPROG]));
+        const float hill = (rp * sp[R_EMAX]) * rcp_f(sp[OFF_ECP] + rp);
+        dy[1] = fmaf(dis, fmaf(react, sp[R_KFB], sp[R_KID]), fmaf(-react, fmaf(dose2, sp[R_KDEXA], sp[R_KOFF]), hill));
         dy[2] = react * sp[R_KIM];
-        dy[3] = kel * dose - kel * dose2;
+        dy[3] = sp[R_KEL] * (roche_dose(ds, t, sp[R_KEL], sp[OFF_KL2]) - dose2);
 #pragma unroll
         for (int j = 0; j < ML; ++j) {
             float a = sp[OFF_B + j];
@@ -191,23 +199,22 @@ struct Roche {
         const float kel = sp[R_KEL];
         const float ip = pow_hill(imm, hc);
         const float rp = pow_hill(react, hp);
-        const float den = ecp + rp;
-        const float inv_den = 1.0f / den;
+        const float inv_den = rcp_f(ecp + rp);
         const float l0 = l[0], l1 = l[1], l2 = l[2], l3 = l[3];
-        const float drp = dpow_hill(react, hp);
-        gy[0] = l0 * (sp[R_KDISPROG] - ip * kdci - react * kdcir) + l1 * (sp[R_KID] + react * kfb);
-        gy[1] = l0 * (-dis * kdcir) +
-                l1 * (-sp[R_KOFF] + dis * kfb + em * drp * ecp * inv_den * inv_den - dose2 * kdexa) + l2 * sp[R_KIM];
-        gy[2] = l0 * (-dis * kdci * dpow_hill(imm, hc));
-        gy[3] = l1 * (-react * kdexa) - l3 * kel;
+        const float l0d = l0 * dis;
+        const float hill_d = (em * ecp) * dpow_hill(react, hp) * (inv_den * inv_den);  // d/dR of the Hill term
+        gy[0] = fmaf(l0, fmaf(-react, kdcir, fmaf(-ip, kdci, sp[R_KDISPROG])), l1 * fmaf(react, kfb, sp[R_KID]));
+        gy[1] = fmaf(-l0d, kdcir, fmaf(l1, fmaf(dis, kfb, hill_d) - fmaf(dose2, kdexa, sp[R_KOFF]), l2 * sp[R_KIM]));
+        gy[2] = -l0d * kdci * dpow_hill(imm, hc);
+        gy[3] = fmaf(-l1 * react, kdexa, -l3 * kel);
 #pragma unroll
         for (int d = 4; d < D_; ++d) gy[d] = 0.0f;
         if (EG) {
             const float ec50 = sp[R_EC50];
-            acc[R_KDISPROG] += l0 * dis;
-            acc[R_KDCI] -= l0 * dis * ip;
-            acc[R_KDCIR] -= l0 * dis * react;
-            acc[R_HC] -= l0 * dis * kdci * dpow_hill_exp(imm, ip, hc);
+            acc[R_KDISPROG] += l0d;
+            acc[R_KDCI] -= l0d * ip;
+            acc[R_KDCIR] -= l0d * react;
+            acc[R_HC] -= l0d * kdci * dpow_hill_exp(imm, ip, hc);
             acc[R_KID] += l1 * dis;
             acc[R_KOFF] -= l1 * react;
             acc[R_KFB] += l1 * dis * react;
@@ -218,8 +225,8 @@ struct Roche {
                          inv_den;
             acc[R_KDEXA] -= l1 * dose2 * react;
             acc[R_KIM] += l2 * react;
-            const float dose = roche_dose(ds, t, kel);
-            acc[R_KEL] += l3 * (dose - dose2 + kel * roche_dose_dkel(ds, t, kel));
+            const float dose = roche_dose(ds, t, kel, sp[OFF_KL2]);
+            acc[R_KEL] += l3 * (dose - dose2 + kel * roche_dose_dkel(ds, t, kel, sp[OFF_KL2]));
         }
 #pragma unroll
         for (int j = 0; j < ML; ++j) {
@@ -232,7 +239,7 @@ struct Roche {
                 for (int d = 0; d < D_; ++d) a = fmaf(sp[OFF_W + j * D_ + d], y[d], a);
                 s = tanh_f(a);
             }
-            const float u = l[4 + j] * (1.0f - s * s);
+            const float u = l[4 + j] * fmaf(-s, s, 1.0f);
 #pragma unroll
             for (int d = 0; d < D_; ++d) {
                 gy[d] = fmaf(sp[OFF_W + j * D_ + d], u, gy[d]);
@@ -365,19 +372,20 @@ HODE_HD void fixed_step(const float* __restrict__ sp, const Dose& ds, float t0, 
         F::eval(sp, add_rn(t0, half_dt), ds, ym, k2);
 #pragma unroll
         for (int d = 0; d < D; ++d) y1[d] = y0[d] + dt * k2[d];
-    } else {  // 3/8 rule (tde rk4_alt_step_func)
+    } else {  // 3/8 rule (tde rk4_alt_step_func), written with fused multiply-adds
+        const float c13 = dt * HODE_ONE_THIRD, w1 = dt * 0.125f, w3 = dt * 0.375f;
         float yi[D], k2[D], k3[D], k4[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) yi[d] = y0[d] + dt * k1[d] * HODE_ONE_THIRD;
+        for (int d = 0; d < D; ++d) yi[d] = fmaf(c13, k1[d], y0[d]);
         F::eval(sp, add_rn(t0, mul_rn(dt, HODE_ONE_THIRD)), ds, yi, k2);
 #pragma unroll
-        for (int d = 0; d < D; ++d) yi[d] = y0[d] + dt * (k2[d] - k1[d] * HODE_ONE_THIRD);
+        for (int d = 0; d < D; ++d) yi[d] = fmaf(dt, k2[d], fmaf(-c13, k1[d], y0[d]));
         F::eval(sp, add_rn(t0, mul_rn(dt, HODE_TWO_THIRDS)), ds, yi, k3);
 #pragma unroll
-        for (int d = 0; d < D; ++d) yi[d] = y0[d] + dt * (k1[d] - k2[d] + k3[d]);
+        for (int d = 0; d < D; ++d) yi[d] = fmaf(dt, (k1[d] - k2[d]) + k3[d], y0[d]);
         F::eval(sp, perturb ? t_prev(t1) : t1, ds, yi, k4);
 #pragma unroll
-        for (int d = 0; d < D; ++d) y1[d] = y0[d] + (k1[d] + 3.0f * (k2[d] + k3[d]) + k4[d]) * dt * 0.125f;
+        for (int d = 0; d < D; ++d) y1[d] = fmaf(w1, k1[d] + k4[d], fmaf(w3, k2[d] + k3[d], y0[d]));
     }
 }
 
@@ -413,50 +421,50 @@ HODE_HD void fixed_step_vjp(const float* __restrict__ sp, const Dose& ds, float 
 #pragma unroll
         for (int d = 0; d < D; ++d) lam0[d] += g[d];
     } else {
-        // Butcher form of the 3/8 rule: A = [[],[1/3],[-1/3,1],[1,-1,1]], b = [1/8,3/8,3/8,1/8]
+        // Butcher form of the 3/8 rule: A = [[],[1/3],[-1/3,1],[1,-1,1]], b = [1/8,3/8,3/8,1/8].
+        // Stage inputs are rebuilt from k1..k3 when needed instead of being kept (register pressure).
         const float tb = add_rn(t0, mul_rn(dt, HODE_ONE_THIRD));
         const float tc = add_rn(t0, mul_rn(dt, HODE_TWO_THIRDS));
         const float td = perturb ? t_prev(t1) : t1;
-        float k1[D], k2[D], k3[D], Y2[D], Y3[D], Y4[D];
+        const float c13 = dt * HODE_ONE_THIRD, w1 = dt * 0.125f, w3 = dt * 0.375f;
+        float k1[D], k2[D], k3[D], Y[D], g4[D], g3[D];
         F::eval(sp, ta, ds, y0, k1);
 #pragma unroll
-        for (int d = 0; d < D; ++d) Y2[d] = y0[d] + dt * k1[d] * HODE_ONE_THIRD;
-        F::eval(sp, tb, ds, Y2, k2);
+        for (int d = 0; d < D; ++d) Y[d] = fmaf(c13, k1[d], y0[d]);
+        F::eval(sp, tb, ds, Y, k2);
 #pragma unroll
-        for (int d = 0; d < D; ++d) Y3[d] = y0[d] + dt * (k2[d] - k1[d] * HODE_ONE_THIRD);
-        F::eval(sp, tc, ds, Y3, k3);
-#pragma unroll
-        for (int d = 0; d < D; ++d) Y4[d] = y0[d] + dt * (k1[d] - k2[d] + k3[d]);
-        const float w1 = dt * 0.125f, w3 = dt * 0.375f, third = dt * HODE_ONE_THIRD;
-        float kb1[D], kb2[D];
-        // stage 4
-#pragma unroll
-        for (int d = 0; d < D; ++d) kb[d] = w1 * lam1[d];
-        F::template vjp<EG>(sp, td, ds, Y4, nullptr, kb, g, acc);
+        for (int d = 0; d < D; ++d) Y[d] = fmaf(dt, k2[d], fmaf(-c13, k1[d], y0[d]));
+        F::eval(sp, tc, ds, Y, k3);
+        // stage 4: kb4 = b4 dt lam1
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            lam0[d] = lam1[d] + g[d];
-            kb[d] = w3 * lam1[d] + dt * g[d];   // k3 adjoint
-            kb2[d] = w3 * lam1[d] - dt * g[d];  // k2 adjoint (partial)
-            kb1[d] = w1 * lam1[d] + dt * g[d];  // k1 adjoint (partial)
+            Y[d] = fmaf(dt, (k1[d] - k2[d]) + k3[d], y0[d]);
+            kb[d] = w1 * lam1[d];
         }
-        // stage 3
-        F::template vjp<EG>(sp, tc, ds, Y3, k3, kb, g, acc);
+        F::template vjp<EG>(sp, td, ds, Y, nullptr, kb, g4, acc);
+        // stage 3: kb3 = b3 dt lam1 + a43 dt g4
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            lam0[d] = lam1[d] + g4[d];
+            Y[d] = fmaf(dt, k2[d], fmaf(-c13, k1[d], y0[d]));
+            kb[d] = fmaf(dt, g4[d], w3 * lam1[d]);
+        }
+        F::template vjp<EG>(sp, tc, ds, Y, k3, kb, g3, acc);
+        // stage 2: kb2 = b2 dt lam1 + a42 dt g4 + a32 dt g3 = 3/8 dt lam1 + dt (g3 - g4)
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            lam0[d] += g3[d];
+            Y[d] = fmaf(c13, k1[d], y0[d]);
+            kb[d] = fmaf(dt, g3[d] - g4[d], w3 * lam1[d]);
+        }
+        F::template vjp<EG>(sp, tb, ds, Y, k2, kb, g, acc);
+        // stage 1: kb1 = b1 dt lam1 + a41 dt g4 + a31 dt g3 + a21 dt g2 = 1/8 dt lam1 + dt g4 + dt/3 (g2 - g3)
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             lam0[d] += g[d];
-            kb2[d] += dt * g[d];
-            kb1[d] -= third * g[d];
+            kb[d] = fmaf(c13, g[d] - g3[d], fmaf(dt, g4[d], w1 * lam1[d]));
         }
-        // stage 2
-        F::template vjp<EG>(sp, tb, ds, Y2, k2, kb2, g, acc);
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            lam0[d] += g[d];
-            kb1[d] += third * g[d];
-        }
-        // stage 1
-        F::template vjp<EG>(sp, ta, ds, y0, k1, kb1, g, acc);
+        F::template vjp<EG>(sp, ta, ds, y0, k1, kb, g, acc);
 #pragma unroll
         for (int d = 0; d < D; ++d) lam0[d] += g[d];
     }
