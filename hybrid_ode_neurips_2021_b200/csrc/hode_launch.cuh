@@ -9,6 +9,9 @@
 
 #include "hode_bodies.cuh"
 
+#ifndef HODE_BWD_MINBLOCKS
+#define HODE_BWD_MINBLOCKS 1
+#endif
 #ifndef HODE_DOPRI5_MAX_THREADS
 #define HODE_DOPRI5_MAX_THREADS 512
 #endif
@@ -137,7 +140,7 @@ __global__ void __launch_bounds__(128) fixed_fwd_kernel(const SolveArgs a, int t
 }
 
 template <class F, int METHOD, bool EG, int ND>
-__global__ void __launch_bounds__(128) fixed_bwd_kernel(const SolveArgs a, int tiles_per_group) {
+__global__ void __launch_bounds__(128, HODE_BWD_MINBLOCKS) fixed_bwd_kernel(const SolveArgs a, int tiles_per_group) {
     extern __shared__ float smem[];
     float* sp = smem;
     float* sred = smem + F::SP;
