@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(HERE, LIB_NAME)
 FIELD_ROCHE, FIELD_NEURAL = 0, 1
 EULER, MIDPOINT, RK4_38, DOPRI5 = 0, 1, 2, 3
 CTRL_BATCH, CTRL_TRAJ = 0, 1
+FLAG_HILL2 = 1
 METHODS = {"euler": EULER, "midpoint": MIDPOINT, "rk4": RK4_38, "dopri5": DOPRI5}
 SOLVE_OK, SOLVE_DT_UNDERFLOW, SOLVE_NONFINITE, SOLVE_MAX_STEPS, SOLVE_TAPE_FULL = 0, 1, 2, 3, 4
 OK, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = 0, -1, -2, -3, -4
@@ -31,7 +32,7 @@ class HodeCfg(C.Structure):
         ("perturb", C.c_int32),
         ("n_dose", C.c_int32),
         ("expert_grads", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("flags", C.c_int32),
         ("rtol", C.c_double),
         ("atol", C.c_double),
         ("safety", C.c_double),

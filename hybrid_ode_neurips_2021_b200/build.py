@@ -40,7 +40,9 @@ def _units():
     """(object name, source, extra defines)"""
     units = [("hode_api.o", "hode_api.cu", []), ("hode_aux.o", "hode_aux.cu", [])]
     for d in ROCHE_DIMS:
-        units.append(("inst_roche_d{}.o".format(d), "inst_roche.cu", ["-DHODE_INST_D={}".format(d)]))
+        for hill2 in (0, 1):
+            units.append(("inst_roche_d{}_h{}.o".format(d, hill2), "inst_roche.cu",
+                          ["-DHODE_INST_D={}".format(d), "-DHODE_INST_HILL2={}".format(hill2)]))
     if os.path.exists(os.path.join(CSRC, "inst_neural.cu")):
         for d in NEURAL_DIMS:
             units.append(("inst_neural_d{}.o".format(d), "inst_neural.cu", ["-DHODE_INST_D={}".format(d)]))

@@ -43,11 +43,12 @@ static bool roche_dim_ok(int d) { return d == 4 || d == 6 || d == 8 || d == 12; 
 static int dispatch(Op op, const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) {
     int rc = -1;
     if (cfg.field == HODE_FIELD_ROCHE) {
+        const bool hill2 = (cfg.flags & HODE_FLAG_HILL2) != 0;
         switch (cfg.latent_dim) {
-            case 4: rc = run<Roche<4>>(op, cfg, a, st); break;
-            case 6: rc = run<Roche<6>>(op, cfg, a, st); break;
-            case 8: rc = run<Roche<8>>(op, cfg, a, st); break;
-            case 12: rc = run<Roche<12>>(op, cfg, a, st); break;
+            case 4: rc = hill2 ? run<Roche<4, true>>(op, cfg, a, st) : run<Roche<4>>(op, cfg, a, st); break;
+            case 6: rc = hill2 ? run<Roche<6, true>>(op, cfg, a, st) : run<Roche<6>>(op, cfg, a, st); break;
+            case 8: rc = hill2 ? run<Roche<8, true>>(op, cfg, a, st) : run<Roche<8>>(op, cfg, a, st); break;
+            case 12: rc = hill2 ? run<Roche<12, true>>(op, cfg, a, st) : run<Roche<12>>(op, cfg, a, st); break;
             default: return fail(HODE_ERR_UNSUPPORTED, "RocheODE latent_dim %s%lld is not compiled in (4, 6, 8, 12)", "", cfg.latent_dim);
         }
     } else if (cfg.field == HODE_FIELD_NEURAL) {

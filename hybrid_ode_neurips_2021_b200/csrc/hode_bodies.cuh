@@ -85,13 +85,17 @@ HODE_HD void store_vec(float* __restrict__ p, const float (&v)[D]) {
 // ==============================================================================================================
 // fixed grid (tde solvers.py FixedGridODESolver.integrate)
 // ==============================================================================================================
-template <class F, int METHOD, class Dose>
-HODE_HD void fixed_fwd_traj(const SolveArgs& a, const float* __restrict__ sp, const Dose& ds, int64_t idx) {
+template <class F, int METHOD, class PS, class Dose>
+HODE_HD void fixed_fwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t idx) {
     constexpr int D = F::D;
     const int64_t n_traj = a.n_groups * a.batch;
     float y[D], y1[D];
     load_vec<D>(a.y0 + idx * D, y);
     store_vec<D>(a.h_out + idx * D, y);  // solution[0] = y0
+    if (!F::params_ok(sp)) {  // kernel variant and parameters disagree (hode_cfg.flags): fail loudly
+#pragma unroll
+        for (int d = 0; d < D; ++d) y[d] = nanf("");
+    }
     int j = 1;
     const bool perturb = a.perturb != 0;
     for (int s = 0; s + 1 < a.n_grid; ++s) {
@@ -120,8 +124,8 @@ HODE_HD void fixed_fwd_traj(const SolveArgs& a, const float* __restrict__ sp, co
     }
 }
 
-template <class F, int METHOD, bool EG, class Dose>
-HODE_HD void fixed_bwd_traj(const SolveArgs& a, const float* __restrict__ sp, const Dose& ds, int64_t idx,
+template <class F, int METHOD, bool EG, class PS, class Dose>
+HODE_HD void fixed_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t idx,
                             float* acc) {
     constexpr int D = F::D;
     const int64_t n_traj = a.n_groups * a.batch;
@@ -163,6 +167,10 @@ HODE_HD void fixed_bwd_traj(const SolveArgs& a, const float* __restrict__ sp, co
     load_vec<D>(a.grad_h + idx * D, g0);
 #pragma unroll
     for (int d = 0; d < D; ++d) lam[d] += g0[d];
+    if (!F::params_ok(sp)) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) lam[d] = nanf("");
+    }
     store_vec<D>(a.grad_y0 + idx * D, lam);
 }
 
@@ -173,8 +181,8 @@ HODE_HD void fixed_bwd_traj(const SolveArgs& a, const float* __restrict__ sp, co
 //   ctrl   controller index (group or trajectory); leader writes the controller-level records
 //   count  number of state elements under one controller (batch*D or D): the RMS norm is over all of them
 // ==============================================================================================================
-template <class F, class Dose, class Comm>
-HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, const float* __restrict__ sp, const Dose& ds, int64_t idx,
+template <class F, class PS, class Dose, class Comm>
+HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds, int64_t idx,
                              bool valid, int64_t ctrl, bool leader, float count) {
     constexpr int D = F::D;
     const int64_t n_traj = a.n_groups * a.batch;
@@ -184,6 +192,11 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, const float* __restri
     float y0[D], y1[D], k[7][D];
     load_vec<D>(a.y0 + idx * D, y0);
     if (valid) store_vec<D>(a.h_out + idx * D, y0);
+    const bool poisoned = !F::params_ok(sp);  // kernel variant and parameters disagree: HODE_SOLVE_NONFINITE
+    if (poisoned) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) y0[d] = nanf("");
+    }
 
     double t0 = a.t_eval_d[0];
     const float t0f_init = (float)t0;
@@ -245,6 +258,7 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, const float* __restri
 
     while (j < a.n_t) {
         // _advance(t[j]): while next_t > rk_state.t1 -> _adaptive_step
+        if (poisoned) { status = HODE_SOLVE_NONFINITE; break; }
         if (n_steps >= a.max_num_steps || attempts >= a.attempt_cap) { status = HODE_SOLVE_MAX_STEPS; break; }
         if (!(t0 + dt > t0)) { status = HODE_SOLVE_DT_UNDERFLOW; break; }
         if (y0_bad) { status = HODE_SOLVE_NONFINITE; break; }
@@ -333,8 +347,8 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, const float* __restri
 // dopri5 reverse sweep over the tape (discrete adjoint of the accepted-step map with constant step sizes, through
 // FSAL and the quartic dense output).  SURVEY.md Appendix D.4.
 // ==============================================================================================================
-template <class F, bool EG, class Dose>
-HODE_HD void dopri5_bwd_traj(const SolveArgs& a, const float* __restrict__ sp, const Dose& ds, int64_t idx,
+template <class F, bool EG, class PS, class Dose>
+HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t idx,
                              int64_t ctrl, float* acc) {
     constexpr int D = F::D;
     const int64_t n_traj = a.n_groups * a.batch;
@@ -426,6 +440,10 @@ HODE_HD void dopri5_bwd_traj(const SolveArgs& a, const float* __restrict__ sp, c
     load_vec<D>(a.grad_h + idx * D, g0);
 #pragma unroll
     for (int d = 0; d < D; ++d) lam[d] += g0[d];
+    if (!F::params_ok(sp)) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) lam[d] = nanf("");
+    }
     store_vec<D>(a.grad_y0 + idx * D, lam);
 }
 

@@ -62,10 +62,22 @@ HODE_D float tanh_f(float x) { return fmaf(-2.0f, rcp_approx(ex2_approx(x * 2.88
 // exp(kel * d) with kl2 = kel * log2(e) pre-multiplied
 HODE_D float exp_scaled(float kl2, float /*kel*/, float d) { return ex2_approx(kl2 * d); }
 HODE_D float rcp_f(float x) { return rcp_approx(x); }
+// tanh of a pre-scaled argument: xs = x * 2 log2(e).  The RocheODE kernels fold the factor into the staged ml_net
+// weights, which removes one multiply per hidden unit per evaluation.
+#define HODE_FOLD_TANH 1
+HODE_D float tanh_pre(float xs) { return fmaf(-2.0f, rcp_approx(ex2_approx(xs) + 1.0f), 1.0f); }
 #else
+#define HODE_FOLD_TANH 0
+HODE_HD float tanh_pre(float x) { return tanhf(x); }
 HODE_HD float tanh_f(float x) { return tanhf(x); }
 HODE_HD float exp_scaled(float /*kl2*/, float kel, float d) { return expf(mul_rn(kel, d)); }
 HODE_HD float rcp_f(float x) { return 1.0f / x; }
+#endif
+
+#if HODE_FOLD_TANH
+static constexpr float kTanhPre = 2.8853900817779268f, kTanhPreInv = 0.34657359027997264f;
+#else
+static constexpr float kTanhPre = 1.0f, kTanhPreInv = 1.0f;
 #endif
 
 // x ** p with a float32 tensor exponent (model.py:529, 537-538).  p == 2 (RochConfig default) is a multiply.
@@ -144,9 +156,10 @@ enum RocheIdx {
     R_NSCALAR
 };
 
-template <int D_>
+template <int D_, bool HILL2_ = false>
 struct Roche {
     static constexpr int D = D_;
+    static constexpr bool HILL2 = HILL2_;  // caller guarantees HillCure == HillPatho == 2 (checked on the device)
     static constexpr int ML = D_ - 4;
     static constexpr int P = R_NSCALAR + ML * D_ + ML;  // packed parameter count
     static constexpr int OFF_W = R_NSCALAR;
@@ -156,24 +169,31 @@ struct Roche {
     static constexpr int OFF_KL2 = P + 1;   // kel * log2(e)
     static constexpr int SP = P + 2;
     static constexpr bool kAccInRegs = true;  // per-thread gradient accumulators fit in registers
+    static constexpr bool kConstBank = true;  // staged parameters may be read from the constant bank (hode_launch.cuh)
 
-    // cooperative copy of one packed parameter set into the staged layout (thread `tid` of `nthr`)
+    // cooperative copy of one packed parameter set into the staged layout (thread `tid` of `nthr`).
+    // With HODE_FOLD_TANH the ml_net weights and biases are pre-multiplied by 2 log2(e): W y + b is then directly the
+    // argument of the ex2 inside tanh_pre().
     HODE_HD static void stage(const float* __restrict__ src, float* sp, int tid, int nthr) {
-        for (int i = tid; i < P; i += nthr) sp[i] = src[i];
+        for (int i = tid; i < P; i += nthr) sp[i] = (i >= OFF_W) ? src[i] * kTanhPre : src[i];
     }
     HODE_HD static void prepare(float* sp) {
         sp[OFF_ECP] = pow_hill(sp[R_EC50], sp[R_HP]);
         sp[OFF_KL2] = sp[R_KEL] * 1.4426950408889634f;
     }
+    // false if this instantiation may not be used with the staged parameters (HILL2 kernels with other exponents)
+    template <class PS>
+    HODE_HD static bool params_ok(PS sp) { return !HILL2 || (sp[R_HC] == 2.0f && sp[R_HP] == 2.0f); }
+    HODE_HD static float hpow(float x, float p) { return HILL2 ? x * x : pow_hill(x, p); }
+    HODE_HD static float hdpow(float x, float p) { return HILL2 ? 2.0f * x : dpow_hill(x, p); }
 
     // f(t, y).  Same terms as model.py:527-544, factored to minimise issue slots (the kernels are issue-bound):
     //   dx1 = D (kp - I^hc kdi - R kdr);  dx2 = D (kid + R kfb) - R (koff + Q kdexa) + R^hp emax / (ec50^hp + R^hp)
-    template <class Dose>
-    HODE_HD static void eval(const float* __restrict__ sp, float t, const Dose& ds, const float (&y)[D_],
-                             float (&dy)[D_]) {
+    template <class PS, class Dose>
+    HODE_HD static void eval(PS sp, float t, const Dose& ds, const float (&y)[D_], float (&dy)[D_]) {
         const float dis = y[0], react = y[1], imm = y[2], dose2 = y[3];
-        const float ip = pow_hill(imm, sp[R_HC]);
-        const float rp = pow_hill(react, sp[R_HP]);
+        const float ip = hpow(imm, sp[R_HC]);
+        const float rp = hpow(react, sp[R_HP]);
         dy[0] = dis * fmaf(-react, sp[R_KDCIR], fmaf(-ip, sp[R_KDCI], sp[R_KDISPROG]));
         const float hill = (rp * sp[R_EMAX]) * rcp_f(sp[OFF_ECP] + rp);
         dy[1] = fmaf(dis, fmaf(react, sp[R_KFB], sp[R_KID]), fmaf(-react, fmaf(dose2, sp[R_KDEXA], sp[R_KOFF]), hill));
@@ -184,28 +204,28 @@ struct Roche {
             float a = sp[OFF_B + j];
 #pragma unroll
             for (int d = 0; d < D_; ++d) a = fmaf(sp[OFF_W + j * D_ + d], y[d], a);
-            dy[4 + j] = tanh_f(a);
+            dy[4 + j] = tanh_pre(a);
         }
     }
 
     // gy = J^T l ; acc += d<l, f>/dtheta.  `k` (may be null) is f(t, y) if the caller already has it: its ML part is
     // tanh(W y + b), which is all the MLP backward needs.  EG: also accumulate the 13 expert scalars.
-    template <bool EG, class Dose>
-    HODE_HD static void vjp(const float* __restrict__ sp, float t, const Dose& ds, const float (&y)[D_],
-                            const float* k, const float (&l)[D_], float (&gy)[D_], float* acc) {
+    template <bool EG, class PS, class Dose>
+    HODE_HD static void vjp(PS sp, float t, const Dose& ds, const float (&y)[D_], const float* k,
+                            const float (&l)[D_], float (&gy)[D_], float* acc) {
         const float dis = y[0], react = y[1], imm = y[2], dose2 = y[3];
         const float hc = sp[R_HC], hp = sp[R_HP], em = sp[R_EMAX], ecp = sp[OFF_ECP];
         const float kdci = sp[R_KDCI], kdcir = sp[R_KDCIR], kfb = sp[R_KFB], kdexa = sp[R_KDEXA];
         const float kel = sp[R_KEL];
-        const float ip = pow_hill(imm, hc);
-        const float rp = pow_hill(react, hp);
+        const float ip = hpow(imm, hc);
+        const float rp = hpow(react, hp);
         const float inv_den = rcp_f(ecp + rp);
         const float l0 = l[0], l1 = l[1], l2 = l[2], l3 = l[3];
         const float l0d = l0 * dis;
-        const float hill_d = (em * ecp) * dpow_hill(react, hp) * (inv_den * inv_den);  // d/dR of the Hill term
+        const float hill_d = (em * ecp) * hdpow(react, hp) * (inv_den * inv_den);  // d/dR of the Hill term
         gy[0] = fmaf(l0, fmaf(-react, kdcir, fmaf(-ip, kdci, sp[R_KDISPROG])), l1 * fmaf(react, kfb, sp[R_KID]));
         gy[1] = fmaf(-l0d, kdcir, fmaf(l1, fmaf(dis, kfb, hill_d) - fmaf(dose2, kdexa, sp[R_KOFF]), l2 * sp[R_KIM]));
-        gy[2] = -l0d * kdci * dpow_hill(imm, hc);
+        gy[2] = -l0d * kdci * hdpow(imm, hc);
         gy[3] = fmaf(-l1 * react, kdexa, -l3 * kel);
 #pragma unroll
         for (int d = 4; d < D_; ++d) gy[d] = 0.0f;
@@ -237,12 +257,13 @@ struct Roche {
                 float a = sp[OFF_B + j];
 #pragma unroll
                 for (int d = 0; d < D_; ++d) a = fmaf(sp[OFF_W + j * D_ + d], y[d], a);
-                s = tanh_f(a);
+                s = tanh_pre(a);
             }
             const float u = l[4 + j] * fmaf(-s, s, 1.0f);
+            const float uw = u * kTanhPreInv;  // the staged weights carry the factor kTanhPre
 #pragma unroll
             for (int d = 0; d < D_; ++d) {
-                gy[d] = fmaf(sp[OFF_W + j * D_ + d], u, gy[d]);
+                gy[d] = fmaf(sp[OFF_W + j * D_ + d], uw, gy[d]);
                 acc[OFF_W + j * D_ + d] = fmaf(u, y[d], acc[OFF_W + j * D_ + d]);
             }
             acc[OFF_B + j] += u;
@@ -269,6 +290,7 @@ struct Neural {
     static constexpr int OFF_W2 = OFF_B1 + H;
     static constexpr int OFF_B2 = OFF_W2 + D_ * H;
     static constexpr bool kAccInRegs = false;  // P is 846..3132: accumulators live in local memory
+    static constexpr bool kConstBank = false;
 
     HODE_HD static void stage(const float* __restrict__ src, float* sp, int tid, int nthr) {
         for (int e = tid; e < H * R; e += nthr) {
@@ -282,6 +304,9 @@ struct Neural {
         for (int d = tid; d < D_; d += nthr) sp[H * R + d] = src[OFF_B2 + d];
     }
     HODE_HD static void prepare(float*) {}
+
+    template <class PS>
+    HODE_HD static bool params_ok(PS) { return true; }
 
     template <class Dose>
     HODE_HD static void eval(const float* __restrict__ sp, float t, const Dose& ds, const float (&y)[D_],
@@ -355,8 +380,8 @@ enum Method { M_EULER = 0, M_MIDPOINT = 1, M_RK4_38 = 2, M_DOPRI5 = 3 };
 #define HODE_ONE_THIRD ((float)(1.0 / 3.0))
 #define HODE_TWO_THIRDS ((float)(2.0 / 3.0))
 
-template <class F, int METHOD, class Dose>
-HODE_HD void fixed_step(const float* __restrict__ sp, const Dose& ds, float t0, float t1, float dt, bool perturb,
+template <class F, int METHOD, class PS, class Dose>
+HODE_HD void fixed_step(PS sp, const Dose& ds, float t0, float t1, float dt, bool perturb,
                         const float (&y0)[F::D], float (&y1)[F::D]) {
     constexpr int D = F::D;
     float k1[D];
@@ -391,8 +416,8 @@ HODE_HD void fixed_step(const float* __restrict__ sp, const Dose& ds, float t0, 
 
 // reverse of one fixed-grid step:  lam0 = lam1 + (d dy/d y0)^T lam1 ; acc += (d dy/d theta)^T lam1.
 // Stages are recomputed from y0 (the tape holds only the state at the start of the step).
-template <class F, int METHOD, bool EG, class Dose>
-HODE_HD void fixed_step_vjp(const float* __restrict__ sp, const Dose& ds, float t0, float t1, float dt, bool perturb,
+template <class F, int METHOD, bool EG, class PS, class Dose>
+HODE_HD void fixed_step_vjp(PS sp, const Dose& ds, float t0, float t1, float dt, bool perturb,
                             const float (&y0)[F::D], const float (&lam1)[F::D], float (&lam0)[F::D], float* acc) {
     constexpr int D = F::D;
     const float ta = perturb ? t_next(t0) : t0;
@@ -513,8 +538,8 @@ HODE_HD double optimal_step(double last, float ratio, double safety, double ifac
 }
 
 // The 7 stages of one attempt.  k[0] must hold f0 on entry.  On exit k[1..6] are filled and y1 is the last stage input.
-template <class F, class Dose>
-HODE_HD void dopri5_stages(const float* __restrict__ sp, const Dose& ds, const Dopri5Tab& T, float t0f, float dtf,
+template <class F, class PS, class Dose>
+HODE_HD void dopri5_stages(PS sp, const Dose& ds, const Dopri5Tab& T, float t0f, float dtf,
                            float t1f, const float (&y0)[F::D], float (&k)[7][F::D], float (&y1)[F::D]) {
     constexpr int D = F::D;
 #pragma unroll

@@ -6,9 +6,15 @@
 // groups, so a CTA has exactly one parameter set and (dopri5, batch-coupled) one controller.
 #pragma once
 #include <cuda_runtime.h>
+#include <stdlib.h>
+
+#include <mutex>
 
 #include "hode_bodies.cuh"
 
+#ifndef HODE_FWD_MINBLOCKS
+#define HODE_FWD_MINBLOCKS 1
+#endif
 #ifndef HODE_BWD_MINBLOCKS
 #define HODE_BWD_MINBLOCKS 1
 #endif
@@ -42,6 +48,78 @@ struct CommCta {
         }
     }
 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// Constant-bank parameters.  When a launch has ONE parameter set (every reference call site: model.py:1116), the staged
+// RocheODE parameters are copied (device to device, stream-ordered) into this __constant__ array and the kernels read
+// them as c[bank][imm] operands of FFMA/FMUL: no shared-memory loads and, above all, no registers (36-117 floats that
+// ptxas otherwise keeps live across the whole solve).  Launches with several parameter sets stage into shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kConstParamMax = 128;  // >= Roche<12>::SP
+static __constant__ float c_params[kConstParamMax];
+static __device__ float g_param_stage[kConstParamMax];
+
+struct ParamConst {
+    __device__ __forceinline__ float operator[](int i) const { return c_params[i]; }
+};
+
+template <class F>
+__global__ void __launch_bounds__(128) prep_params_kernel(const float* __restrict__ src) {
+    F::stage(src, g_param_stage, (int)threadIdx.x, (int)blockDim.x);
+    __syncthreads();
+    if (threadIdx.x == 0) F::prepare(g_param_stage);
+}
+
+// The constant array is per-device state shared by every stream: a lease serialises its users (host mutex for the
+// bookkeeping, an event so that a launch on another stream waits until the previous user's kernel has finished).
+struct ConstParamLease {
+    static constexpr int kMaxDev = 64;
+    struct PerDevice { cudaEvent_t ev = nullptr; cudaStream_t last = nullptr; bool used = false; };
+    static std::mutex& mu() { static std::mutex m; return m; }
+    static PerDevice* slots() { static PerDevice s[kMaxDev]; return s; }
+    std::unique_lock<std::mutex> lock;
+    PerDevice* pd = nullptr;
+    cudaStream_t st;
+    int rc = 0;
+    template <class F>
+    ConstParamLease(F*, const float* params, cudaStream_t stream) : lock(mu()), st(stream) {
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess || dev < 0 || dev >= kMaxDev) { rc = (int)(e != cudaSuccess ? e : cudaErrorInvalidDevice); return; }
+        pd = &slots()[dev];
+        if (pd->ev == nullptr) {
+            e = cudaEventCreateWithFlags(&pd->ev, cudaEventDisableTiming);
+            if (e != cudaSuccess) { rc = (int)e; return; }
+        }
+        if (pd->used && pd->last != st) {
+            e = cudaStreamWaitEvent(st, pd->ev, 0);
+            if (e != cudaSuccess) { rc = (int)e; return; }
+        }
+        prep_params_kernel<F><<<1, 128, 0, st>>>(params);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) { rc = (int)e; return; }
+        void* stage_ptr = nullptr;
+        e = cudaGetSymbolAddress(&stage_ptr, g_param_stage);
+        if (e != cudaSuccess) { rc = (int)e; return; }
+        e = cudaMemcpyToSymbolAsync(c_params, stage_ptr, sizeof(float) * F::SP, 0, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) { rc = (int)e; return; }
+    }
+    // call after the consumer kernel has been enqueued
+    void done() {
+        if (pd != nullptr && rc == 0) {
+            cudaEventRecord(pd->ev, st);
+            pd->last = st;
+            pd->used = true;
+        }
+    }
+};
+
+inline bool const_params_enabled() {
+    static const bool on = getenv("HODE_NO_CONST_PARAMS") == nullptr;
+    return on;
+}
+template <class F>
+inline bool use_const_params(const SolveArgs& a) { return F::kConstBank && a.pset == nullptr && const_params_enabled(); }
 
 template <class F>
 __device__ __forceinline__ void stage_params(const SolveArgs& a, int64_t group, float* sp) {
@@ -123,53 +201,56 @@ __device__ __forceinline__ Tile tile_of(const SolveArgs& a, int tiles_per_group)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-template <class F, int METHOD, int ND>
-__global__ void __launch_bounds__(128) fixed_fwd_kernel(const SolveArgs a, int tiles_per_group) {
+// kernels.  CP: parameters come from the constant bank (ParamConst) instead of the CTA's shared-memory copy.
+// ---------------------------------------------------------------------------------------------------------------
+#define HODE_WITH_DOSE(ND, a, idx, CALL)                                                   \
+    do {                                                                                   \
+        if (ND > 0) {                                                                      \
+            const DoseReg<(ND > 0 ? ND : 1)> ds = load_dose_reg<(ND > 0 ? ND : 1)>(a, idx); \
+            CALL;                                                                          \
+        } else {                                                                           \
+            const DoseMem ds = load_dose_mem(a, idx);                                      \
+            CALL;                                                                          \
+        }                                                                                  \
+    } while (0)
+
+template <class F, int METHOD, int ND, bool CP>
+__global__ void __launch_bounds__(128, HODE_FWD_MINBLOCKS) fixed_fwd_kernel(const SolveArgs a, int tiles_per_group) {
     extern __shared__ float smem[];
     const Tile tl = tile_of(a, tiles_per_group);
-    stage_params<F>(a, tl.group, smem);
+    if constexpr (!CP) stage_params<F>(a, tl.group, smem);
     if (tl.b >= a.batch) return;
     const int64_t idx = tl.group * a.batch + tl.b;
-    if (ND > 0) {
-        const DoseReg<(ND > 0 ? ND : 1)> ds = load_dose_reg<(ND > 0 ? ND : 1)>(a, idx);
-        fixed_fwd_traj<F, METHOD>(a, smem, ds, idx);
-    } else {
-        const DoseMem ds = load_dose_mem(a, idx);
-        fixed_fwd_traj<F, METHOD>(a, smem, ds, idx);
-    }
+    if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (fixed_fwd_traj<F, METHOD>(a, ParamConst(), ds, idx))); }
+    else { HODE_WITH_DOSE(ND, a, idx, (fixed_fwd_traj<F, METHOD>(a, (const float*)smem, ds, idx))); }
 }
 
-template <class F, int METHOD, bool EG, int ND>
+template <class F, int METHOD, bool EG, int ND, bool CP>
 __global__ void __launch_bounds__(128, HODE_BWD_MINBLOCKS) fixed_bwd_kernel(const SolveArgs a, int tiles_per_group) {
     extern __shared__ float smem[];
     float* sp = smem;
-    float* sred = smem + F::SP;
+    float* sred = smem + (CP ? 0 : F::SP);
     const Tile tl = tile_of(a, tiles_per_group);
-    stage_params<F>(a, tl.group, sp);
+    if constexpr (!CP) stage_params<F>(a, tl.group, sp);
     float acc[F::P];
     zero_acc<F>(acc);
     if (tl.b < a.batch) {
         const int64_t idx = tl.group * a.batch + tl.b;
-        if (ND > 0) {
-            const DoseReg<(ND > 0 ? ND : 1)> ds = load_dose_reg<(ND > 0 ? ND : 1)>(a, idx);
-            fixed_bwd_traj<F, METHOD, EG>(a, sp, ds, idx, acc);
-        } else {
-            const DoseMem ds = load_dose_mem(a, idx);
-            fixed_bwd_traj<F, METHOD, EG>(a, sp, ds, idx, acc);
-        }
+        if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (fixed_bwd_traj<F, METHOD, EG>(a, ParamConst(), ds, idx, acc))); }
+        else { HODE_WITH_DOSE(ND, a, idx, (fixed_bwd_traj<F, METHOD, EG>(a, (const float*)sp, ds, idx, acc))); }
     }
     reduce_param_grads<F>(a, tl.group, acc, sred);
 }
 
 // MAXT: launch bound.  128 for per-trajectory control and small groups (up to 255 registers per thread);
 // HODE_DOPRI5_MAX_THREADS for a batch-coupled group that needs a whole large CTA (128 registers per thread).
-template <class F, bool PER_TRAJ, int ND, int MAXT>
+template <class F, bool PER_TRAJ, int ND, int MAXT, bool CP>
 __global__ void __launch_bounds__(MAXT) dopri5_fwd_kernel(const SolveArgs a, int tiles_per_group) {
     extern __shared__ float smem[];
     float* sp = smem;
-    float* red = smem + F::SP;
+    float* red = smem + (CP ? 0 : F::SP);
     const Tile tl = tile_of(a, tiles_per_group);
-    stage_params<F>(a, tl.group, sp);
+    if constexpr (!CP) stage_params<F>(a, tl.group, sp);
     const bool valid = tl.b < a.batch;
     if (PER_TRAJ && !valid) return;
     const int64_t b = valid ? tl.b : (a.batch - 1);
@@ -177,36 +258,31 @@ __global__ void __launch_bounds__(MAXT) dopri5_fwd_kernel(const SolveArgs a, int
     const int64_t ctrl = PER_TRAJ ? idx : tl.group;
     const bool leader = PER_TRAJ ? true : (threadIdx.x == 0);
     const float count = PER_TRAJ ? (float)F::D : (float)(a.batch * F::D);
-    if (ND > 0) {
-        const DoseReg<(ND > 0 ? ND : 1)> ds = load_dose_reg<(ND > 0 ? ND : 1)>(a, idx);
-        if (PER_TRAJ) { CommNone cm; dopri5_fwd_traj<F>(a, cm, sp, ds, idx, valid, ctrl, leader, count); }
-        else { CommCta cm{red, (int)(blockDim.x >> 5)}; dopri5_fwd_traj<F>(a, cm, sp, ds, idx, valid, ctrl, leader, count); }
+    if (PER_TRAJ) {
+        CommNone cm;
+        if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F>(a, cm, ParamConst(), ds, idx, valid, ctrl, leader, count))); }
+        else { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F>(a, cm, (const float*)sp, ds, idx, valid, ctrl, leader, count))); }
     } else {
-        const DoseMem ds = load_dose_mem(a, idx);
-        if (PER_TRAJ) { CommNone cm; dopri5_fwd_traj<F>(a, cm, sp, ds, idx, valid, ctrl, leader, count); }
-        else { CommCta cm{red, (int)(blockDim.x >> 5)}; dopri5_fwd_traj<F>(a, cm, sp, ds, idx, valid, ctrl, leader, count); }
+        CommCta cm{red, (int)(blockDim.x >> 5)};
+        if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F>(a, cm, ParamConst(), ds, idx, valid, ctrl, leader, count))); }
+        else { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F>(a, cm, (const float*)sp, ds, idx, valid, ctrl, leader, count))); }
     }
 }
 
-template <class F, bool EG, int ND>
+template <class F, bool EG, int ND, bool CP>
 __global__ void __launch_bounds__(128) dopri5_bwd_kernel(const SolveArgs a, int tiles_per_group) {
     extern __shared__ float smem[];
     float* sp = smem;
-    float* sred = smem + F::SP;
+    float* sred = smem + (CP ? 0 : F::SP);
     const Tile tl = tile_of(a, tiles_per_group);
-    stage_params<F>(a, tl.group, sp);
+    if constexpr (!CP) stage_params<F>(a, tl.group, sp);
     float acc[F::P];
     zero_acc<F>(acc);
     if (tl.b < a.batch) {
         const int64_t idx = tl.group * a.batch + tl.b;
         const int64_t ctrl = a.per_traj ? idx : tl.group;
-        if (ND > 0) {
-            const DoseReg<(ND > 0 ? ND : 1)> ds = load_dose_reg<(ND > 0 ? ND : 1)>(a, idx);
-            dopri5_bwd_traj<F, EG>(a, sp, ds, idx, ctrl, acc);
-        } else {
-            const DoseMem ds = load_dose_mem(a, idx);
-            dopri5_bwd_traj<F, EG>(a, sp, ds, idx, ctrl, acc);
-        }
+        if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, ParamConst(), ds, idx, ctrl, acc))); }
+        else { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, (const float*)sp, ds, idx, ctrl, acc))); }
     }
     reduce_param_grads<F>(a, tl.group, acc, sred);
 }
@@ -222,20 +298,37 @@ inline int round_up32(int64_t n) { return (int)(((n + 31) / 32) * 32); }
         if (e_ != cudaSuccess) return (int)e_;                \
     } while (0)
 
+// Runs `LAUNCH(CPFLAG)` with CPFLAG = true behind a constant-bank lease when the launch qualifies, else CPFLAG = false.
+#define HODE_DISPATCH_CP(F, a, st, LAUNCH)                               \
+    do {                                                                 \
+        if constexpr (F::kConstBank) {                                   \
+            if (use_const_params<F>(a)) {                                \
+                ConstParamLease lease((F*)nullptr, a.params, st);        \
+                if (lease.rc != 0) return lease.rc;                      \
+                LAUNCH(true);                                            \
+                lease.done();                                            \
+                break;                                                   \
+            }                                                            \
+        }                                                                \
+        LAUNCH(false);                                                   \
+    } while (0)
+
 template <class F>
 int launch_fixed_fwd(const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) {
     const int threads = a.batch >= 128 ? 128 : round_up32(a.batch);
     const int tiles = (int)((a.batch + threads - 1) / threads);
     const int64_t nblk = a.n_groups * tiles;
-    const size_t sh = F::SP * sizeof(float);
-#define HODE_FF(M, ND) fixed_fwd_kernel<F, M, ND><<<(unsigned)nblk, threads, sh, st>>>(a, tiles)
     const bool nd1 = cfg.n_dose == 1;
-    switch (cfg.method) {
-        case HODE_EULER: if (nd1) HODE_FF(M_EULER, 1); else HODE_FF(M_EULER, 0); break;
-        case HODE_MIDPOINT: if (nd1) HODE_FF(M_MIDPOINT, 1); else HODE_FF(M_MIDPOINT, 0); break;
-        case HODE_RK4_38: if (nd1) HODE_FF(M_RK4_38, 1); else HODE_FF(M_RK4_38, 0); break;
-        default: return -1;
+#define HODE_FF(M, ND, CP) fixed_fwd_kernel<F, M, ND, CP><<<(unsigned)nblk, threads, (CP ? 0 : F::SP) * sizeof(float), st>>>(a, tiles)
+#define HODE_FF_CP(CP)                                                                                   \
+    switch (cfg.method) {                                                                                \
+        case HODE_EULER: if (nd1) HODE_FF(M_EULER, 1, CP); else HODE_FF(M_EULER, 0, CP); break;          \
+        case HODE_MIDPOINT: if (nd1) HODE_FF(M_MIDPOINT, 1, CP); else HODE_FF(M_MIDPOINT, 0, CP); break; \
+        case HODE_RK4_38: if (nd1) HODE_FF(M_RK4_38, 1, CP); else HODE_FF(M_RK4_38, 0, CP); break;       \
+        default: return -1;                                                                              \
     }
+    HODE_DISPATCH_CP(F, a, st, HODE_FF_CP);
+#undef HODE_FF_CP
 #undef HODE_FF
     HODE_LAUNCH_CHECK();
     return 0;
@@ -246,22 +339,25 @@ int launch_fixed_bwd(const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) {
     const int threads = a.batch >= 128 ? 128 : round_up32(a.batch);
     const int tiles = (int)((a.batch + threads - 1) / threads);
     const int64_t nblk = a.n_groups * tiles;
-    const size_t sh = (F::SP + F::P) * sizeof(float);
     const bool nd1 = cfg.n_dose == 1;
     const bool eg = cfg.expert_grads != 0;
-#define HODE_FB(M)                                                                                          \
-    do {                                                                                                    \
-        if (eg) { if (nd1) fixed_bwd_kernel<F, M, true, 1><<<(unsigned)nblk, threads, sh, st>>>(a, tiles);  \
-                  else fixed_bwd_kernel<F, M, true, 0><<<(unsigned)nblk, threads, sh, st>>>(a, tiles); }    \
-        else    { if (nd1) fixed_bwd_kernel<F, M, false, 1><<<(unsigned)nblk, threads, sh, st>>>(a, tiles); \
-                  else fixed_bwd_kernel<F, M, false, 0><<<(unsigned)nblk, threads, sh, st>>>(a, tiles); }   \
+#define HODE_FB(M, EG, ND, CP) \
+    fixed_bwd_kernel<F, M, EG, ND, CP><<<(unsigned)nblk, threads, ((CP ? 0 : F::SP) + F::P) * sizeof(float), st>>>(a, tiles)
+#define HODE_FB_M(M, CP)                                                           \
+    do {                                                                           \
+        if (eg) { if (nd1) HODE_FB(M, true, 1, CP); else HODE_FB(M, true, 0, CP); } \
+        else    { if (nd1) HODE_FB(M, false, 1, CP); else HODE_FB(M, false, 0, CP); } \
     } while (0)
-    switch (cfg.method) {
-        case HODE_EULER: HODE_FB(M_EULER); break;
-        case HODE_MIDPOINT: HODE_FB(M_MIDPOINT); break;
-        case HODE_RK4_38: HODE_FB(M_RK4_38); break;
-        default: return -1;
+#define HODE_FB_CP(CP)                                      \
+    switch (cfg.method) {                                   \
+        case HODE_EULER: HODE_FB_M(M_EULER, CP); break;     \
+        case HODE_MIDPOINT: HODE_FB_M(M_MIDPOINT, CP); break; \
+        case HODE_RK4_38: HODE_FB_M(M_RK4_38, CP); break;   \
+        default: return -1;                                 \
     }
+    HODE_DISPATCH_CP(F, a, st, HODE_FB_CP);
+#undef HODE_FB_CP
+#undef HODE_FB_M
 #undef HODE_FB
     HODE_LAUNCH_CHECK();
     return 0;
@@ -270,24 +366,21 @@ int launch_fixed_bwd(const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) {
 template <class F>
 int launch_dopri5_fwd(const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) {
     const bool nd1 = cfg.n_dose == 1;
-    const size_t sh = (F::SP + 64) * sizeof(float);
-    if (a.per_traj) {
-        const int threads = a.batch >= 128 ? 128 : round_up32(a.batch);
-        const int tiles = (int)((a.batch + threads - 1) / threads);
-        const int64_t nblk = a.n_groups * tiles;
-        if (nd1) dopri5_fwd_kernel<F, true, 1, 128><<<(unsigned)nblk, threads, sh, st>>>(a, tiles);
-        else dopri5_fwd_kernel<F, true, 0, 128><<<(unsigned)nblk, threads, sh, st>>>(a, tiles);
-    } else {
-        if (a.batch > HODE_DOPRI5_MAX_THREADS) return -2;
-        const int threads = round_up32(a.batch);
-        if (threads <= 128) {
-            if (nd1) dopri5_fwd_kernel<F, false, 1, 128><<<(unsigned)a.n_groups, threads, sh, st>>>(a, 1);
-            else dopri5_fwd_kernel<F, false, 0, 128><<<(unsigned)a.n_groups, threads, sh, st>>>(a, 1);
-        } else {
-            if (nd1) dopri5_fwd_kernel<F, false, 1, HODE_DOPRI5_MAX_THREADS><<<(unsigned)a.n_groups, threads, sh, st>>>(a, 1);
-            else dopri5_fwd_kernel<F, false, 0, HODE_DOPRI5_MAX_THREADS><<<(unsigned)a.n_groups, threads, sh, st>>>(a, 1);
-        }
-    }
+    if (!a.per_traj && a.batch > HODE_DOPRI5_MAX_THREADS) return -2;
+    const int threads = a.per_traj ? (a.batch >= 128 ? 128 : round_up32(a.batch)) : round_up32(a.batch);
+    const int tiles = a.per_traj ? (int)((a.batch + threads - 1) / threads) : 1;
+    const int64_t nblk = a.n_groups * tiles;
+#define HODE_DF(PT, ND, MAXT, CP) \
+    dopri5_fwd_kernel<F, PT, ND, MAXT, CP><<<(unsigned)nblk, threads, ((CP ? 0 : F::SP) + 64) * sizeof(float), st>>>(a, tiles)
+#define HODE_DF_CP(CP)                                                                                       \
+    do {                                                                                                     \
+        if (a.per_traj) { if (nd1) HODE_DF(true, 1, 128, CP); else HODE_DF(true, 0, 128, CP); }              \
+        else if (threads <= 128) { if (nd1) HODE_DF(false, 1, 128, CP); else HODE_DF(false, 0, 128, CP); }   \
+        else { if (nd1) HODE_DF(false, 1, HODE_DOPRI5_MAX_THREADS, CP); else HODE_DF(false, 0, HODE_DOPRI5_MAX_THREADS, CP); } \
+    } while (0)
+    HODE_DISPATCH_CP(F, a, st, HODE_DF_CP);
+#undef HODE_DF_CP
+#undef HODE_DF
     HODE_LAUNCH_CHECK();
     return 0;
 }
@@ -297,15 +390,18 @@ int launch_dopri5_bwd(const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) 
     const int threads = a.batch >= 128 ? 128 : round_up32(a.batch);
     const int tiles = (int)((a.batch + threads - 1) / threads);
     const int64_t nblk = a.n_groups * tiles;
-    const size_t sh = (F::SP + F::P) * sizeof(float);
     const bool nd1 = cfg.n_dose == 1;
-    if (cfg.expert_grads) {
-        if (nd1) dopri5_bwd_kernel<F, true, 1><<<(unsigned)nblk, threads, sh, st>>>(a, tiles);
-        else dopri5_bwd_kernel<F, true, 0><<<(unsigned)nblk, threads, sh, st>>>(a, tiles);
-    } else {
-        if (nd1) dopri5_bwd_kernel<F, false, 1><<<(unsigned)nblk, threads, sh, st>>>(a, tiles);
-        else dopri5_bwd_kernel<F, false, 0><<<(unsigned)nblk, threads, sh, st>>>(a, tiles);
-    }
+    const bool eg = cfg.expert_grads != 0;
+#define HODE_DB(EG, ND, CP) \
+    dopri5_bwd_kernel<F, EG, ND, CP><<<(unsigned)nblk, threads, ((CP ? 0 : F::SP) + F::P) * sizeof(float), st>>>(a, tiles)
+#define HODE_DB_CP(CP)                                                         \
+    do {                                                                       \
+        if (eg) { if (nd1) HODE_DB(true, 1, CP); else HODE_DB(true, 0, CP); }  \
+        else    { if (nd1) HODE_DB(false, 1, CP); else HODE_DB(false, 0, CP); } \
+    } while (0)
+    HODE_DISPATCH_CP(F, a, st, HODE_DB_CP);
+#undef HODE_DB_CP
+#undef HODE_DB
     HODE_LAUNCH_CHECK();
     return 0;
 }

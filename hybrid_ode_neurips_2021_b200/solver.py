@@ -108,6 +108,28 @@ def pack_params(func, kind) -> torch.Tensor:
     return torch.cat(parts).to(torch.float32)
 
 
+_hill_cache = {}
+
+
+def hill_exponents_are_two(func) -> bool:
+    """True when ``HillCure == HillPatho == 2`` exactly (the ``RochConfig`` defaults; the simulation experiments never
+    train them, ``run_simulation.py:125-129``): the kernels then compute ``x ** Hill`` as a multiply
+    (``HODE_FLAG_HILL2``).  The two scalars live on the device, so the answer is cached per parameter version: one
+    host read per change, none in a training loop that leaves the expert parameters alone."""
+    hc, hp = func.HillCure, func.HillPatho
+    key = (id(func), hc.data_ptr(), hp.data_ptr())
+    ver = (hc._version, hp._version)
+    hit = _hill_cache.get(key)
+    if hit is not None and hit[0] == ver and hit[1]() is func:
+        return hit[2]
+    with torch.no_grad():
+        ok = bool(((hc == 2.0) & (hp == 2.0)).item())
+    if len(_hill_cache) > 256:
+        _hill_cache.clear()
+    _hill_cache[key] = (ver, weakref.ref(func), ok)
+    return ok
+
+
 def fixed_grid_points(t: torch.Tensor, step_size) -> torch.Tensor:
     """torchdiffeq's fixed grid, computed in ``t.dtype`` exactly as ``_grid_constructor_from_step_size`` does."""
     if step_size is None:
@@ -216,7 +238,8 @@ def _raise_on_failure(st: torch.Tensor):
 
 _FIXED_KEYS = {"step_size", "perturb", "grid_constructor", "interp"}
 _ADAPTIVE_KEYS = {"first_step", "step_t", "jump_t", "safety", "ifactor", "dfactor", "max_num_steps", "dtype", "norm"}
-_OUR_KEYS = {"controller", "n_groups", "tape_capacity", "expert_grads", "attempt_cap", "param_sets", "param_set_of_group"}
+_OUR_KEYS = {"controller", "n_groups", "tape_capacity", "expert_grads", "attempt_cap", "param_sets", "param_set_of_group",
+             "hill2_kernels"}
 _NAMES = {"euler": "Euler", "midpoint": "Midpoint", "rk4": "RK4", "dopri5": "Dopri5Solver"}
 
 
@@ -279,6 +302,7 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
         ifactor=float(options.get("ifactor", 10.0)), dfactor=float(options.get("dfactor", 0.2)),
         first_step=options.get("first_step", None), max_num_steps=int(options.get("max_num_steps", 2 ** 31 - 1)),
         attempt_cap=int(options.get("attempt_cap", ops.ATTEMPT_CAP_DEFAULT)),
+        hill2=(kind == L.FIELD_ROCHE and bool(options.get("hill2_kernels", True)) and hill_exponents_are_two(func)),
     )
     packed = pack_params(func, kind)
     pb = ops.Problem(cfg, n_groups, batch, dose_amt, dose_t, None, None)

@@ -72,6 +72,12 @@ typedef struct hode_stats {
     int32_t status;   /* hode_solve_status */
 } hode_stats;
 
+/* hode_cfg.flags.  HODE_FLAG_HILL2: the caller guarantees HillCure == HillPatho == 2.0 exactly (the RochConfig
+ * defaults, sim_config.py:5-6; never trained by the simulation experiments) in EVERY parameter set of the call; the
+ * library then runs kernels in which x**Hill is a multiply (model.py:529, 537-538).  A violated guarantee is detected on
+ * the device and reported loudly: NaN in the solution / gradients (dopri5: status HODE_SOLVE_NONFINITE). */
+typedef enum hode_flags { HODE_FLAG_HILL2 = 1 } hode_flags;
+
 typedef struct hode_cfg {
     int32_t field;        /* hode_field */
     int32_t latent_dim;   /* D */
@@ -80,7 +86,7 @@ typedef struct hode_cfg {
     int32_t perturb;      /* fixed-grid option 'perturb' (model.py:825): first/last stage times moved by one ulp */
     int32_t n_dose;       /* doses per patient, columns of dose_t (model.py:507 `times [B, n_dose]`) */
     int32_t expert_grads; /* backward also accumulates the 13 expert-scalar gradients (Roche) */
-    int32_t reserved0;
+    int32_t flags;        /* hode_flags */
     double rtol, atol;                /* model.py:1079-1080 */
     double safety, ifactor, dfactor;  /* torchdiffeq defaults 0.9, 10, 0.2 */
     double first_step;                /* <= 0: automatic selection (torchdiffeq `_select_initial_step`) */

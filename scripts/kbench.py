@@ -19,6 +19,7 @@ ap.add_argument("--method", default="rk4")
 ap.add_argument("--eg", type=int, default=0)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--lib", default=None)
+ap.add_argument("--hill2", type=int, default=1)
 args = ap.parse_args()
 dev = "cuda:0"
 lib = L.get_lib() if args.lib is None else L.HodeLib(args.lib)
@@ -34,7 +35,7 @@ mask = (torch.rand(15, B, obs, device=dev) < 0.5).float()
 lin = torch.nn.Linear(D, obs).to(dev)
 tt = torch.arange(0, 15.0, device=dev)
 grid = solver.fixed_grid_points(tt.cpu(), args.h).to(dev)
-cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.METHODS[args.method], n_dose=1, expert_grads=bool(args.eg))
+cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.METHODS[args.method], n_dose=1, expert_grads=bool(args.eg), hill2=bool(args.hill2))
 pb = ops.Problem(cfg, 1, B, m.dosage, m._dose_t_f32, solver.pack_params(m, L.FIELD_ROCHE).detach()[None].contiguous(), None)
 
 

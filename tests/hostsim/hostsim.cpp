@@ -140,11 +140,12 @@ int run(Op op, const hode_cfg& cfg, const SolveArgs& a) {
 }
 int dispatch(Op op, const hode_cfg& cfg, const SolveArgs& a) {
     if (cfg.field == HODE_FIELD_ROCHE) {
+        const bool h2 = (cfg.flags & HODE_FLAG_HILL2) != 0;
         switch (cfg.latent_dim) {
-            case 4: return run<Roche<4>>(op, cfg, a);
-            case 6: return run<Roche<6>>(op, cfg, a);
-            case 8: return run<Roche<8>>(op, cfg, a);
-            case 12: return run<Roche<12>>(op, cfg, a);
+            case 4: return h2 ? run<Roche<4, true>>(op, cfg, a) : run<Roche<4>>(op, cfg, a);
+            case 6: return h2 ? run<Roche<6, true>>(op, cfg, a) : run<Roche<6>>(op, cfg, a);
+            case 8: return h2 ? run<Roche<8, true>>(op, cfg, a) : run<Roche<8>>(op, cfg, a);
+            case 12: return h2 ? run<Roche<12, true>>(op, cfg, a) : run<Roche<12>>(op, cfg, a);
         }
     }
 #ifdef HODE_HAVE_NEURAL

@@ -58,7 +58,8 @@ def problem(o, cfg, B, n_groups=1, neural=False):
 @pytest.mark.parametrize("D", [4, 6, 8, 12])
 @pytest.mark.parametrize("method,opts", [("rk4", {"step_size": 0.0625}), ("rk4", {"step_size": 0.3, "perturb": True}),
                                          ("midpoint", {"step_size": 0.125, "perturb": True}), ("euler", {"step_size": 0.0625})])
-def test_fixed_grid_forward_and_reverse_sweep(lib, D, method, opts):
+@pytest.mark.parametrize("hill2", [False, True])
+def test_fixed_grid_forward_and_reverse_sweep(lib, D, method, opts, hill2):
     B = 6
     o = oracle_roche(D, 1, True)
     y0, a, _, _ = make_cohort(B, D, seed=D)
@@ -69,7 +70,7 @@ def test_fixed_grid_forward_and_reverse_sweep(lib, D, method, opts):
     ref = OI.odeint(o, z, t, method=method, options=opts)
     (ref * W).sum().backward()
     grid = OI.fixed_grid_points(t, opts.get("step_size")).contiguous()
-    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.METHODS[method], perturb=opts.get("perturb", False), n_dose=1)
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.METHODS[method], perturb=opts.get("perturb", False), n_dose=1, hill2=hill2)
     pb = problem(o, cfg, B)
     h, tape = ops.fixed_fwd(lib, pb, y0, grid, t, True)
     gy0, gp = ops.fixed_bwd(lib, pb, grid, t, W, tape)
@@ -83,7 +84,8 @@ def test_fixed_grid_forward_and_reverse_sweep(lib, D, method, opts):
 
 @pytest.mark.parametrize("D", [4, 6, 8, 12])
 @pytest.mark.parametrize("ctrl", ["batch", "trajectory"])
-def test_dopri5_forward_and_reverse_sweep(lib, D, ctrl):
+@pytest.mark.parametrize("hill2", [False, True])
+def test_dopri5_forward_and_reverse_sweep(lib, D, ctrl, hill2):
     B = 5 if ctrl == "batch" else 1
     o = oracle_roche(D, 2, True)
     y0, a, _, _ = make_cohort(B, D, seed=20 + D)
@@ -94,7 +96,7 @@ def test_dopri5_forward_and_reverse_sweep(lib, D, ctrl):
     tr = OI.SolveTrace()
     ref = OI.odeint(o, z, t, rtol=1e-7, atol=1e-8, method="dopri5", options={"trace": tr, "differentiable_first_step": False})
     (ref * W).sum().backward()
-    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.DOPRI5, n_dose=1, rtol=1e-7, atol=1e-8,
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.DOPRI5, n_dose=1, rtol=1e-7, atol=1e-8, hill2=hill2,
                        controller=L.CTRL_TRAJ if ctrl == "trajectory" else L.CTRL_BATCH)
     pb = problem(o, cfg, B)
     h, stats, tape = ops.dopri5_fwd(lib, pb, y0, t.double(), 1024)
@@ -124,6 +126,23 @@ def test_dopri5_first_attempt_is_exactly_the_oracle_attempt(lib):
     assert relerr(out[:4], ref[:4]) < 1e-6
     assert tr.attempts[0][3] and tr.attempts[1][3]
     assert abs(tape[0][0, 1, 1].item() - tr.attempts[1][1]) <= 1e-3 * tr.attempts[1][1]
+
+
+def test_hill2_kernels_refuse_other_exponents(lib):
+    """HODE_FLAG_HILL2 is a caller guarantee; a violated guarantee must fail loudly (NaN / NONFINITE), not silently."""
+    D, B = 6, 3
+    o = oracle_roche(D, 5, True)
+    with torch.no_grad():
+        o.HillPatho.fill_(1.5)
+    y0, a, _, _ = make_cohort(B, D, seed=5)
+    o.set_action(a)
+    t = torch.arange(0, 3.0)
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.RK4_38, n_dose=1, hill2=True)
+    h, tape = ops.fixed_fwd(lib, problem(o, cfg, B), y0, OI.fixed_grid_points(t, 0.25).contiguous(), t, True)
+    assert torch.isnan(h[1:]).all()
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.DOPRI5, n_dose=1, hill2=True)
+    _, stats, _ = ops.dopri5_fwd(lib, problem(o, cfg, B), y0, t.double(), 0)
+    assert int(stats[0, 3]) == L.SOLVE_NONFINITE
 
 
 def test_failure_statuses(lib):
