@@ -49,10 +49,11 @@ def _units():
     return units
 
 
-def _source_digest(extra) -> str:
+def _source_digest(src, extra) -> str:
+    """Digest of one unit's inputs: its own .cu, every header of csrc/ (conservative) and include/hode.h."""
     h = hashlib.sha256()
     for name in sorted(os.listdir(CSRC)):
-        if name.endswith((".cu", ".cuh", ".h")):
+        if name == src or name.endswith((".cuh", ".h")):
             with open(os.path.join(CSRC, name), "rb") as f:
                 h.update(name.encode())
                 h.update(f.read())
@@ -64,7 +65,7 @@ def _source_digest(extra) -> str:
 
 def _compile(obj, src, defs, extra):
     stamp = os.path.join(OBJ, obj + ".stamp")
-    dig = _source_digest(list(defs) + list(extra))
+    dig = _source_digest(src, list(defs) + list(extra))
     out = os.path.join(OBJ, obj)
     if os.path.exists(out) and os.path.exists(stamp) and open(stamp).read() == dig:
         return obj, "cached", ""

@@ -3,6 +3,7 @@
 //   * decode_sse_kernel    : output_function (model.py:1120) + masked SSE (model.py:1179) + their gradients, one pass
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 namespace hode {
 
@@ -154,78 +155,161 @@ __global__ void __launch_bounds__(kThreads) decode_sse_kernel(
 // ---------------------------------------------------------------------------------------------------------------
 // Fast path of decode + masked SSE for contiguous x / mask [n_t, n_traj, obs] with obs % 4 == 0 (the layout a training
 // loop keeps on the device).  Same two passes as above, but
-//   * the x / mask tiles are fetched with 16-byte cp.async (LDGSTS): 2 * TR * obs * 4 bytes in flight per CTA, several
-//     CTAs per SM, so HBM latency is covered without register staging (the scalar version was latency-bound: ~1 TB/s);
-//   * rows are padded to an odd number of 16-byte chunks: thread-per-row LDS.128 / STS.128 are bank-conflict free.
+//   * the x / mask tiles are fetched by the TMA engine: every row owner issues one cp.async.bulk (obs * 4 bytes) per
+//     array for its own row into a TWO-STAGE ring, completion is tracked by one mbarrier per stage (expect_tx /
+//     complete_tx).  The tile after next is requested as soon as a stage is released, so two tiles are always in
+//     flight per CTA and the copy costs two instructions per thread per tile;
+//   * rows land padded to an odd number of 16-byte chunks: thread-per-row LDS.128 / STS.128 are bank-conflict free;
+//   * SPLIT threads share one trajectory row in pass 1 (each takes a contiguous range of observation chunks; the
+//     partial grad_h are combined through shared memory): twice the warps for the same tile, which is what the issue
+//     rate needs (about 35 instructions per (t, trajectory, observation) element against 384 B of HBM traffic per row);
+//   * the next tile's h row is prefetched into registers before the wait.
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory"); }
+// one arrival that also announces `bytes` of asynchronous (TMA) traffic for the current phase
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// orders this thread's generic-proxy shared-memory accesses before later async-proxy (TMA) writes to the same bytes
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int D, int TR>
-__global__ void __launch_bounds__(TR) decode_sse_fast_kernel(
+template <int D, int TR, int SPLIT>
+__global__ void __launch_bounds__(TR * SPLIT) decode_sse_fast_kernel(
     int32_t obs, int32_t ldx, int32_t n_t, int64_t n_traj, float scale, float inv_norm, const float* __restrict__ h,
     const float* __restrict__ W, const float* __restrict__ bias, const float* __restrict__ x,
     const float* __restrict__ mask, float* __restrict__ loss, float* __restrict__ grad_h, float* __restrict__ grad_w,
     float* __restrict__ grad_b) {
     extern __shared__ __align__(16) float smem[];
-    constexpr int DP = (D + 3) / 4 * 4;  // W rows padded to 16 bytes
+    constexpr int NT = TR * SPLIT;
+    constexpr int DP = (D + 3) / 4 * 4;  // W / h rows padded to 16 bytes
     const int obs4 = obs / 4;
-    float* sW = smem;                      // [obs][DP]
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);  // [2] mbarriers (16 bytes)
+    float* sW = smem + 4;                  // [obs][DP]
     float* sB = sW + obs * DP;             // [obs]
     float* sH = sB + obs;                  // [TR][DP]
-    float* sX = sH + TR * DP;              // [TR][ldx]
-    float* sM = sX + TR * ldx;             // [TR][ldx]
+    float* sG = sH + TR * DP;              // [TR][DP] partial grad_h of the second row part (SPLIT == 2)
+    float* sXM = sG + (SPLIT > 1 ? TR * DP : 0);  // 2 stages x {x tile, mask tile}, each [TR][ldx]
+    const int tile_floats = TR * ldx;
     const int tid = threadIdx.x;
-    for (int i = tid; i < obs * DP; i += TR) {
+    if (tid == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < obs * DP; i += NT) {
         const int o = i / DP, d = i % DP;
         sW[i] = d < D ? W[o * D + d] : 0.0f;
     }
-    for (int i = tid; i < obs; i += TR) sB[i] = bias[i];
+    for (int i = tid; i < obs; i += NT) sB[i] = bias[i];
 
-    const int nsub = TR / obs > 0 ? TR / obs : 1;
-    const int o2 = tid % obs, sub2 = tid / obs;
+    // pass-2 ownership: 4 adjacent observation columns (one 16-byte chunk) x a subset of the rows
+    const int nsub = NT / obs4 > 0 ? NT / obs4 : 1;
+    const int cg2 = tid % obs4, sub2 = tid / obs4;
     const bool act2 = sub2 < nsub && grad_w != nullptr;
-    float gw[D];
+    float gw[4][D], gb[4];
 #pragma unroll
-    for (int d = 0; d < D; ++d) gw[d] = 0.0f;
-    float gb = 0.0f, lsum = 0.0f;
+    for (int i = 0; i < 4; ++i) {
+        gb[i] = 0.0f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) gw[i][d] = 0.0f;
+    }
+    float lsum = 0.0f;
+
+    // pass-1 ownership: row `row`, observation chunks [q_lo, q_hi)
+    const int row = tid % TR, part = tid / TR;
+    const int q_lo = (part * obs4) / SPLIT, q_hi = ((part + 1) * obs4) / SPLIT;
 
     const int64_t tiles_per_t = (n_traj + TR - 1) / TR;
     const int64_t n_tiles = tiles_per_t * n_t;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+
+    // one elected thread requests the whole x tile and the whole mask tile (each contiguous in global memory)
+    auto issue = [&](int64_t tile, int stage) {
+        if (tid != 0) return;
         const int64_t t = tile / tiles_per_t;
         const int64_t b0 = (tile % tiles_per_t) * TR;
         const int rows = (int)((n_traj - b0) < TR ? (n_traj - b0) : TR);
-        __syncthreads();
-        {   // tile load: chunk c of the tile is 16 contiguous bytes; consecutive lanes take consecutive chunks
-            const float* xb = x + ((int64_t)t * n_traj + b0) * obs;
-            const float* mb = mask + ((int64_t)t * n_traj + b0) * obs;
-            int r = tid / obs4, c4 = tid % obs4;
-            const int dr = TR / obs4, dc = TR % obs4;
-            while (r < rows) {
-                const int src = (r * obs4 + c4) * 4, dst = r * ldx + c4 * 4;
-                cp_async16(sX + dst, xb + src);
-                cp_async16(sM + dst, mb + src);
-                r += dr; c4 += dc;
-                if (c4 >= obs4) { c4 -= obs4; ++r; }
-            }
-        }
-        const bool act1 = tid < rows;
-        float hv[D], gh[D];
-        if (act1) {
-            const float* hp = h + ((int64_t)t * n_traj + b0 + tid) * D;
+        const int64_t g = ((int64_t)t * n_traj + b0) * obs;
+        const unsigned bytes = (unsigned)rows * (unsigned)obs * 4u;
+        float* dX = sXM + stage * 2 * tile_floats;
+        mbar_arrive_expect_tx(&full[stage], 2u * bytes);
+        bulk_g2s(dX, x + g, bytes, &full[stage]);
+        bulk_g2s(dX + tile_floats, mask + g, bytes, &full[stage]);
+    };
+    auto load_h = [&](int64_t tile, float (&hv)[D]) {
+        const int64_t t = tile / tiles_per_t;
+        const int64_t b0 = (tile % tiles_per_t) * TR;
+        const int rows = (int)((n_traj - b0) < TR ? (n_traj - b0) : TR);
+        if (row < rows) {
+            const float* hp = h + ((int64_t)t * n_traj + b0 + row) * D;
+            if (D % 4 == 0) {
 #pragma unroll
-            for (int d = 0; d < D; ++d) { hv[d] = hp[d]; sH[tid * DP + d] = hv[d]; gh[d] = 0.0f; }
+                for (int i = 0; i < D / 4; ++i) {
+                    const float4 v = reinterpret_cast<const float4*>(hp)[i];
+                    hv[4 * i] = v.x; hv[4 * i + 1] = v.y; hv[4 * i + 2] = v.z; hv[4 * i + 3] = v.w;
+                }
+            } else if (D % 2 == 0) {
+#pragma unroll
+                for (int i = 0; i < D / 2; ++i) {
+                    const float2 v = reinterpret_cast<const float2*>(hp)[i];
+                    hv[2 * i] = v.x; hv[2 * i + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int d = 0; d < D; ++d) hv[d] = hp[d];
+            }
+        } else {
+#pragma unroll
+            for (int d = 0; d < D; ++d) hv[d] = 0.0f;
         }
-        cp_async_wait_all();
-        __syncthreads();
+    };
+
+    int64_t tile = blockIdx.x;
+    float hv[D], hn[D];
+    __syncthreads();  // barriers initialised, sW / sB staged
+    if (tile < n_tiles) { issue(tile, 0); load_h(tile, hv); }
+    if (tile + gridDim.x < n_tiles) issue(tile + gridDim.x, 1);
+    for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+        const int stage = it & 1;
+        const int64_t next = tile + gridDim.x;
+        if (next < n_tiles) load_h(next, hn);
+        mbar_wait(&full[stage], (unsigned)(it >> 1) & 1u);  // tile `tile` has landed
+        const int64_t t = tile / tiles_per_t;
+        const int64_t b0 = (tile % tiles_per_t) * TR;
+        const int rows = (int)((n_traj - b0) < TR ? (n_traj - b0) : TR);
+        float* sX = sXM + stage * 2 * tile_floats;
+        const float* sM = sX + tile_floats;
+        // ---- pass 1 -------------------------------------------------------------------------------------------
+        const bool act1 = row < rows;
+        float gh[D];
         if (act1) {
-            float4* xr = reinterpret_cast<float4*>(sX + tid * ldx);
-            const float4* mr = reinterpret_cast<const float4*>(sM + tid * ldx);
-            for (int q = 0; q < obs4; ++q) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) gh[d] = 0.0f;
+            if (part == 0) {
+                float hp4[DP];
+#pragma unroll
+                for (int d = 0; d < DP; ++d) hp4[d] = d < D ? hv[d] : 0.0f;
+#pragma unroll
+                for (int i = 0; i < DP / 4; ++i)
+                    reinterpret_cast<float4*>(sH + row * DP)[i] = make_float4(hp4[4 * i], hp4[4 * i + 1], hp4[4 * i + 2], hp4[4 * i + 3]);
+            }
+            float4* xr = reinterpret_cast<float4*>(sX + row * ldx);
+            const float4* mr = reinterpret_cast<const float4*>(sM + row * ldx);
+            for (int q = q_lo; q < q_hi; ++q) {
                 const float4 xv = xr[q], mv = mr[q];
                 const float4 bv = reinterpret_cast<const float4*>(sB)[q];
                 const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ms[4] = {mv.x, mv.y, mv.z, mv.w};
@@ -233,7 +317,12 @@ __global__ void __launch_bounds__(TR) decode_sse_fast_kernel(
                 float cs[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
-                    const float* w = sW + (q * 4 + i) * DP;
+                    float w[DP];
+#pragma unroll
+                    for (int v = 0; v < DP / 4; ++v) {
+                        const float4 wv = reinterpret_cast<const float4*>(sW + (q * 4 + i) * DP)[v];
+                        w[4 * v] = wv.x; w[4 * v + 1] = wv.y; w[4 * v + 2] = wv.z; w[4 * v + 3] = wv.w;
+                    }
                     float xh = bs[i];
 #pragma unroll
                     for (int d = 0; d < D; ++d) xh = fmaf(w[d], hv[d], xh);
@@ -247,55 +336,83 @@ __global__ void __launch_bounds__(TR) decode_sse_fast_kernel(
                 }
                 xr[q] = make_float4(cs[0], cs[1], cs[2], cs[3]);
             }
-            if (grad_h != nullptr) {
-                float* gp = grad_h + ((int64_t)t * n_traj + b0 + tid) * D;
+            if (SPLIT > 1 && part != 0) {
 #pragma unroll
-                for (int d = 0; d < D; ++d) gp[d] = gh[d];
+                for (int d = 0; d < D; ++d) sG[row * DP + d] = gh[d];
             }
         }
         __syncthreads();
+        if (act1 && part == 0 && grad_h != nullptr) {
+            if (SPLIT > 1) {
+#pragma unroll
+                for (int d = 0; d < D; ++d) gh[d] += sG[row * DP + d];
+            }
+            float* gp = grad_h + ((int64_t)t * n_traj + b0 + row) * D;
+#pragma unroll
+            for (int d = 0; d < D; ++d) gp[d] = gh[d];
+        }
+        // ---- pass 2 -------------------------------------------------------------------------------------------
         if (act2) {
             for (int r = sub2; r < rows; r += nsub) {
-                const float c = sX[r * ldx + o2];
-                gb += c;
+                const float4 cv = reinterpret_cast<const float4*>(sX + r * ldx)[cg2];
+                const float cs[4] = {cv.x, cv.y, cv.z, cv.w};
+                float hr[DP];
 #pragma unroll
-                for (int d = 0; d < D; ++d) gw[d] = fmaf(c, sH[r * DP + d], gw[d]);
+                for (int v = 0; v < DP / 4; ++v) {
+                    const float4 q4 = reinterpret_cast<const float4*>(sH + r * DP)[v];
+                    hr[4 * v] = q4.x; hr[4 * v + 1] = q4.y; hr[4 * v + 2] = q4.z; hr[4 * v + 3] = q4.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    gb[i] += cs[i];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) gw[i][d] = fmaf(cs[i], hr[d], gw[i][d]);
+                }
             }
         }
+#pragma unroll
+        for (int d = 0; d < D; ++d) hv[d] = hn[d];
+        fence_proxy_async();
+        __syncthreads();  // every thread is done with this stage (and with sH / sG): refill it with the tile after next
+        if (next + gridDim.x < n_tiles) issue(next + gridDim.x, stage);
     }
     if (act2) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) atomicAdd(&grad_w[o2 * D + d], gw[d]);
-        if (grad_b != nullptr) atomicAdd(&grad_b[o2], gb);
+        for (int i = 0; i < 4; ++i) {
+#pragma unroll
+            for (int d = 0; d < D; ++d) atomicAdd(&grad_w[(cg2 * 4 + i) * D + d], gw[i][d]);
+            if (grad_b != nullptr) atomicAdd(&grad_b[cg2 * 4 + i], gb[i]);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) lsum += __shfl_xor_sync(0xffffffffu, lsum, o);
     if ((tid & 31) == 0) atomicAdd(loss, lsum * inv_norm);
 }
 
-template <int D, int TR>
+template <int D, int TR, int SPLIT>
 static int launch_decode_fast(int32_t obs, int32_t n_t, int64_t n_traj, double n_norm, const float* h, const float* W,
                               const float* b, const float* x, const float* mask, float* loss, float* grad_h,
                               float* grad_w, float* grad_b, cudaStream_t stream) {
     constexpr int DP = (D + 3) / 4 * 4;
+    constexpr int NT = TR * SPLIT;
     const int obs4 = obs / 4;
-    const int ldx = (obs4 % 2 == 0) ? obs + 4 : obs;
-    const size_t sh = sizeof(float) * ((size_t)obs * DP + obs + (size_t)TR * DP + 2 * (size_t)TR * ldx);
+    const int ldx = obs;  // whole-tile TMA copies land unpadded
+    (void)obs4;
+    const size_t sh = sizeof(float) * (4 + (size_t)obs * DP + obs + (size_t)(SPLIT > 1 ? 2 : 1) * TR * DP + 4 * (size_t)TR * ldx);
     if (sh > 227 * 1024) return -1;
-    cudaError_t e = cudaFuncSetAttribute(decode_sse_fast_kernel<D, TR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    cudaError_t e = cudaFuncSetAttribute(decode_sse_fast_kernel<D, TR, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
     if (e != cudaSuccess) return (int)e;
     int dev = 0, sms = 148, per_sm = 1;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_sse_fast_kernel<D, TR>, TR, sh);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_sse_fast_kernel<D, TR, SPLIT>, NT, sh);
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) per_sm = 1;
     const int64_t n_tiles = ((n_traj + TR - 1) / TR) * n_t;
     int64_t grid = (int64_t)sms * per_sm;
     if (grid > n_tiles) grid = n_tiles;
-    decode_sse_fast_kernel<D, TR><<<(unsigned)grid, TR, sh, stream>>>(obs, ldx, n_t, n_traj, (float)(-2.0 / n_norm),
-                                                                     (float)(1.0 / n_norm), h, W, b, x, mask, loss,
-                                                                     grad_h, grad_w, grad_b);
+    decode_sse_fast_kernel<D, TR, SPLIT><<<(unsigned)grid, NT, sh, stream>>>(
+        obs, ldx, n_t, n_traj, (float)(-2.0 / n_norm), (float)(1.0 / n_norm), h, W, b, x, mask, loss, grad_h, grad_w, grad_b);
     return (int)cudaGetLastError();
 }
 
@@ -306,9 +423,17 @@ static int launch_decode_sse_d(int32_t obs, int32_t n_t, int64_t n_traj, double 
     const bool contiguous = so == 1 && sb == obs && (n_t == 1 || st == n_traj * (int64_t)obs);
     const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(mask)) & 15) == 0;
     if (contiguous && aligned && obs % 4 == 0 && obs >= 4) {
-        if (obs <= 48) return launch_decode_fast<D, 128>(obs, n_t, n_traj, n_norm, h, W, b, x, mask, loss, grad_h, grad_w, grad_b, stream);
-        if (obs <= 64) return launch_decode_fast<D, 64>(obs, n_t, n_traj, n_norm, h, W, b, x, mask, loss, grad_h, grad_w, grad_b, stream);
-        if (obs <= 128) return launch_decode_fast<D, 128>(obs, n_t, n_traj, n_norm, h, W, b, x, mask, loss, grad_h, grad_w, grad_b, stream);
+        // obs >= 8: every row part of a SPLIT = 2 tile owns at least one 16-byte chunk
+        static const int variant = getenv("HODE_DECODE_VARIANT") ? atoi(getenv("HODE_DECODE_VARIANT")) : 0;
+        if (variant == 1) return launch_decode_fast<D, 128, 1>(obs, n_t, n_traj, n_norm, h, W, b, x, mask, loss, grad_h, grad_w, grad_b, stream);
+        if (variant == 2) return launch_decode_fast<D, 64, 2>(obs, n_t, n_traj, n_norm, h, W, b, x, mask, loss, grad_h, grad_w, grad_b, stream);
+        if (variant == 3) return launch_decode_fast<D, 64, 1>(obs, n_t, n_traj, n_norm, h, W, b, x, mask, loss, grad_h, grad_w, grad_b, stream);
+        if (variant == 5) return launch_decode_fast<D, 32, 1>(obs, n_t, n_traj, n_norm, h, W, b, x, mask, loss, grad_h, grad_w, grad_b, stream);
+        if (variant == 6) return launch_decode_fast<D, 32, 2>(obs, n_t, n_traj, n_norm, h, W, b, x, mask, loss, grad_h, grad_w, grad_b, stream);
+        if (variant == 7) return launch_decode_fast<D, 128, 2>(obs, n_t, n_traj, n_norm, h, W, b, x, mask, loss, grad_h, grad_w, grad_b, stream);
+        // measured on B200 (scripts/kbench_decode.py): obs 20 / 40 -> <64, 1>, obs 80 -> <32, 2>
+        if (obs <= 48) return launch_decode_fast<D, 64, 1>(obs, n_t, n_traj, n_norm, h, W, b, x, mask, loss, grad_h, grad_w, grad_b, stream);
+        if (obs <= 256) return launch_decode_fast<D, 32, 2>(obs, n_t, n_traj, n_norm, h, W, b, x, mask, loss, grad_h, grad_w, grad_b, stream);
     }
     const int ld = obs | 1;
     const size_t sh = sizeof(float) * ((size_t)obs * D + obs + (size_t)kTR * D + 2 * (size_t)kTR * ld);

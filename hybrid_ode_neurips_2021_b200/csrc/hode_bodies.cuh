@@ -31,6 +31,7 @@ struct SolveArgs {
     double safety, ifactor, dfactor, first_step;
     int64_t max_num_steps, attempt_cap;
     int32_t per_traj;
+    int64_t ctrl_batch;  // > 0: "flat" launch (threads enumerate all trajectories); trajectories per controller group
     // common
     int32_t n_t;
     float* h_out;

@@ -121,6 +121,24 @@ inline bool const_params_enabled() {
 template <class F>
 inline bool use_const_params(const SolveArgs& a) { return F::kConstBank && a.pset == nullptr && const_params_enabled(); }
 
+// several small groups share one warp: a group is a segment of `size` consecutive lanes; only the lanes of a segment
+// take part in its shuffles (independent thread scheduling lets segments follow different accept/reject sequences)
+struct CommSeg {
+    unsigned mask;  // lanes of this segment
+    int base, size, rel;
+    // every lane adds the segment's values in the same order (lane base, base+1, ...): the sums are bit-identical
+    // across the group, which the group-uniform accept/reject decision relies on
+    __device__ __forceinline__ void sum2(float& a, float& b) {
+        const float a0 = a, b0 = b;
+        float sa = 0.0f, sb = 0.0f;
+        for (int i = 0; i < size; ++i) {
+            sa += __shfl_sync(mask, a0, base + i);
+            sb += __shfl_sync(mask, b0, base + i);
+        }
+        a = sa; b = sb;
+    }
+};
+
 template <class F>
 __device__ __forceinline__ void stage_params(const SolveArgs& a, int64_t group, float* sp) {
     const int set = a.pset ? a.pset[group] : 0;
@@ -269,6 +287,28 @@ __global__ void __launch_bounds__(MAXT) dopri5_fwd_kernel(const SolveArgs a, int
     }
 }
 
+// Batch-coupled controller for SMALL groups (batch <= 16, one parameter set): floor(32 / batch) groups per warp, each a
+// lane segment with its own step-size sequence.  (One group per CTA leaves 22 of 32 lanes idle at the reference's
+// batch of 10, run_dim.sh:41.)
+template <class F, int ND, bool CP>
+__global__ void __launch_bounds__(128) dopri5_fwd_seg_kernel(const SolveArgs a) {
+    extern __shared__ float smem[];
+    if constexpr (!CP) stage_params<F>(a, 0, smem);
+    const int lane = threadIdx.x & 31;
+    const int size = (int)a.batch, gpw = 32 / size, seg = lane / size;
+    if (seg >= gpw) return;
+    const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int64_t group = warp * gpw + seg;
+    if (group >= a.n_groups) return;
+    CommSeg cm;
+    cm.base = seg * size; cm.size = size; cm.rel = lane - cm.base;
+    cm.mask = (size == 32 ? 0xffffffffu : ((1u << size) - 1u)) << cm.base;
+    const int64_t idx = group * a.batch + cm.rel;
+    const float count = (float)(a.batch * F::D);
+    if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F>(a, cm, ParamConst(), ds, idx, true, group, cm.rel == 0, count))); }
+    else { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F>(a, cm, (const float*)smem, ds, idx, true, group, cm.rel == 0, count))); }
+}
+
 template <class F, bool EG, int ND, bool CP>
 __global__ void __launch_bounds__(128) dopri5_bwd_kernel(const SolveArgs a, int tiles_per_group) {
     extern __shared__ float smem[];
@@ -280,7 +320,7 @@ __global__ void __launch_bounds__(128) dopri5_bwd_kernel(const SolveArgs a, int 
     zero_acc<F>(acc);
     if (tl.b < a.batch) {
         const int64_t idx = tl.group * a.batch + tl.b;
-        const int64_t ctrl = a.per_traj ? idx : tl.group;
+        const int64_t ctrl = a.per_traj ? idx : (a.ctrl_batch > 0 ? idx / a.ctrl_batch : tl.group);
         if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, ParamConst(), ds, idx, ctrl, acc))); }
         else { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, (const float*)sp, ds, idx, ctrl, acc))); }
     }
@@ -313,8 +353,21 @@ inline int round_up32(int64_t n) { return (int)(((n + 31) / 32) * 32); }
         LAUNCH(false);                                                   \
     } while (0)
 
+// With ONE parameter set nothing ties a CTA to a group: threads enumerate all trajectories ("flat"), so small groups do
+// not leave lanes idle.  The trajectory index is unchanged (group * batch + b).
+inline SolveArgs flatten(const SolveArgs& a) {
+    SolveArgs f = a;
+    if (a.pset == nullptr && a.n_groups > 1) {
+        f.ctrl_batch = a.batch;
+        f.batch = a.n_groups * a.batch;
+        f.n_groups = 1;
+    }
+    return f;
+}
+
 template <class F>
-int launch_fixed_fwd(const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) {
+int launch_fixed_fwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st) {
+    const SolveArgs a = flatten(a_in);
     const int threads = a.batch >= 128 ? 128 : round_up32(a.batch);
     const int tiles = (int)((a.batch + threads - 1) / threads);
     const int64_t nblk = a.n_groups * tiles;
@@ -335,7 +388,8 @@ int launch_fixed_fwd(const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) {
 }
 
 template <class F>
-int launch_fixed_bwd(const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) {
+int launch_fixed_bwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st) {
+    const SolveArgs a = flatten(a_in);
     const int threads = a.batch >= 128 ? 128 : round_up32(a.batch);
     const int tiles = (int)((a.batch + threads - 1) / threads);
     const int64_t nblk = a.n_groups * tiles;
@@ -364,9 +418,27 @@ int launch_fixed_bwd(const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) {
 }
 
 template <class F>
-int launch_dopri5_fwd(const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) {
+int launch_dopri5_fwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st) {
     const bool nd1 = cfg.n_dose == 1;
-    if (!a.per_traj && a.batch > HODE_DOPRI5_MAX_THREADS) return -2;
+    if (!a_in.per_traj && a_in.batch > HODE_DOPRI5_MAX_THREADS) return -2;
+    if (!a_in.per_traj && a_in.pset == nullptr && a_in.batch <= 16) {
+        // small batch-coupled groups: several groups per warp
+        const SolveArgs& a = a_in;
+        const int gpw = 32 / (int)a.batch;
+        const int64_t warps = (a.n_groups + gpw - 1) / gpw;
+        const int threads = warps >= 4 ? 128 : (int)warps * 32;
+        const int64_t nblk = (warps * 32 + threads - 1) / threads;
+#define HODE_DS_CP(CP)                                                                                                     \
+    do {                                                                                                                   \
+        if (nd1) dopri5_fwd_seg_kernel<F, 1, CP><<<(unsigned)nblk, threads, (CP ? 0 : F::SP) * sizeof(float), st>>>(a);    \
+        else dopri5_fwd_seg_kernel<F, 0, CP><<<(unsigned)nblk, threads, (CP ? 0 : F::SP) * sizeof(float), st>>>(a);        \
+    } while (0)
+        HODE_DISPATCH_CP(F, a, st, HODE_DS_CP);
+#undef HODE_DS_CP
+        HODE_LAUNCH_CHECK();
+        return 0;
+    }
+    const SolveArgs a = a_in.per_traj ? flatten(a_in) : a_in;
     const int threads = a.per_traj ? (a.batch >= 128 ? 128 : round_up32(a.batch)) : round_up32(a.batch);
     const int tiles = a.per_traj ? (int)((a.batch + threads - 1) / threads) : 1;
     const int64_t nblk = a.n_groups * tiles;
@@ -386,7 +458,8 @@ int launch_dopri5_fwd(const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) 
 }
 
 template <class F>
-int launch_dopri5_bwd(const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) {
+int launch_dopri5_bwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st) {
+    const SolveArgs a = flatten(a_in);
     const int threads = a.batch >= 128 ? 128 : round_up32(a.batch);
     const int tiles = (int)((a.batch + threads - 1) / threads);
     const int64_t nblk = a.n_groups * tiles;

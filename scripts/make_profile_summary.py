@@ -1,0 +1,56 @@
+"""Turn one gpurun_out/prof_<tag>/ directory (scripts/profile.sh) into the committed text evidence under profiles/:
+    python scripts/make_profile_summary.py <tag> [<round label>]
+writes profiles/<label>_launches.txt (per-kernel share of the step from the ncu launch list), profiles/<label>_<kernel>.txt
+(key `ncu --set full` counters per hot kernel) and copies the plain bench line."""
+import collections
+import csv
+import os
+import re
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+tag = sys.argv[1]
+label = sys.argv[2] if len(sys.argv) > 2 else tag
+src = os.path.join(ROOT, "gpurun_out", "prof_" + tag)
+dst = os.path.join(ROOT, "profiles")
+os.makedirs(dst, exist_ok=True)
+
+# ---- launch list -----------------------------------------------------------------------------------------------------
+rows = []
+with open(os.path.join(src, "launches.csv")) as f:
+    lines = [ln for ln in f if ln.startswith('"')]
+rd = csv.reader(lines)
+hdr = next(rd)
+ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+for r in rd:
+    v = float(r[vi].replace(",", ""))
+    v = v / 1e3 if r[ui] in ("ns", "nsecond") else (v * 1e3 if r[ui] in ("ms", "msecond") else v)  # -> us
+    rows.append((re.sub(r"\(.*", "", r[ki]), v))
+agg = collections.OrderedDict()
+for k, v in rows:
+    c, t = agg.get(k, (0, 0.0))
+    agg[k] = (c + 1, t + v)
+tot = sum(t for _, t in agg.values())
+with open(os.path.join(dst, label + "_launches.txt"), "w") as f:
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none   python bench.py --steps 2 --warmup 3 --cpu-patients 512\n")
+    f.write("# per-launch times are cold-cache and serialised: compare SHARES, not absolutes. {} launches, {:.1f} ms total\n".format(len(rows), tot / 1e3))
+    f.write("{:>7} {:>12} {:>12} {:>7}  kernel\n".format("count", "total_us", "mean_us", "share"))
+    for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        f.write("{:>7} {:>12.1f} {:>12.1f} {:>6.1f}%  {}\n".format(c, t, t / c, 100 * t / tot, k[:140]))
+
+# ---- per-kernel full captures ----------------------------------------------------------------------------------------
+for name in sorted(os.listdir(src)):
+    if not name.endswith(".ncu-rep"):
+        continue
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), os.path.join(src, name)],
+                         capture_output=True, text=True).stdout
+    keep = [ln for ln in out.splitlines() if not re.search(r"occupancy_per_|fp16|_adu|_cbu|membar|sleeping|tex_throttle|misc_per|drain|syslts", ln)]
+    with open(os.path.join(dst, "{}_{}.txt".format(label, name[:-8])), "w") as f:
+        f.write("# ncu --set full --clock-control none --import-source on -k regex:{} (bench.py --patients 131072; one launch)\n".format(name[:-8]))
+        f.write("\n".join(keep) + "\n")
+for name in ("plain.json", "plain_small.json"):
+    if os.path.exists(os.path.join(src, name)):
+        shutil.copy(os.path.join(src, name), os.path.join(dst, "{}_bench_{}".format(label, name)))
+print(sorted(os.listdir(dst)))
