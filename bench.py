@@ -137,7 +137,10 @@ def dist_setup(n_gpus):
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        import datetime
+
+        # a short collective timeout: a rank-asymmetric bug must fail loudly instead of hanging the box
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=180))
     return world, rank, local
 
 
@@ -313,22 +316,23 @@ def run_ours(args):
             ms, wall = float(tt[0]), float(tt[1]) / 1e3
         return ms, wall
 
+    # every rank runs the SAME sequence of steps (device_step contains a collective when N > 1); only rank 0 samples clocks
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler is not None:
         sampler.__enter__()
     for _ in range(max(args.warmup, 3)):
         device_step()
+    time.sleep(1.0)  # let nvidia-smi come up before the timed region
+    for _ in range(2):
+        device_step()
     if sampler is not None:
-        time.sleep(1.0)  # let nvidia-smi come up before the timed region
-        for _ in range(2):
-            device_step()
         sampler.mark()
-    ms, wall = timed(device_step, args.steps)
+    ms, wall = timed(device_step, args.steps)  # ms: max over ranks, identical on every rank
+    if ms < 1500.0:  # the K timed steps are short: keep the same loop running so that clocks get >= ~1.5 s of samples
+        for _ in range(int(1500.0 / max(ms / args.steps, 1e-3)) + 1):
+            device_step()
+        torch.cuda.synchronize()
     if sampler is not None:
-        if ms < 1500.0:  # the K timed steps are short: keep the same loop running so that clocks get >= ~1.5 s of samples
-            for _ in range(int(1500.0 / max(ms / args.steps, 1e-3)) + 1):
-                device_step()
-            torch.cuda.synchronize()
         sampler.__exit__()
     value = B_global * N_STEPS * args.steps / (ms * 1e-3)
 
@@ -406,18 +410,19 @@ def run_ours(args):
 
     if rank != 0:
         if world > 1:
+            dist.barrier()  # matched by rank 0 after it has printed the line
             dist.destroy_process_group()
         return
 
     cpu_val, cpu_s, cores = cpu_reference_rate(args.cpu_patients, 2)
-    h2d = sum(t.numel() * t.element_size() for c in host_chunks for t in c)
+    h2d = world * sum(t.numel() * t.element_size() for c in host_chunks for t in c)  # whole job, like `value`
     n_par = sum(p.numel() for p in train_params)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(B, world),
         "clocks": sampler.summary() if sampler else None,
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 + 4 * n_par,
+        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": world * (4 + 4 * n_par),
                 "ms_per_step": max(ms_e, wall_e * 1e3) / args.steps,
                 "api": "RocheExpertDecoder.solve + masked_sse + backward over {} pinned host mini-batches, H2D on a copy "
                        "stream overlapped with the previous mini-batch's kernels".format(n_chunks)},
@@ -433,6 +438,7 @@ def run_ours(args):
     line.update(extra)
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
