@@ -237,22 +237,33 @@ __global__ void __launch_bounds__(TR * SPLIT) decode_sse_fast_kernel(
     const int64_t tiles_per_t = (n_traj + TR - 1) / TR;
     const int64_t n_tiles = tiles_per_t * n_t;
 
+    // Tile cursor (t, index of the tile inside its time slice), advanced by gridDim.x without 64-bit divisions.
+    struct Cursor {
+        int64_t tile;
+        int t;
+        int64_t k;  // tile index inside time slice t
+    };
+    auto advance = [&](Cursor c) {
+        c.tile += gridDim.x;
+        c.k += gridDim.x;
+        while (c.k >= tiles_per_t) { c.k -= tiles_per_t; ++c.t; }
+        return c;
+    };
     // one elected thread requests the whole x tile and the whole mask tile (each contiguous in global memory)
-    auto issue = [&](int64_t tile, int stage) {
+    auto issue = [&](const Cursor& c, int stage) {
         if (tid != 0) return;
-        const int64_t t = tile / tiles_per_t;
-        const int64_t b0 = (tile % tiles_per_t) * TR;
+        const int64_t b0 = c.k * TR;
         const int rows = (int)((n_traj - b0) < TR ? (n_traj - b0) : TR);
-        const int64_t g = ((int64_t)t * n_traj + b0) * obs;
+        const int64_t g = ((int64_t)c.t * n_traj + b0) * obs;
         const unsigned bytes = (unsigned)rows * (unsigned)obs * 4u;
         float* dX = sXM + stage * 2 * tile_floats;
         mbar_arrive_expect_tx(&full[stage], 2u * bytes);
         bulk_g2s(dX, x + g, bytes, &full[stage]);
         bulk_g2s(dX + tile_floats, mask + g, bytes, &full[stage]);
     };
-    auto load_h = [&](int64_t tile, float (&hv)[D]) {
-        const int64_t t = tile / tiles_per_t;
-        const int64_t b0 = (tile % tiles_per_t) * TR;
+    auto load_h = [&](const Cursor& c, float (&hv)[D]) {
+        const int64_t t = c.t;
+        const int64_t b0 = c.k * TR;
         const int rows = (int)((n_traj - b0) < TR ? (n_traj - b0) : TR);
         if (row < rows) {
             const float* hp = h + ((int64_t)t * n_traj + b0 + row) * D;
@@ -278,18 +289,21 @@ __global__ void __launch_bounds__(TR * SPLIT) decode_sse_fast_kernel(
         }
     };
 
-    int64_t tile = blockIdx.x;
+    Cursor cur;
+    cur.tile = blockIdx.x;
+    cur.t = (int)(cur.tile / tiles_per_t);
+    cur.k = cur.tile - (int64_t)cur.t * tiles_per_t;
+    Cursor nxt = advance(cur), nxt2 = advance(nxt);
     float hv[D], hn[D];
     __syncthreads();  // barriers initialised, sW / sB staged
-    if (tile < n_tiles) { issue(tile, 0); load_h(tile, hv); }
-    if (tile + gridDim.x < n_tiles) issue(tile + gridDim.x, 1);
-    for (int it = 0; tile < n_tiles; tile += gridDim.x, ++it) {
+    if (cur.tile < n_tiles) { issue(cur, 0); load_h(cur, hv); }
+    if (nxt.tile < n_tiles) issue(nxt, 1);
+    for (int it = 0; cur.tile < n_tiles; ++it) {
         const int stage = it & 1;
-        const int64_t next = tile + gridDim.x;
-        if (next < n_tiles) load_h(next, hn);
-        mbar_wait(&full[stage], (unsigned)(it >> 1) & 1u);  // tile `tile` has landed
-        const int64_t t = tile / tiles_per_t;
-        const int64_t b0 = (tile % tiles_per_t) * TR;
+        if (nxt.tile < n_tiles) load_h(nxt, hn);
+        mbar_wait(&full[stage], (unsigned)(it >> 1) & 1u);  // tile `cur` has landed
+        const int64_t t = cur.t;
+        const int64_t b0 = cur.k * TR;
         const int rows = (int)((n_traj - b0) < TR ? (n_traj - b0) : TR);
         float* sX = sXM + stage * 2 * tile_floats;
         const float* sM = sX + tile_floats;
@@ -374,7 +388,8 @@ __global__ void __launch_bounds__(TR * SPLIT) decode_sse_fast_kernel(
         for (int d = 0; d < D; ++d) hv[d] = hn[d];
         fence_proxy_async();
         __syncthreads();  // every thread is done with this stage (and with sH / sG): refill it with the tile after next
-        if (next + gridDim.x < n_tiles) issue(next + gridDim.x, stage);
+        if (nxt2.tile < n_tiles) issue(nxt2, stage);
+        cur = nxt; nxt = nxt2; nxt2 = advance(nxt2);
     }
     if (act2) {
 #pragma unroll

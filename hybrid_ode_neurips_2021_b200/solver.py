@@ -26,7 +26,7 @@ import torch
 from . import _lib as L
 from . import ops
 
-__all__ = ["odeint", "SolveInfo", "last_solve_info", "fixed_grid_points"]
+__all__ = ["odeint", "odeint_ensemble", "SolveInfo", "last_solve_info", "fixed_grid_points"]
 
 EXPERT_NAMES = (
     "HillCure", "HillPatho", "ec50_patho", "emax_patho", "k_dexa", "k_discure_immunereact", "k_discure_immunity",
@@ -243,11 +243,48 @@ _OUR_KEYS = {"controller", "n_groups", "tape_capacity", "expert_grads", "attempt
 _NAMES = {"euler": "Euler", "midpoint": "Midpoint", "rk4": "RK4", "dopri5": "Dopri5Solver"}
 
 
+def _dose_tensors(func, n, device):
+    if func.dosage is None or func.times is None:
+        raise RuntimeError("set_action must be called before integrating (model.py:1113)")
+    dose_amt = func.dosage.detach().to(device=device, dtype=torch.float32).contiguous()
+    dose_t = getattr(func, "_dose_t_f32", None)
+    if dose_t is None or dose_t.shape[0] != n:
+        dose_t = func.times.detach().to(device=device, dtype=torch.float32).contiguous()
+    if dose_amt.shape[0] != n or dose_t.shape[0] != n:
+        raise RuntimeError("dose schedule has {} patients but y0 has {}".format(dose_amt.shape[0], n))
+    return dose_amt, dose_t
+
+
 def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None):
+    """torchdiffeq's ``odeint`` for one vector field (module docstring)."""
+    return _odeint_impl([func], y0, t, rtol, atol, method, options, event_fn)
+
+
+def odeint_ensemble(funcs, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None):
+    """``M`` independent ``odeint`` calls -- one per ensemble member / restart, each with its OWN parameters -- in ONE
+    kernel launch (BASELINE config 4; the reference runs restarts and methods one after the other:
+    ``run_simulation.py:95``, ``Fig3.sh:12-50``).
+
+    ``funcs``: ``M`` vector fields of the same class and ``latent_dim``, each after its own ``set_action`` on ``B``
+    patients.  ``y0``: ``[M * B, D]``, member-major.  Returns ``[len(t), M * B, D]``; gradients flow to every member's
+    parameters.  Each member is its own controller group (``options={'n_groups': g}`` splits a member into ``g`` groups).
+    """
+    funcs = list(funcs)
+    if len(funcs) == 0:
+        raise ValueError("odeint_ensemble needs at least one member")
+    return _odeint_impl(funcs, y0, t, rtol, atol, method, options, None)
+
+
+def _odeint_impl(funcs, y0, t, rtol, atol, method, options, event_fn):
     global _last_info
+    func = funcs[0]
+    M = len(funcs)
     if event_fn is not None:
         raise NotImplementedError("event_fn is not used by the reference and has no fused kernel")
     kind = field_kind(func)
+    for f in funcs[1:]:
+        if field_kind(f) != kind or int(f.latent_dim) != int(func.latent_dim):
+            raise ValueError("ensemble members must be vector fields of the same class and latent_dim")
     if not isinstance(y0, torch.Tensor):
         raise NotImplementedError("tuple states are not used by the reference and have no fused kernel")
     if not y0.is_cuda:
@@ -273,25 +310,28 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
     B, D = y0.shape
     if D != int(func.latent_dim):
         raise ValueError("y0 has {} columns but the vector field has latent_dim {}".format(D, func.latent_dim))
-    n_groups = int(options.get("n_groups", 1))
-    if n_groups < 1 or B % n_groups != 0:
+    if B % M != 0:
+        raise ValueError("y0 has {} rows, not a multiple of the {} ensemble members".format(B, M))
+    groups_per_member = int(options.get("n_groups", 1))
+    n_groups = groups_per_member * M
+    if groups_per_member < 1 or (B // M) % groups_per_member != 0:
         raise ValueError("n_groups must divide the batch")
     batch = B // n_groups
-    if func.dosage is None or func.times is None:
-        raise RuntimeError("set_action must be called before integrating (model.py:1113)")
-    dose_amt = func.dosage.detach().to(device=y0.device, dtype=torch.float32).contiguous()
-    dose_t = getattr(func, "_dose_t_f32", None)
-    if dose_t is None or dose_t.shape[0] != B:
-        dose_t = func.times.detach().to(device=y0.device, dtype=torch.float32).contiguous()
-    if dose_amt.shape[0] != B or dose_t.shape[0] != B:
-        raise RuntimeError("dose schedule has {} patients but y0 has {}".format(dose_amt.shape[0], B))
+    if M == 1:
+        dose_amt, dose_t = _dose_tensors(func, B, y0.device)
+    else:
+        parts = [_dose_tensors(f, B // M, y0.device) for f in funcs]
+        if len({p[1].shape[1:] for p in parts}) != 1:
+            raise RuntimeError("ensemble members must have the same number of doses per patient")
+        dose_amt = torch.cat([p[0] for p in parts]).contiguous()
+        dose_t = torch.cat([p[1] for p in parts]).contiguous()
     n_dose = dose_t.shape[1] if dose_t.dim() == 2 else 0
 
     ctrl_name = options.get("controller", "batch")
     if ctrl_name not in ("batch", "trajectory"):
         raise ValueError("controller must be 'batch' or 'trajectory'")
     need_grad = torch.is_grad_enabled() and (
-        y0.requires_grad or any(p.requires_grad for p in func.parameters())
+        y0.requires_grad or any(p.requires_grad for f in funcs for p in f.parameters())
     )
     cfg = ops.make_cfg(
         kind, D, L.METHODS[method],
@@ -302,11 +342,17 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
         ifactor=float(options.get("ifactor", 10.0)), dfactor=float(options.get("dfactor", 0.2)),
         first_step=options.get("first_step", None), max_num_steps=int(options.get("max_num_steps", 2 ** 31 - 1)),
         attempt_cap=int(options.get("attempt_cap", ops.ATTEMPT_CAP_DEFAULT)),
-        hill2=(kind == L.FIELD_ROCHE and bool(options.get("hill2_kernels", True)) and hill_exponents_are_two(func)),
+        hill2=(kind == L.FIELD_ROCHE and bool(options.get("hill2_kernels", True))
+               and all(hill_exponents_are_two(f) for f in funcs)),
     )
-    packed = pack_params(func, kind)
-    pb = ops.Problem(cfg, n_groups, batch, dose_amt, dose_t, None, None)
-    pb.params_shape = (1, packed.numel())
+    if M == 1:
+        packed = pack_params(func, kind)
+        pset = None
+    else:
+        packed = torch.stack([pack_params(f, kind) for f in funcs]).reshape(-1)
+        pset = torch.arange(M, dtype=torch.int32, device=y0.device).repeat_interleave(groups_per_member).contiguous()
+    pb = ops.Problem(cfg, n_groups, batch, dose_amt, dose_t, None, pset)
+    pb.params_shape = (M, packed.numel() // M)
 
     if fixed:
         if options.get("grid_constructor") is not None:

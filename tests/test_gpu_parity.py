@@ -262,6 +262,38 @@ def test_small_groups_share_warps_and_flat_launches_match_single_calls():
     assert relerr(out[:, :B], ref) < 5e-4
 
 
+@pytest.mark.parametrize("method,kw", [("rk4", dict(options={"step_size": 0.125})), ("dopri5", dict(rtol=1e-3, atol=1e-4))])
+def test_ensemble_members_with_own_weights_in_one_launch(method, kw):
+    """BASELINE config 4: M members, each with its own ml_net, integrated by ONE launch (parameter sets per group)
+    must equal M separate odeint calls, values and gradients."""
+    D, B, M = 8, 12, 3
+    members = [build_pair(D, seed=30 + i)[1] for i in range(M)]
+    # smooth cohort: the group reductions of the two launch shapes add in different orders, which must not be able to
+    # flip an accept/reject decision (see test_dopri5_identical_step_sequence_on_smooth_problem)
+    y0, a = smooth_cohort(B * M, D, seed=17)
+    t = torch.arange(0, 15.0).to(DEV)
+    W = torch.randn(15, B * M, D, generator=torch.Generator().manual_seed(4)).to(DEV)
+    for i, m in enumerate(members):
+        m.zero_grad(); m.set_action(a[:, i * B:(i + 1) * B].to(DEV))
+    zg = y0.clone().to(DEV).requires_grad_(True)
+    out = H.odeint_ensemble(members, zg, t, method=method, **kw)
+    (out * W).sum().backward()
+    ens_grads = [(m.ml_net[0].weight.grad.clone(), m.k_dexa.grad.clone()) for m in members]
+    for i, m in enumerate(members):
+        sl = slice(i * B, (i + 1) * B)
+        m.zero_grad()
+        z1 = y0[sl].clone().to(DEV).requires_grad_(True)
+        one = H.odeint(m, z1, t, method=method, **kw)
+        (one * W[:, sl]).sum().backward()
+        # shared-memory parameters (ensemble) vs constant-bank parameters (single call): same arithmetic, same order
+        assert relerr(out[:, sl], one) < (1e-6 if method == "rk4" else 1e-5), (method, i)
+        assert relerr(zg.grad[sl], z1.grad) < 1e-5
+        assert relerr(ens_grads[i][0], m.ml_net[0].weight.grad) < 1e-5
+        assert abs(ens_grads[i][1].item() - m.k_dexa.grad.item()) <= 1e-4 * max(1.0, abs(m.k_dexa.grad.item()))
+    with pytest.raises(ValueError):
+        H.odeint_ensemble(members, zg[:-1], t, method=method, **kw)
+
+
 def test_multi_warp_group_matches_oracle():
     D, B = 6, 200  # 7 warps in one CTA: exercises the shared-memory stage of the group reduction
     o, m = build_pair(D)
