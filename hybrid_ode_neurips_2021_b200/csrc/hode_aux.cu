@@ -300,7 +300,6 @@ __global__ void __launch_bounds__(TR * SPLIT) decode_sse_fast_kernel(
     if (nxt.tile < n_tiles) issue(nxt, 1);
     for (int it = 0; cur.tile < n_tiles; ++it) {
         const int stage = it & 1;
-        if (nxt.tile < n_tiles) load_h(nxt, hn);
         mbar_wait(&full[stage], (unsigned)(it >> 1) & 1u);  // tile `cur` has landed
         const int64_t t = cur.t;
         const int64_t b0 = cur.k * TR;
@@ -323,30 +322,53 @@ __global__ void __launch_bounds__(TR * SPLIT) decode_sse_fast_kernel(
             }
             float4* xr = reinterpret_cast<float4*>(sX + row * ldx);
             const float4* mr = reinterpret_cast<const float4*>(sM + row * ldx);
+            const float4* sB4 = reinterpret_cast<const float4*>(sB);
+            // Software pipeline (shared-memory latency would otherwise sit in front of every dependent FFMA chain):
+            // the x / mask / bias chunk is fetched one chunk ahead, the W rows one PAIR of observation columns ahead.
+            auto load_wpair = [&](int o, float (&w)[2][DP]) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int v = 0; v < DP / 4; ++v) {
+                        const float4 wv = reinterpret_cast<const float4*>(sW + (o + i) * DP)[v];
+                        w[i][4 * v] = wv.x; w[i][4 * v + 1] = wv.y; w[i][4 * v + 2] = wv.z; w[i][4 * v + 3] = wv.w;
+                    }
+            };
+            float4 xn, mn, bn;
+            float wn[2][DP];
+            if (q_lo < q_hi) {
+                xn = xr[q_lo]; mn = mr[q_lo]; bn = sB4[q_lo];
+                load_wpair(q_lo * 4, wn);
+            }
             for (int q = q_lo; q < q_hi; ++q) {
-                const float4 xv = xr[q], mv = mr[q];
-                const float4 bv = reinterpret_cast<const float4*>(sB)[q];
+                const float4 xv = xn, mv = mn, bv = bn;
+                if (q + 1 < q_hi) { xn = xr[q + 1]; mn = mr[q + 1]; bn = sB4[q + 1]; }
                 const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ms[4] = {mv.x, mv.y, mv.z, mv.w};
                 const float bs[4] = {bv.x, bv.y, bv.z, bv.w};
                 float cs[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    float w[DP];
+                for (int pr = 0; pr < 2; ++pr) {
+                    float w[2][DP];
 #pragma unroll
-                    for (int v = 0; v < DP / 4; ++v) {
-                        const float4 wv = reinterpret_cast<const float4*>(sW + (q * 4 + i) * DP)[v];
-                        w[4 * v] = wv.x; w[4 * v + 1] = wv.y; w[4 * v + 2] = wv.z; w[4 * v + 3] = wv.w;
+                    for (int i = 0; i < 2; ++i)
+#pragma unroll
+                        for (int d = 0; d < DP; ++d) w[i][d] = wn[i][d];
+                    if (pr == 0) load_wpair(q * 4 + 2, wn);
+                    else if (q + 1 < q_hi) load_wpair(q * 4 + 4, wn);
+#pragma unroll
+                    for (int i = 0; i < 2; ++i) {
+                        const int e = 2 * pr + i;
+                        float xh = bs[e];
+#pragma unroll
+                        for (int d = 0; d < D; ++d) xh = fmaf(w[i][d], hv[d], xh);
+                        const float diff = xs[e] - xh;
+                        const float dm = diff * ms[e];
+                        lsum = fmaf(diff, dm, lsum);
+                        const float c = scale * dm;
+#pragma unroll
+                        for (int d = 0; d < D; ++d) gh[d] = fmaf(c, w[i][d], gh[d]);
+                        cs[e] = c;
                     }
-                    float xh = bs[i];
-#pragma unroll
-                    for (int d = 0; d < D; ++d) xh = fmaf(w[d], hv[d], xh);
-                    const float diff = xs[i] - xh;
-                    const float dm = diff * ms[i];
-                    lsum = fmaf(diff, dm, lsum);
-                    const float c = scale * dm;
-#pragma unroll
-                    for (int d = 0; d < D; ++d) gh[d] = fmaf(c, w[d], gh[d]);
-                    cs[i] = c;
                 }
                 xr[q] = make_float4(cs[0], cs[1], cs[2], cs[3]);
             }
@@ -366,16 +388,26 @@ __global__ void __launch_bounds__(TR * SPLIT) decode_sse_fast_kernel(
             for (int d = 0; d < D; ++d) gp[d] = gh[d];
         }
         // ---- pass 2 -------------------------------------------------------------------------------------------
+        if (nxt.tile < n_tiles) load_h(nxt, hn);  // after this tile's h went to shared memory (no shared scoreboard)
         if (act2) {
-            for (int r = sub2; r < rows; r += nsub) {
-                const float4 cv = reinterpret_cast<const float4*>(sX + r * ldx)[cg2];
-                const float cs[4] = {cv.x, cv.y, cv.z, cv.w};
-                float hr[DP];
+            auto load_row = [&](int r, float4& cv, float (&hr)[DP]) {
+                cv = reinterpret_cast<const float4*>(sX + r * ldx)[cg2];
 #pragma unroll
                 for (int v = 0; v < DP / 4; ++v) {
                     const float4 q4 = reinterpret_cast<const float4*>(sH + r * DP)[v];
                     hr[4 * v] = q4.x; hr[4 * v + 1] = q4.y; hr[4 * v + 2] = q4.z; hr[4 * v + 3] = q4.w;
                 }
+            };
+            float4 cn;
+            float hnx[DP];
+            if (sub2 < rows) load_row(sub2, cn, hnx);
+            for (int r = sub2; r < rows; r += nsub) {  // one row ahead
+                const float4 cv = cn;
+                float hr[DP];
+#pragma unroll
+                for (int d = 0; d < DP; ++d) hr[d] = hnx[d];
+                if (r + nsub < rows) load_row(r + nsub, cn, hnx);
+                const float cs[4] = {cv.x, cv.y, cv.z, cv.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     gb[i] += cs[i];
