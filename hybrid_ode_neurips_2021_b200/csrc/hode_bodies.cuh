@@ -99,29 +99,41 @@ HODE_HD void fixed_fwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t i
     }
     int j = 1;
     const bool perturb = a.perturb != 0;
+    // loop-carried scalars instead of per-step index arithmetic: grid time, tape cursor, next output time
+    float t0 = a.grid[0];
+    float* tp = a.tape_y != nullptr ? a.tape_y + idx * D : nullptr;
+    const int64_t tape_stride = n_traj * D;
+    float tj = (j < a.n_t) ? a.t_eval_f[j] : INFINITY;
     for (int s = 0; s + 1 < a.n_grid; ++s) {
-        const float t0 = a.grid[s], t1 = a.grid[s + 1];
+        const float t1 = a.grid[s + 1];
         const float dt = sub_rn(t1, t0);
-        if (a.tape_y != nullptr) store_vec<D>(a.tape_y + ((int64_t)s * n_traj + idx) * D, y);
+        if (tp != nullptr) {
+            store_vec<D>(tp, y);
+            tp += tape_stride;
+        }
         fixed_step<F, METHOD>(sp, ds, t0, t1, dt, perturb, y, y1);
-        while (j < a.n_t && t1 >= a.t_eval_f[j]) {
-            const float tj = a.t_eval_f[j];
-            float* o = a.h_out + ((int64_t)j * n_traj + idx) * D;
-            if (tj == t0) {
-                store_vec<D>(o, y);
-            } else if (tj == t1) {
-                store_vec<D>(o, y1);
-            } else {  // _linear_interp
-                const float slope = div_rn(sub_rn(tj, t0), sub_rn(t1, t0));
-                float v[D];
+        if (t1 >= tj) {  // rare: an output time is reached (false for NaN times, like the reference's `while`)
+            while (j < a.n_t && t1 >= a.t_eval_f[j]) {
+                const float te = a.t_eval_f[j];
+                float* o = a.h_out + ((int64_t)j * n_traj + idx) * D;
+                if (te == t0) {
+                    store_vec<D>(o, y);
+                } else if (te == t1) {
+                    store_vec<D>(o, y1);
+                } else {  // _linear_interp
+                    const float slope = div_rn(sub_rn(te, t0), sub_rn(t1, t0));
+                    float v[D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) v[d] = y[d] + slope * (y1[d] - y[d]);
-                store_vec<D>(o, v);
+                    for (int d = 0; d < D; ++d) v[d] = y[d] + slope * (y1[d] - y[d]);
+                    store_vec<D>(o, v);
+                }
+                ++j;
             }
-            ++j;
+            tj = (j < a.n_t) ? a.t_eval_f[j] : INFINITY;
         }
 #pragma unroll
         for (int d = 0; d < D; ++d) y[d] = y1[d];
+        t0 = t1;
     }
 }
 
@@ -135,34 +147,44 @@ HODE_HD void fixed_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t i
     for (int d = 0; d < D; ++d) lam[d] = 0.0f;
     int j = a.n_t - 1;
     const bool perturb = a.perturb != 0;
+    // loop-carried scalars: grid time, tape cursor, time of the latest output not yet consumed
+    const int64_t tape_stride = n_traj * D;
+    const float* tp = a.tape_y + ((int64_t)(a.n_grid - 2) * n_traj + idx) * D;
+    float t1 = a.n_grid >= 1 ? a.grid[a.n_grid - 1] : 0.0f;
+    float tj = (j >= 1) ? a.t_eval_f[j] : -INFINITY;
     for (int s = a.n_grid - 2; s >= 0; --s) {
-        const float t0 = a.grid[s], t1 = a.grid[s + 1];
+        const float t0 = a.grid[s];
         const float dt = sub_rn(t1, t0);
         float y0[D], yb0[D], lam0[D];
-        load_vec<D>(a.tape_y + ((int64_t)s * n_traj + idx) * D, y0);
+        load_vec<D>(tp, y0);
+        tp -= tape_stride;
 #pragma unroll
         for (int d = 0; d < D; ++d) yb0[d] = 0.0f;
         // outputs emitted by this step in the forward pass: grid[s] < t_eval[j] <= grid[s+1]
-        while (j >= 1 && a.t_eval_f[j] > t0) {
-            const float tj = a.t_eval_f[j];
-            float g[D];
-            load_vec<D>(a.grad_h + ((int64_t)j * n_traj + idx) * D, g);
-            if (tj == t1) {
+        if (tj > t0) {
+            while (j >= 1 && a.t_eval_f[j] > t0) {
+                const float te = a.t_eval_f[j];
+                float g[D];
+                load_vec<D>(a.grad_h + ((int64_t)j * n_traj + idx) * D, g);
+                if (te == t1) {
 #pragma unroll
-                for (int d = 0; d < D; ++d) lam[d] += g[d];
-            } else {
-                const float slope = div_rn(sub_rn(tj, t0), sub_rn(t1, t0));
+                    for (int d = 0; d < D; ++d) lam[d] += g[d];
+                } else {
+                    const float slope = div_rn(sub_rn(te, t0), sub_rn(t1, t0));
 #pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    lam[d] += slope * g[d];
-                    yb0[d] += g[d] - slope * g[d];
+                    for (int d = 0; d < D; ++d) {
+                        lam[d] += slope * g[d];
+                        yb0[d] += g[d] - slope * g[d];
+                    }
                 }
+                --j;
             }
-            --j;
+            tj = (j >= 1) ? a.t_eval_f[j] : -INFINITY;
         }
         fixed_step_vjp<F, METHOD, EG>(sp, ds, t0, t1, dt, perturb, y0, lam, lam0, acc);
 #pragma unroll
         for (int d = 0; d < D; ++d) lam[d] = lam0[d] + yb0[d];
+        t1 = t0;
     }
     float g0[D];
     load_vec<D>(a.grad_h + idx * D, g0);
