@@ -9,7 +9,9 @@
  * Conventions
  *  - every pointer is a DEVICE pointer on the current CUDA device unless named host_*; the library never
  *    allocates, frees or retains memory; work is enqueued on `stream` (a cudaStream_t passed as void*) and the call
- *    returns without synchronising;
+ *    returns without synchronising.  Thread-safe.  The only library state is one per-device constant-memory copy of the
+ *    staged parameters used by launches with a single parameter set (param_set_of_group == NULL): such launches issued on
+ *    DIFFERENT streams of one device are ordered by an internal event (they would each fill the GPU anyway);
  *  - return value: HODE_OK, or a negative hode_status; hode_last_error() gives a per-thread message;
  *    solver failures (torchdiffeq's assertions) are reported per controller group in `stats`, not by return value;
  *  - trajectories are independent patients.  n_traj = n_groups * batch.  A "group" is what ONE reference odeint
