@@ -65,6 +65,8 @@ SIGNATURES = {
         [_CFG, _I64, _I64, _P, _P, _I64, _P, _P, _I32, _P, _I32, _P, _P, _P, _I32, _P, _P, _P, _P],
     ),
     "hode_bench_ffma": (_I64, [_I32, _I32, _P, _P]),
+    "hode_crps_ensemble": (_I32, [_P, _P, _I64, _I32, _I64, _I64, _P, _P]),
+    "hode_decode_crps": (_I32, [_I32, _I32, _I32, _I64, _I32, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P]),
     "hode_decode_sse": (_I32, [_I32, _I32, _I32, _I64, _F64, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P]),
 }
 

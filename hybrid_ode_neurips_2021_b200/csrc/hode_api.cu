@@ -15,6 +15,9 @@ int launch_decode_sse(int32_t, int32_t, int32_t, int64_t, double, const float*, 
                       const float*, const float*, int64_t, int64_t, int64_t, float*, float*, float*, float*,
                       cudaStream_t);
 int launch_ffma_probe(int, int, float*, cudaStream_t);
+int launch_crps_ensemble(const float*, const float*, int64_t, int32_t, int64_t, int64_t, float*, cudaStream_t);
+int launch_decode_crps(int32_t, int32_t, int32_t, int64_t, int32_t, const float*, const float*, const float*,
+                       const float*, int64_t, int64_t, int64_t, float*, cudaStream_t);
 }  // namespace hode
 
 using namespace hode;
@@ -225,6 +228,29 @@ int32_t hode_decode_sse(int32_t D, int32_t obs, int32_t n_t, int64_t n_traj, dou
     const int rc = launch_decode_sse(D, obs, n_t, n_traj, n_norm, h, W, b, x, mask, st, sb, so, loss, grad_h, grad_w,
                                      grad_b, (cudaStream_t)stream);
     if (rc == -1) return fail(HODE_ERR_UNSUPPORTED, "decode_sse: obs*D too large for one CTA's shared memory");
+    if (rc != 0) return fail(HODE_ERR_CUDA, "CUDA error: %s (%lld)", cudaGetErrorString((cudaError_t)rc), rc);
+    return HODE_OK;
+}
+
+int32_t hode_crps_ensemble(const float* truth, const float* forecasts, int64_t n, int32_t n_mc, int64_t stride_n,
+                           int64_t stride_mc, float* out, void* stream) {
+    if (n < 0 || n_mc < 1) return fail(HODE_ERR_ARG, "bad n / n_mc");
+    if (n == 0) return HODE_OK;
+    if (!truth || !forecasts || !out) return fail(HODE_ERR_ARG, "NULL pointer");
+    const int rc = launch_crps_ensemble(truth, forecasts, n, n_mc, stride_n, stride_mc, out, (cudaStream_t)stream);
+    if (rc == -1) return fail(HODE_ERR_UNSUPPORTED, "crps_ensemble: more than %s%lld ensemble members", "", 128);
+    if (rc != 0) return fail(HODE_ERR_CUDA, "CUDA error: %s (%lld)", cudaGetErrorString((cudaError_t)rc), rc);
+    return HODE_OK;
+}
+
+int32_t hode_decode_crps(int32_t D, int32_t obs, int32_t n_t, int64_t batch, int32_t n_mc, const float* h,
+                         const float* W, const float* b, const float* x, int64_t st, int64_t sb, int64_t so,
+                         float* crps, void* stream) {
+    if (D < 1 || obs < 1 || n_t < 1 || batch < 0 || n_mc < 1) return fail(HODE_ERR_ARG, "bad D / obs / n_t / batch / n_mc");
+    if (batch == 0) return HODE_OK;
+    if (!h || !W || !b || !x || !crps) return fail(HODE_ERR_ARG, "NULL pointer");
+    const int rc = launch_decode_crps(D, obs, n_t, batch, n_mc, h, W, b, x, st, sb, so, crps, (cudaStream_t)stream);
+    if (rc == -1) return fail(HODE_ERR_UNSUPPORTED, "decode_crps: latent_dim / n_mc (<= 128) / size not compiled in");
     if (rc != 0) return fail(HODE_ERR_CUDA, "CUDA error: %s (%lld)", cudaGetErrorString((cudaError_t)rc), rc);
     return HODE_OK;
 }

@@ -154,3 +154,32 @@ def decode_sse(lib, h, W, b, x, mask, n_norm, want_grads=True):
                              x.stride(0), x.stride(1), x.stride(2), _ptr(loss), _ptr(gh), _ptr(gw), _ptr(gb), _stream(h))
     lib.check(rc, "hode_decode_sse")
     return loss, gh, gw, gb
+
+
+def crps_ensemble(lib, truth, forecasts):
+    """``truth [...]``, ``forecasts [..., n_mc]`` (any strides on the last axis pair after flattening) -> CRPS ``[...]``."""
+    assert forecasts.shape[:-1] == truth.shape and truth.dtype == torch.float32 and forecasts.dtype == torch.float32
+    n_mc = forecasts.shape[-1]
+    t = truth.contiguous().reshape(-1)
+    f = forecasts.reshape(-1, n_mc)
+    if f.stride(0) != n_mc * f.stride(1) and not f.is_contiguous():
+        f = f.contiguous()
+    out = torch.empty_like(t)
+    rc = lib.hode_crps_ensemble(_ptr(t), _ptr(f), t.numel(), n_mc, f.stride(0), f.stride(1), _ptr(out), _stream(t))
+    lib.check(rc, "hode_crps_ensemble")
+    return out.reshape(truth.shape)
+
+
+def decode_crps(lib, h, W, b, x, n_mc):
+    """``h [n_t, n_mc * batch, D]`` (sample-major trajectories), ``x [n_t, batch, obs]`` -> CRPS ``[n_t, batch, obs]``."""
+    n_t, n_traj, D = h.shape
+    obs = W.shape[0]
+    assert n_traj % n_mc == 0
+    batch = n_traj // n_mc
+    assert x.shape == (n_t, batch, obs) and x.dtype == torch.float32
+    h, W, b = _f32c(h), _f32c(W), _f32c(b)
+    out = torch.empty(n_t, batch, obs, dtype=torch.float32, device=h.device)
+    rc = lib.hode_decode_crps(D, obs, n_t, batch, n_mc, _ptr(h), _ptr(W), _ptr(b), _ptr(x), x.stride(0), x.stride(1),
+                              x.stride(2), _ptr(out), _stream(h))
+    lib.check(rc, "hode_decode_crps")
+    return out

@@ -157,6 +157,19 @@ int32_t hode_decode_sse(int32_t D, int32_t obs, int32_t n_t, int64_t n_traj, dou
                         const float* W, const float* b, const float* x, const float* mask, int64_t st, int64_t sb,
                         int64_t so, float* loss, float* grad_h, float* grad_w, float* grad_b, void* stream);
 
+/* ---- Monte-Carlo evaluation (training_utils.py:144-177, evaluate / evaluate_horizon / evaluate_ensemble): the mc_itr
+ * decoder solves of a test chunk are ONE solve with n_groups = n_mc (trajectory index s * batch + b); the CRPS that the
+ * reference computes with properscoring.crps_ensemble in Python loops is
+ *     crps = mean_s |x_s - y| - 1/(2 n_mc^2) sum_{s,s'} |x_s - x_s'|          (n_mc <= 128).
+ * hode_crps_ensemble: truth [n], member s of element i at forecasts + i*stride_n + s*stride_mc  ->  out [n].
+ * hode_decode_crps:   x_s = W h[t, s*batch + b] + bias evaluated on the fly from the latent solution
+ *                     h [n_t, n_mc*batch, D]; observations x with element strides (st, sb, so) -> crps [n_t, batch, obs]. */
+int32_t hode_crps_ensemble(const float* truth, const float* forecasts, int64_t n, int32_t n_mc, int64_t stride_n,
+                           int64_t stride_mc, float* out, void* stream);
+int32_t hode_decode_crps(int32_t D, int32_t obs, int32_t n_t, int64_t batch, int32_t n_mc, const float* h,
+                         const float* W, const float* b, const float* x, int64_t st, int64_t sb, int64_t so,
+                         float* crps, void* stream);
+
 /* ---- measurement aid: FP32 FMA peak probe (the roofline denominator of the solver kernels; bench.py times it).
  * Launches `blocks` CTAs of 256 threads running 16 independent FFMA chains for `iters` iterations.
  * Returns the number of floating-point operations the launch performs (FMA = 2), or a negative hode_status. */

@@ -432,3 +432,50 @@ def test_failures_raise_like_torchdiffeq():
         H.odeint(m, y0, t.cpu())
     with pytest.warns(UserWarning, match="Unexpected arguments"):
         H.odeint(m, y0.to(DEV), t, method="midpoint", options={"step_size": 0.25, "step_t": [1.0]})
+
+
+def _crps_numpy(obs, fc):
+    """properscoring.crps_ensemble for equally weighted members, sorted-CDF form (independent of the kernel's pair sum)."""
+    obs = np.asarray(obs, dtype=np.float64)
+    fc = np.sort(np.asarray(fc, dtype=np.float64), axis=-1)
+    M = fc.shape[-1]
+    term1 = np.abs(fc - obs[..., None]).mean(axis=-1)
+    w = 2 * np.arange(M) - M + 1  # E|X - X'| = 2 / M^2 * sum_i (2i - M + 1) x_(i)
+    term2 = (fc * w).sum(axis=-1) * 2.0 / M ** 2
+    return term1 - 0.5 * term2
+
+
+@pytest.mark.parametrize("M", [1, 7, 50, 128])
+def test_crps_ensemble_kernel_matches_properscoring_formula(M):
+    g = torch.Generator().manual_seed(M)
+    truth = torch.randn(5, 33, 3, generator=g)
+    fc = truth[..., None] * 0.5 + torch.randn(5, 33, 3, M, generator=g)
+    out = H.crps_ensemble(truth.to(DEV), fc.to(DEV))
+    ref = _crps_numpy(truth.numpy(), fc.numpy())
+    assert out.shape == truth.shape
+    assert np.abs(out.cpu().numpy() - ref).max() < 2e-6
+    # non-contiguous member axis (the reference stacks samples on the LAST axis of [T, B, obs, mc], training_utils.py:165)
+    fc_t = fc.permute(3, 0, 1, 2).contiguous().to(DEV).permute(1, 2, 3, 0)
+    out2 = H.crps_ensemble(truth.to(DEV), fc_t)
+    assert torch.equal(out, out2)
+
+
+def test_mc_evaluation_chunk_equals_separate_solves():
+    """training_utils.py:144-177: mc decoder solves + CRPS loops == one launch + fused read-out/CRPS kernel."""
+    D, obs, B, mc, t0 = 6, 20, 9, 11, 5
+    torch.manual_seed(3)
+    dec = H.RocheExpertDecoder(obs, D, 1, 14, 1, method="dopri5", device=DEV)
+    y0, a, x, mask = make_cohort(B, D, obs=obs, seed=21)
+    a, x, mask = a.to(DEV), x.to(DEV), mask.to(DEV)
+    z_samples = (y0[None] * (1 + 0.3 * torch.randn(mc, B, D))).abs().to(DEV)
+    res = H.evaluate_chunk(dec, y0.to(DEV), z_samples, a, x, mask, t0)
+    with torch.no_grad():
+        xs = torch.stack([dec(z_samples[s], a)[0] for s in range(mc)], dim=-1)[t0:]  # [T', B, obs, mc]
+    ref = _crps_numpy(x[t0:].cpu().numpy(), xs.cpu().numpy())
+    assert res["crps_x_full"].shape == (15 - t0, B, obs)
+    assert np.abs(res["crps_x_full"].cpu().numpy() - ref).max() < 1e-5 * max(1.0, np.abs(ref).max())
+    assert np.abs(res["crps_x"].cpu().numpy() - ref.mean(axis=(0, 2))).max() < 1e-5 * max(1.0, np.abs(ref).max())
+    with torch.no_grad():
+        xh = dec(y0.to(DEV), a)[0][t0:]
+    se = torch.sum((x[t0:] - xh) ** 2 * mask[t0:], dim=(0, 2)) / torch.sum(mask[t0:], dim=(0, 2))
+    assert torch.allclose(res["se_x"], se)
