@@ -407,6 +407,11 @@ def run_ours(args):
                                     "peak_source": hbm_src, "algorithmic_bytes_per_launch": dec_bytes},
         }
         del h, tape, gh
+        if not args.no_extras:
+            try:
+                extra["other_configs"] = dopri5_extras(lib, dev)
+            except Exception as e:  # secondary figures must never take the headline down
+                extra["other_configs"] = {"error": repr(e)}
 
     if rank != 0:
         if world > 1:
@@ -442,6 +447,55 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def dopri5_extras(lib, dev):
+    """Secondary figures (not the headline): adaptive dopri5 at the reference tolerances (rtol 1e-7 / atol 1e-8,
+    model.py:1079-1080), forward + tape + reverse sweep, batch-coupled controller = one controller per odeint call.
+    C3 shape (run_dim.sh:41): D = 12, groups of 10 patients; C1 shape (sim_config.py:52): D = 6, groups of 50.
+    1 trajectory-step = one attempt (accepted or rejected) of one trajectory."""
+    import hybrid_ode_neurips_2021_b200 as H
+    from hybrid_ode_neurips_2021_b200 import _lib as L
+    from hybrid_ode_neurips_2021_b200 import ops, solver
+
+    out = {}
+    for name, Dd, groups, batch in (("C3_dim12_dopri5_groups_of_10", 12, 8192, 10), ("C1_dim6_dopri5_groups_of_50", 6, 2048, 50)):
+        Bt = groups * batch
+        torch.manual_seed(666)
+        m = H.RocheODE(Dd, 1, T_MAX, 1, device=dev)
+        g = torch.Generator(device=dev).manual_seed(5)
+        y0 = torch.empty(Bt, Dd, device=dev).exponential_(100.0, generator=g)
+        a = torch.zeros(T, Bt, 1, device=dev)
+        a[torch.randint(0, T_MAX, (Bt,), device=dev, generator=g), torch.arange(Bt, device=dev), 0] = \
+            torch.rand(Bt, device=dev, generator=g) * 10 + 1e-3
+        m.set_action(a)
+        tt = torch.arange(0, T_MAX + 1, 1, device=dev, dtype=torch.float64)
+        cfg = ops.make_cfg(L.FIELD_ROCHE, Dd, L.DOPRI5, n_dose=1, expert_grads=False, hill2=True, rtol=1e-7, atol=1e-8)
+        pb = ops.Problem(cfg, groups, batch, m.dosage, m._dose_t_f32,
+                         solver.pack_params(m, L.FIELD_ROCHE).detach()[None].contiguous(), None)
+
+        def ev(fn, n=3):
+            fn(); torch.cuda.synchronize()
+            ts = []
+            for _ in range(n):
+                s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s_.record(); r = fn(); e_.record(); torch.cuda.synchronize()
+                ts.append(s_.elapsed_time(e_))
+            return statistics.median(ts), r
+
+        t_f, (h, stats, tape) = ev(lambda: ops.dopri5_fwd(lib, pb, y0, tt, 768))
+        st = stats.cpu()
+        if int(st[:, 3].max()) != 0:
+            out[name] = {"error": "solver status {}".format(st[:, 3].unique().tolist())}
+            continue
+        gh = torch.randn_like(h)
+        t_b, _ = ev(lambda: ops.dopri5_bwd(lib, pb, tt, gh, tape, stats))
+        attempts = int((st[:, 0] + st[:, 1]).sum()) * batch
+        out[name] = {"value": attempts / ((t_f + t_b) * 1e-3), "unit": UNIT, "fwd_ms": t_f, "bwd_ms": t_b, "patients": Bt,
+                     "accepted_per_call": float(st[:, 0].float().mean()), "rejected_per_call": float(st[:, 1].float().mean()),
+                     "latent_dim": Dd, "batch_per_odeint_call": batch}
+        del h, tape, gh
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -452,6 +506,7 @@ def main():
     ap.add_argument("--cpu-patients", type=int, default=8192, help="bounded CPU-baseline sample")
     ap.add_argument("--ref-patients", type=int, default=4096, help="patients per step of --impl reference")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="host mini-batches per step of the end-to-end measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary dopri5 figures")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

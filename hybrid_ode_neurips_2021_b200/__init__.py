@@ -7,6 +7,7 @@ hard error (there is no CPU fallback).
 """
 from .solver import odeint, odeint_ensemble, last_solve_info, fixed_grid_points  # noqa: F401
 from .model import RocheODE, NeuralODE, RocheExpertDecoder, RochConfig  # noqa: F401
+from .real import RocheODEReal, NeuralODEReal, NeuralODEReal2nd, DecoderReal  # noqa: F401
 from .loss import masked_sse, decode_sse_loss  # noqa: F401
 from .integrate import install_as_torchdiffeq, patch_model  # noqa: F401
 from .evaluation import crps_ensemble, mc_solve, decode_crps, evaluate_chunk  # noqa: F401

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, LIB_NAME)
 
 # enums of include/hode.h
 FIELD_ROCHE, FIELD_NEURAL = 0, 1
+FIELD_ROCHE_REAL, FIELD_NEURAL_REAL, FIELD_NEURAL_REAL_2ND = 2, 3, 4
 EULER, MIDPOINT, RK4_38, DOPRI5 = 0, 1, 2, 3
 CTRL_BATCH, CTRL_TRAJ = 0, 1
 FLAG_HILL2 = 1
@@ -65,6 +66,10 @@ SIGNATURES = {
         [_CFG, _I64, _I64, _P, _P, _I64, _P, _P, _I32, _P, _I32, _P, _P, _P, _I32, _P, _P, _P, _P],
     ),
     "hode_bench_ffma": (_I64, [_I32, _I32, _P, _P]),
+    "hode_real_param_count": (_I64, [_I32, _I32, _I32]),
+    "hode_real_dose_tables": (_I32, [_I32, _P, _I64, _I64, _I32, _I64, _P, _P, _P]),
+    "hode_real_fixed_fwd": (_I32, [_I32, _I32, _I32, _I32, _I32, _I64, _P, _P, _I32, _P, _P, _I32, _P, _I32, _P, _P, _P]),
+    "hode_real_fixed_bwd": (_I32, [_I32, _I32, _I32, _I32, _I32, _I64, _P, _I32, _P, _P, _I32, _P, _I32, _P, _P, _P, _P, _P]),
     "hode_crps_ensemble": (_I32, [_P, _P, _I64, _I32, _I64, _I64, _P, _P]),
     "hode_decode_crps": (_I32, [_I32, _I32, _I32, _I64, _I32, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P]),
     "hode_decode_sse": (_I32, [_I32, _I32, _I32, _I64, _F64, _P, _P, _P, _P, _P, _I64, _I64, _I64, _P, _P, _P, _P, _P]),

@@ -15,6 +15,16 @@ int launch_decode_sse(int32_t, int32_t, int32_t, int64_t, double, const float*, 
                       const float*, const float*, int64_t, int64_t, int64_t, float*, float*, float*, float*,
                       cudaStream_t);
 int launch_ffma_probe(int, int, float*, cudaStream_t);
+struct RealArgs {
+    SolveArgs a;
+    const float* tab;
+    int32_t T;
+    int32_t hidden;
+    int32_t P;
+};
+int real_param_count(int, int, int);
+int launch_real_dose_table(int, const float*, int64_t, int64_t, int32_t, int64_t, const float*, float*, cudaStream_t);
+int launch_real_fixed(bool, int, int, int, const RealArgs&, cudaStream_t);
 int launch_crps_ensemble(const float*, const float*, int64_t, int32_t, int64_t, int64_t, float*, cudaStream_t);
 int launch_decode_crps(int32_t, int32_t, int32_t, int64_t, int32_t, const float*, const float*, const float*,
                        const float*, int64_t, int64_t, int64_t, float*, cudaStream_t);
@@ -228,6 +238,70 @@ int32_t hode_decode_sse(int32_t D, int32_t obs, int32_t n_t, int64_t n_traj, dou
     const int rc = launch_decode_sse(D, obs, n_t, n_traj, n_norm, h, W, b, x, mask, st, sb, so, loss, grad_h, grad_w,
                                      grad_b, (cudaStream_t)stream);
     if (rc == -1) return fail(HODE_ERR_UNSUPPORTED, "decode_sse: obs*D too large for one CTA's shared memory");
+    if (rc != 0) return fail(HODE_ERR_CUDA, "CUDA error: %s (%lld)", cudaGetErrorString((cudaError_t)rc), rc);
+    return HODE_OK;
+}
+
+int64_t hode_real_param_count(int32_t field, int32_t latent_dim, int32_t hidden) {
+    return real_param_count(field, latent_dim, hidden);
+}
+
+int32_t hode_real_dose_tables(int32_t field, const float* action, int64_t stride_t, int64_t stride_b, int32_t T,
+                              int64_t n_traj, const float* params, float* tab, void* stream) {
+    if (field < HODE_FIELD_ROCHE_REAL || field > HODE_FIELD_NEURAL_REAL_2ND) return fail(HODE_ERR_ARG, "not a real-data field");
+    if (T < 1 || n_traj < 0) return fail(HODE_ERR_ARG, "bad T / n_traj");
+    if (n_traj == 0) return HODE_OK;
+    if (!action || !tab || (field == HODE_FIELD_ROCHE_REAL && !params)) return fail(HODE_ERR_ARG, "NULL pointer");
+    const int rc = launch_real_dose_table(field, action, stride_t, stride_b, T, n_traj, params, tab, (cudaStream_t)stream);
+    if (rc != 0) return fail(HODE_ERR_CUDA, "CUDA error: %s (%lld)", cudaGetErrorString((cudaError_t)rc), rc);
+    return HODE_OK;
+}
+
+static int real_common(bool bwd, int32_t field, int32_t latent_dim, int32_t hidden, int32_t method, int32_t perturb,
+                       int64_t n_traj, const float* tab, int32_t T, const float* params, const float* grid, int32_t n_grid,
+                       const float* t_eval, int32_t n_t, RealArgs& r) {
+    const int P = real_param_count(field, latent_dim, hidden);
+    if (P < 0) return fail(HODE_ERR_UNSUPPORTED, "real-data field / latent_dim / hidden (<= 64) %s%lld is not compiled in", "", latent_dim);
+    if (method < HODE_EULER || method > HODE_RK4_38) return fail(HODE_ERR_UNSUPPORTED, "real-data fields are integrated with euler / midpoint / rk4 only (method %s%lld)", "", method);
+    if (n_traj < 0 || n_grid < 1 || n_t < 1 || T < 1) return fail(HODE_ERR_ARG, "bad sizes");
+    if (!tab || !params || !grid || !t_eval) return fail(HODE_ERR_ARG, "NULL pointer");
+    memset(&r, 0, sizeof(r));
+    r.a.n_groups = 1; r.a.batch = n_traj; r.a.params = params; r.a.perturb = perturb;
+    r.a.grid = grid; r.a.n_grid = n_grid; r.a.t_eval_f = t_eval; r.a.n_t = n_t;
+    r.tab = tab; r.T = T; r.hidden = hidden; r.P = P;
+    (void)bwd;
+    return HODE_OK;
+}
+
+int32_t hode_real_fixed_fwd(int32_t field, int32_t latent_dim, int32_t hidden, int32_t method, int32_t perturb,
+                            int64_t n_traj, const float* y0, const float* tab, int32_t T, const float* params,
+                            const float* grid, int32_t n_grid, const float* t_eval, int32_t n_t, float* h_out,
+                            float* tape, void* stream) {
+    RealArgs r;
+    int rc = real_common(false, field, latent_dim, hidden, method, perturb, n_traj, tab, T, params, grid, n_grid, t_eval, n_t, r);
+    if (rc) return rc;
+    if (n_traj == 0) return HODE_OK;
+    if (!y0 || !h_out) return fail(HODE_ERR_ARG, "NULL y0 / h_out");
+    r.a.y0 = y0; r.a.h_out = h_out; r.a.tape_y = tape;
+    rc = launch_real_fixed(false, field, latent_dim, method, r, (cudaStream_t)stream);
+    if (rc != 0) return fail(HODE_ERR_CUDA, "CUDA error: %s (%lld)", cudaGetErrorString((cudaError_t)rc), rc);
+    return HODE_OK;
+}
+
+int32_t hode_real_fixed_bwd(int32_t field, int32_t latent_dim, int32_t hidden, int32_t method, int32_t perturb,
+                            int64_t n_traj, const float* tab, int32_t T, const float* params, const float* grid,
+                            int32_t n_grid, const float* t_eval, int32_t n_t, const float* grad_h, const float* tape,
+                            float* grad_y0, float* grad_params, void* stream) {
+    RealArgs r;
+    int rc = real_common(true, field, latent_dim, hidden, method, perturb, n_traj, tab, T, params, grid, n_grid, t_eval, n_t, r);
+    if (rc) return rc;
+    if (!grad_params) return fail(HODE_ERR_ARG, "NULL grad_params");
+    cudaError_t e = cudaMemsetAsync(grad_params, 0, sizeof(float) * (size_t)r.P, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(HODE_ERR_CUDA, "CUDA error: %s (%lld)", cudaGetErrorString(e), (long long)e);
+    if (n_traj == 0) return HODE_OK;
+    if (!grad_h || !grad_y0 || (n_grid > 1 && !tape)) return fail(HODE_ERR_ARG, "NULL grad_h / grad_y0 / tape");
+    r.a.grad_h = grad_h; r.a.tape_y = const_cast<float*>(tape); r.a.grad_y0 = grad_y0; r.a.grad_params = grad_params;
+    rc = launch_real_fixed(true, field, latent_dim, method, r, (cudaStream_t)stream);
     if (rc != 0) return fail(HODE_ERR_CUDA, "CUDA error: %s (%lld)", cudaGetErrorString((cudaError_t)rc), rc);
     return HODE_OK;
 }

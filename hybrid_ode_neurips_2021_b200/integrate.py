@@ -30,4 +30,10 @@ def patch_model(module):
     module.RocheODE = _model.RocheODE
     module.NeuralODE = _model.NeuralODE
     module.RocheExpertDecoder = _model.RocheExpertDecoder
+    from . import real as _real
+
+    module.RocheODEReal = _real.RocheODEReal
+    module.NeuralODEReal = _real.NeuralODEReal
+    module.NeuralODEReal2nd = _real.NeuralODEReal2nd
+    module.DecoderReal = _real.DecoderReal
     return module

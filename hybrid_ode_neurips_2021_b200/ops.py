@@ -183,3 +183,40 @@ def decode_crps(lib, h, W, b, x, n_mc):
                               x.stride(2), _ptr(out), _stream(h))
     lib.check(rc, "hode_decode_crps")
     return out
+
+
+# ---- real-data fields (hode_real_*) ----------------------------------------------------------------------------------
+def real_dose_tables(lib, field, action, params):
+    """``action [T, B, 1]`` -> dose table ``[2 or 1, T + 1, B]`` (``params`` supplies ``kel`` for RocheODEReal)."""
+    assert action.dim() == 3 and action.shape[2] == 1 and action.dtype == torch.float32
+    T, B = action.shape[0], action.shape[1]
+    tab = torch.empty(2 if field == L.FIELD_ROCHE_REAL else 1, T + 1, B, dtype=torch.float32, device=action.device)
+    rc = lib.hode_real_dose_tables(int(field), _ptr(action), action.stride(0), action.stride(1), T, B, _ptr(params),
+                                   _ptr(tab), _stream(action))
+    lib.check(rc, "hode_real_dose_tables")
+    return tab
+
+
+def real_fixed_fwd(lib, field, D, hidden, method, perturb, y0, tab, params, grid, t_eval, want_tape):
+    y0 = _f32c(y0)
+    B = y0.shape[0]
+    n_t, n_grid = t_eval.numel(), grid.numel()
+    h = torch.empty(n_t, B, D, dtype=torch.float32, device=y0.device)
+    tape = torch.empty(max(n_grid - 1, 0), B, D, dtype=torch.float32, device=y0.device) if want_tape else None
+    rc = lib.hode_real_fixed_fwd(int(field), D, int(hidden), int(method), int(bool(perturb)), B, _ptr(y0), _ptr(tab),
+                                 tab.shape[1] - 1, _ptr(params), _ptr(grid), n_grid, _ptr(t_eval), n_t, _ptr(h),
+                                 _ptr(tape), _stream(y0))
+    lib.check(rc, "hode_real_fixed_fwd")
+    return h, tape
+
+
+def real_fixed_bwd(lib, field, D, hidden, method, perturb, tab, params, grid, t_eval, grad_h, tape):
+    grad_h = _f32c(grad_h)
+    B = grad_h.shape[1]
+    gy0 = torch.empty(B, D, dtype=torch.float32, device=grad_h.device)
+    gp = torch.empty_like(params)
+    rc = lib.hode_real_fixed_bwd(int(field), D, int(hidden), int(method), int(bool(perturb)), B, _ptr(tab),
+                                 tab.shape[1] - 1, _ptr(params), _ptr(grid), grid.numel(), _ptr(t_eval), t_eval.numel(),
+                                 _ptr(grad_h), _ptr(tape), _ptr(gy0), _ptr(gp), _stream(grad_h))
+    lib.check(rc, "hode_real_fixed_bwd")
+    return gy0, gp

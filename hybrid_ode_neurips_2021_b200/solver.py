@@ -275,12 +275,47 @@ def odeint_ensemble(funcs, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=
     return _odeint_impl(funcs, y0, t, rtol, atol, method, options, None)
 
 
+def _odeint_real(func, kind, y0, t, method, options):
+    """Real-data fields (model.py:570-769): fixed-grid solvers only, one parameter set, dose tables built per launch."""
+    global _last_info
+    from . import real as _real
+
+    if not isinstance(y0, torch.Tensor) or not y0.is_cuda:
+        raise RuntimeError("hybrid_ode odeint runs on CUDA (sm_100a) only. There is no CPU fallback.")
+    if y0.dtype != torch.float32 or y0.dim() != 2:
+        raise NotImplementedError("real-data fields integrate float32 states of shape [batch, latent_dim]")
+    method = "dopri5" if method is None else method
+    if method not in L.METHODS:
+        raise ValueError('Invalid method "{}". Must be one of {}'.format(method, "{" + ", ".join(L.METHODS) + "}"))
+    if method == "dopri5":
+        raise NotImplementedError("the real-data fields are integrated with euler / midpoint / rk4 only "
+                                  "(experiments/real.sh:9-17); dopri5 on them has no fused kernel")
+    options = {} if options is None else dict(options)
+    unused = {k: v for k, v in options.items() if k not in (_FIXED_KEYS | _OUR_KEYS)}
+    if unused:
+        warnings.warn("{}: Unexpected arguments {}".format(_NAMES[method], unused))
+    if y0.shape[1] != int(func.latent_dim):
+        raise ValueError("y0 has {} columns but the vector field has latent_dim {}".format(y0.shape[1], func.latent_dim))
+    need_grad = torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in func.parameters()))
+    t_dev, grid = _times_for(t, options.get("step_size"), y0.device, True)
+    h = _real.solve_real(func, kind, y0, method, bool(options.get("perturb", False)), grid, t_dev, need_grad)
+    _last_info = SolveInfo(None, (grid.numel() - 1) * y0.shape[0])
+    return h
+
+
 def _odeint_impl(funcs, y0, t, rtol, atol, method, options, event_fn):
     global _last_info
     func = funcs[0]
     M = len(funcs)
     if event_fn is not None:
         raise NotImplementedError("event_fn is not used by the reference and has no fused kernel")
+    from .real import real_field_kind
+
+    rk = real_field_kind(func)
+    if rk is not None:
+        if M != 1:
+            raise NotImplementedError("odeint_ensemble is built for the simulation fields only")
+        return _odeint_real(func, rk, y0, t, method, options)
     kind = field_kind(func)
     for f in funcs[1:]:
         if field_kind(f) != kind or int(f.latent_dim) != int(func.latent_dim):

@@ -49,7 +49,14 @@ typedef enum hode_status {
 } hode_status;
 
 /* vector field: model.py:446-555 (RocheODE, ablate=False) / model.py:969-1026 (NeuralODE) */
-typedef enum hode_field { HODE_FIELD_ROCHE = 0, HODE_FIELD_NEURAL = 1 } hode_field;
+typedef enum hode_field {
+    HODE_FIELD_ROCHE = 0,
+    HODE_FIELD_NEURAL = 1,
+    /* real-data (ICU) fields, hode_real_* entry points only: model.py:570-657, 717-769, 660-714 */
+    HODE_FIELD_ROCHE_REAL = 2,
+    HODE_FIELD_NEURAL_REAL = 3,
+    HODE_FIELD_NEURAL_REAL_2ND = 4
+} hode_field;
 
 /* torchdiffeq SOLVERS keys used by the reference: 'euler', 'midpoint', 'rk4' (= 3/8 rule), 'dopri5' */
 typedef enum hode_method { HODE_EULER = 0, HODE_MIDPOINT = 1, HODE_RK4_38 = 2, HODE_DOPRI5 = 3 } hode_method;
@@ -156,6 +163,29 @@ int32_t hode_dopri5_bwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, co
 int32_t hode_decode_sse(int32_t D, int32_t obs, int32_t n_t, int64_t n_traj, double n_norm, const float* h,
                         const float* W, const float* b, const float* x, const float* mask, int64_t st, int64_t sb,
                         int64_t so, float* loss, float* grad_h, float* grad_w, float* grad_b, void* stream);
+
+/* ---- real-data vector fields: RocheODEReal / NeuralODEReal / NeuralODEReal2nd behind DecoderReal.forward
+ * (model.py:833-862), which integrates them with the fixed-grid solvers only (experiments/real.sh:9-17: midpoint, rk4;
+ * options step_size = 1, perturb = True).  latent_dim in {4, 20} (RocheReal, NeuralReal) / {8, 40} (2nd); hidden <= 64.
+ * Packed parameters (float32, hode_real_param_count()):
+ *   ROCHE_REAL     : k_immunity, kel, kel2, dx1_net.0.weight [H,3], dx1_net.0.bias [H], dx1_net.2.weight [H],
+ *                    dx1_net.2.bias, dx2_net.0.weight [H,2], dx2_net.0.bias [H], dx2_net.2.weight [H], dx2_net.2.bias,
+ *                    lin_hh.weight, lin_hz.weight, lin_hr.weight [Z-4, Z-4] each (absent for Z == 4)
+ *   NEURAL_REAL(_2ND): ml_net.0.weight [H, Z+1], ml_net.0.bias [H], ml_net.2.weight [OUT, H], ml_net.2.bias [OUT]
+ * hode_real_dose_tables replaces set_action_static + the O(T) dose_at_time sums (model.py:646-657, 753-760) by a
+ * per-launch table, `tab` [2 if ROCHE_REAL else 1][T+1][n_traj] float32 (ROCHE_REAL reads kel = params[1]); it must be
+ * rebuilt whenever the actions or kel change.  One parameter set per call; expert-style scalar gradients always on. */
+int64_t hode_real_param_count(int32_t field, int32_t latent_dim, int32_t hidden);
+int32_t hode_real_dose_tables(int32_t field, const float* action, int64_t stride_t, int64_t stride_b, int32_t T,
+                              int64_t n_traj, const float* params, float* tab, void* stream);
+int32_t hode_real_fixed_fwd(int32_t field, int32_t latent_dim, int32_t hidden, int32_t method, int32_t perturb,
+                            int64_t n_traj, const float* y0, const float* tab, int32_t T, const float* params,
+                            const float* grid, int32_t n_grid, const float* t_eval, int32_t n_t, float* h_out,
+                            float* tape, void* stream);
+int32_t hode_real_fixed_bwd(int32_t field, int32_t latent_dim, int32_t hidden, int32_t method, int32_t perturb,
+                            int64_t n_traj, const float* tab, int32_t T, const float* params, const float* grid,
+                            int32_t n_grid, const float* t_eval, int32_t n_t, const float* grad_h, const float* tape,
+                            float* grad_y0, float* grad_params, void* stream);
 
 /* ---- Monte-Carlo evaluation (training_utils.py:144-177, evaluate / evaluate_horizon / evaluate_ensemble): the mc_itr
  * decoder solves of a test chunk are ONE solve with n_groups = n_mc (trajectory index s * batch + b); the CRPS that the

@@ -141,3 +141,110 @@ class OracleDecoder(nn.Module):
 def masked_sse(x, x_hat, mask):
     """Likelihood term of ``VariationalInference.loss`` (model.py:1179): ``sum((x - x_hat)^2 * mask) / B``."""
     return torch.sum((x - x_hat) ** 2 * mask) / x.shape[1]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# real-data (ICU) fields: model.py:570-769, decoder model.py:772-862
+# ----------------------------------------------------------------------------------------------------------------------
+class OracleRocheODEReal(nn.Module):
+    """``RocheODEReal`` (model.py:570-657): learned expert nets + GRU-ODE latent block; dose = sum over ALL past doses."""
+
+    def __init__(self, latent_dim, hidden_dim, dtype=torch.float32):
+        super().__init__()
+        self.latent_dim, self.hidden_dim, self.expert_dim = int(latent_dim), int(hidden_dim), 4
+        H = self.hidden_dim
+        self.dx1_net = nn.Sequential(nn.Linear(3, H), nn.Tanh(), nn.Linear(H, 1), nn.Tanh()).to(dtype)
+        self.dx2_net = nn.Sequential(nn.Linear(2, H), nn.Tanh(), nn.Linear(H, 1), nn.Tanh()).to(dtype)
+        self.expert_only = self.latent_dim == self.expert_dim
+        if not self.expert_only:
+            m = self.latent_dim - self.expert_dim
+            self.lin_hh = nn.Linear(m, m, bias=False).to(dtype)
+            self.lin_hz = nn.Linear(m, m, bias=False).to(dtype)
+            self.lin_hr = nn.Linear(m, m, bias=False).to(dtype)
+        self.k_immunity = nn.Parameter(torch.tensor(1.0, dtype=dtype))
+        self.kel = nn.Parameter(torch.tensor(0.2, dtype=dtype))
+        self.kel2 = nn.Parameter(torch.tensor(0.2, dtype=dtype))
+        self.dosage = None
+        self.times = None
+
+    def set_action_static(self, action, static):
+        self.dosage = action
+        self.times = torch.cumsum(torch.ones_like(action), dim=0)
+
+    def dose_at_time(self, t):
+        inside_exp = self.kel * (self.times - t) * (t >= self.times)
+        return torch.sum(self.dosage * torch.exp(inside_exp) * (t >= self.times), dim=(0, 2))
+
+    def forward(self, t, y):
+        react, dose2 = y[:, 1], y[:, 3]
+        dose = self.dose_at_time(t)
+        d1 = self.dx1_net(y[:, :3])
+        d2 = self.dx2_net(y[:, :2])
+        d3 = (react * self.k_immunity)[..., None]
+        d4 = (self.kel * dose - self.kel2 * dose2)[..., None]
+        if self.expert_only:
+            return torch.cat([d1, d2, d3, d4], dim=-1)
+        x = 0
+        h = y[..., self.expert_dim:]
+        r = torch.sigmoid(x + self.lin_hr(h))
+        z = torch.sigmoid(x + self.lin_hz(h))
+        u = torch.tanh(x + self.lin_hh(r * h))
+        return torch.cat([d1, d2, d3, d4, (1 - z) * (u - h)], dim=-1)
+
+
+class OracleNeuralODEReal(nn.Module):
+    """``NeuralODEReal`` (model.py:717-769) and, with ``second=True``, ``NeuralODEReal2nd`` (model.py:660-714)."""
+
+    def __init__(self, latent_dim, hidden_dim, second=False, dtype=torch.float32):
+        super().__init__()
+        self.latent_dim, self.hidden_dim, self.second = int(latent_dim), int(hidden_dim), bool(second)
+        out = self.latent_dim // 2 if second else self.latent_dim
+        self.ml_net = nn.Sequential(nn.Linear(self.latent_dim + 1, self.hidden_dim), nn.Tanh(),
+                                    nn.Linear(self.hidden_dim, out), nn.Tanh()).to(dtype)
+        self.action = None
+        self.static = None
+
+    def set_action_static(self, action, static):
+        self.action = action
+        self.static = static[0, :, :]
+
+    def dose_at_time(self, t):
+        t_int = int(t)
+        if t_int >= self.action.shape[0]:
+            return torch.zeros_like(self.action[0, :, :])
+        return torch.cumsum(self.action, dim=0)[t_int, :, :]
+
+    def forward(self, t, y):
+        out = self.ml_net(torch.cat([y, self.dose_at_time(t)], dim=-1))
+        if self.second:
+            return torch.cat([out, y[..., : (self.latent_dim // 2)]], dim=-1)
+        return out
+
+
+class OracleDecoderReal(nn.Module):
+    """``DecoderReal`` (model.py:772-862), 2-D ``init`` branch: ``t = arange(t0 - 1, t_max)``, fixed-grid solver with
+    ``options = {step_t, step_size, perturb: True}``, read-out MLP ``Linear -> ELU -> Linear``, ``x_hat = out[1:]``."""
+
+    def __init__(self, obs_dim, latent_dim, hidden_dim, t_max, t0=24, method="midpoint", ode_step_size=1.0,
+                 ode_type="hybrid", dtype=torch.float32):
+        super().__init__()
+        self.t_max, self.t0, self.method = t_max, t0, method
+        self.output_function = nn.Sequential(nn.Linear(latent_dim, latent_dim + 1), nn.ELU(),
+                                             nn.Linear(latent_dim + 1, obs_dim)).to(dtype)
+        if ode_type == "neural":
+            self.ode = OracleNeuralODEReal(latent_dim, hidden_dim, False, dtype)
+        elif ode_type == "2nd":
+            self.ode = OracleNeuralODEReal(latent_dim, hidden_dim, True, dtype)
+        else:
+            self.ode = OracleRocheODEReal(latent_dim, hidden_dim, dtype)
+        self.t = torch.arange(t0 - 1, t_max, 1.0, dtype=dtype)
+        self.options = {"step_t": self.t, "step_size": ode_step_size, "perturb": True}
+
+    def forward(self, init, a, s):
+        self.ode.set_action_static(a, s)
+        import warnings
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")  # fixed-grid solvers warn about the unused step_t, like torchdiffeq
+            h = _oi.odeint(self.ode, init, self.t, method=self.method, options=self.options, rtol=1e-7, atol=1e-8)
+        return self.output_function(h)[1:], h

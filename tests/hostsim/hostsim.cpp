@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "../../hybrid_ode_neurips_2021_b200/csrc/hode_bodies.cuh"
+#include "../../hybrid_ode_neurips_2021_b200/csrc/hode_real.cuh"
 
 using namespace hode;
 
@@ -211,5 +212,79 @@ int32_t hode_dopri5_bwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, co
     a.stats = const_cast<hode_stats*>(stats); a.grad_y0 = grad_y0; a.grad_params = grad_params;
     memset(grad_params, 0, sizeof(float) * pcount(cfg) * n_param_sets);
     return dispatch(DB, *cfg, a);
+}
+// ---- real-data fields (csrc/hode_real.cuh) --------------------------------------------------------------------------
+}  // extern "C"
+namespace {
+template <class F, bool TWO>
+int real_run(bool bwd, int method, int hidden, int P, const SolveArgs& a, const float* tab, int T) {
+    const int64_t n = a.n_groups * a.batch;
+    typename F::Params sp{a.params, hidden};
+    std::vector<float> acc(P, 0.f);
+    for (int64_t idx = 0; idx < n; ++idx) {
+        DoseTab d;
+        d.s = tab + idx; d.s1 = TWO ? tab + (int64_t)(T + 1) * n + idx : nullptr; d.stride = n; d.T = T;
+        if (!bwd) {
+            if (method == HODE_EULER) fixed_fwd_traj<F, M_EULER>(a, sp, d, idx);
+            else if (method == HODE_MIDPOINT) fixed_fwd_traj<F, M_MIDPOINT>(a, sp, d, idx);
+            else fixed_fwd_traj<F, M_RK4_38>(a, sp, d, idx);
+        } else {
+            if (method == HODE_EULER) fixed_bwd_traj<F, M_EULER, true>(a, sp, d, idx, acc.data());
+            else if (method == HODE_MIDPOINT) fixed_bwd_traj<F, M_MIDPOINT, true>(a, sp, d, idx, acc.data());
+            else fixed_bwd_traj<F, M_RK4_38, true>(a, sp, d, idx, acc.data());
+        }
+    }
+    if (bwd) for (int i = 0; i < P; ++i) a.grad_params[i] = acc[i];
+    return 0;
+}
+int real_pcount(int field, int Z, int H) {
+    if (H < 1 || H > 64) return -1;
+    if (field == HODE_FIELD_ROCHE_REAL) return Z == 4 ? RocheReal<4>::p_count(H) : Z == 20 ? RocheReal<20>::p_count(H) : -1;
+    if (field == HODE_FIELD_NEURAL_REAL) return Z == 4 ? NeuralReal<4, false>::p_count(H) : Z == 20 ? NeuralReal<20, false>::p_count(H) : -1;
+    if (field == HODE_FIELD_NEURAL_REAL_2ND) return Z == 8 ? NeuralReal<8, true>::p_count(H) : Z == 40 ? NeuralReal<40, true>::p_count(H) : -1;
+    return -1;
+}
+int real_dispatch(bool bwd, int field, int Z, int hidden, int method, const SolveArgs& a, const float* tab, int T) {
+    const int P = real_pcount(field, Z, hidden);
+    if (P < 0) return HODE_ERR_UNSUPPORTED;
+    if (field == HODE_FIELD_ROCHE_REAL) {
+        if (Z == 4) return real_run<RocheReal<4>, true>(bwd, method, hidden, P, a, tab, T);
+        return real_run<RocheReal<20>, true>(bwd, method, hidden, P, a, tab, T);
+    }
+    if (field == HODE_FIELD_NEURAL_REAL) {
+        if (Z == 4) return real_run<NeuralReal<4, false>, false>(bwd, method, hidden, P, a, tab, T);
+        return real_run<NeuralReal<20, false>, false>(bwd, method, hidden, P, a, tab, T);
+    }
+    if (Z == 8) return real_run<NeuralReal<8, true>, false>(bwd, method, hidden, P, a, tab, T);
+    return real_run<NeuralReal<40, true>, false>(bwd, method, hidden, P, a, tab, T);
+}
+}  // namespace
+extern "C" {
+int64_t hode_real_param_count(int32_t field, int32_t latent_dim, int32_t hidden) { return real_pcount(field, latent_dim, hidden); }
+int32_t hode_real_dose_tables(int32_t field, const float* action, int64_t stride_t, int64_t stride_b, int32_t T,
+                              int64_t n_traj, const float* params, float* tab, void*) {
+    const int kind = field == HODE_FIELD_ROCHE_REAL ? 0 : 1;
+    for (int64_t b = 0; b < n_traj; ++b)
+        real_dose_table_column(kind, action + b * stride_b, stride_t, T, n_traj, kind == 0 ? params[1] : 0.f, tab, b);
+    return 0;
+}
+int32_t hode_real_fixed_fwd(int32_t field, int32_t latent_dim, int32_t hidden, int32_t method, int32_t perturb,
+                            int64_t n_traj, const float* y0, const float* tab, int32_t T, const float* params,
+                            const float* grid, int32_t n_grid, const float* t_eval, int32_t n_t, float* h_out,
+                            float* tape, void*) {
+    SolveArgs a; memset(&a, 0, sizeof(a));
+    a.n_groups = 1; a.batch = n_traj; a.params = params; a.perturb = perturb; a.grid = grid; a.n_grid = n_grid;
+    a.t_eval_f = t_eval; a.n_t = n_t; a.y0 = y0; a.h_out = h_out; a.tape_y = tape;
+    return real_dispatch(false, field, latent_dim, hidden, method, a, tab, T);
+}
+int32_t hode_real_fixed_bwd(int32_t field, int32_t latent_dim, int32_t hidden, int32_t method, int32_t perturb,
+                            int64_t n_traj, const float* tab, int32_t T, const float* params, const float* grid,
+                            int32_t n_grid, const float* t_eval, int32_t n_t, const float* grad_h, const float* tape,
+                            float* grad_y0, float* grad_params, void*) {
+    SolveArgs a; memset(&a, 0, sizeof(a));
+    a.n_groups = 1; a.batch = n_traj; a.params = params; a.perturb = perturb; a.grid = grid; a.n_grid = n_grid;
+    a.t_eval_f = t_eval; a.n_t = n_t; a.grad_h = grad_h; a.tape_y = const_cast<float*>(tape); a.grad_y0 = grad_y0;
+    a.grad_params = grad_params;
+    return real_dispatch(true, field, latent_dim, hidden, method, a, tab, T);
 }
 }
