@@ -212,7 +212,9 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds
     const Dopri5Tab T = dopri5_tab();
     const float rtol = a.rtol_f, atol = a.atol_f;
 
-    float y0[D], y1[D], k[7][D];
+    float y0[D], y1[D];
+    StageRegs<D> ks;
+    float (&k)[7][D] = ks.v;
     load_vec<D>(a.y0 + idx * D, y0);
     if (valid) store_vec<D>(a.h_out + idx * D, y0);
     const bool poisoned = !F::params_ok(sp);  // kernel variant and parameters disagree: HODE_SOLVE_NONFINITE
@@ -287,7 +289,7 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds
         if (y0_bad) { status = HODE_SOLVE_NONFINITE; break; }
         const double t1 = t0 + dt;
         const float t0f = (float)t0, dtf = (float)dt, t1f = (float)t1;
-        dopri5_stages<F>(sp, ds, T, t0f, dtf, t1f, y0, k, y1);
+        dopri5_stages<F>(sp, ds, T, t0f, dtf, t1f, y0, ks, y1);
         // error estimate and ratio
         float ss = 0.0f, bad = 0.0f;
 #pragma unroll
@@ -370,9 +372,9 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds
 // dopri5 reverse sweep over the tape (discrete adjoint of the accepted-step map with constant step sizes, through
 // FSAL and the quartic dense output).  SURVEY.md Appendix D.4.
 // ==============================================================================================================
-template <class F, bool EG, class PS, class Dose>
-HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t idx,
-                             int64_t ctrl, float* acc) {
+template <class F, bool EG, class PS, class Dose, class KS>
+HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t idx, int64_t ctrl, float* acc, KS& k,
+                             KS& kb) {
     constexpr int D = F::D;
     const int64_t n_traj = a.n_groups * a.batch;
     const Dopri5Tab T = dopri5_tab();
@@ -386,17 +388,18 @@ HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t 
         const double dt = a.tape_t[(ctrl * a.tape_cap + n) * 2 + 1];
         const double t1 = t0 + dt;
         const float t0f = (float)t0, dtf = (float)dt, t1f = (float)t1;
-        float y0[D], y1[D], k[7][D], kb[7][D], yb0[D], yb1[D], g[D];
+        float y0[D], y1[D], yb0[D], yb1[D], g[D], kr[D], lr[D];
         load_vec<D>(a.tape_y + ((int64_t)n * n_traj + idx) * D, y0);
         // FSAL: k1 of step n is k7 of step n-1 = f(prev(t1_{n-1}), y1_{n-1}); step 0 uses f(t[0], y0)
-        F::eval(sp, n == 0 ? t0f : t_prev(t0f), ds, y0, k[0]);
+        F::eval(sp, n == 0 ? t0f : t_prev(t0f), ds, y0, kr);
+        stage_set_row<D>(k, 0, kr);
         dopri5_stages<F>(sp, ds, T, t0f, dtf, t1f, y0, k, y1);
 #pragma unroll
-        for (int i = 0; i < 7; ++i)
+        for (int i = 0; i < 6; ++i)
 #pragma unroll
-            for (int d = 0; d < D; ++d) kb[i][d] = 0.0f;
+            for (int d = 0; d < D; ++d) kb.set(i, d, 0.0f);
 #pragma unroll
-        for (int d = 0; d < D; ++d) { yb1[d] = lam[d]; yb0[d] = 0.0f; kb[6][d] = phi[d]; }
+        for (int d = 0; d < D; ++d) { yb1[d] = lam[d]; yb0[d] = 0.0f; kb.set(6, d, phi[d]); }
         // dense outputs emitted by this step: t0 < t_eval[j] <= t1
         while (j >= 1 && a.t_eval_d[j] > t0) {
             const float x = (float)((a.t_eval_d[j] - t0) / (t1 - t0));
@@ -408,15 +411,17 @@ HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t 
                 const float ymb = 16.0f * ab - 32.0f * bb + 16.0f * cb;
                 yb0[d] += eb - 8.0f * ab + 18.0f * bb - 11.0f * cb + ymb;
                 yb1[d] += -8.0f * ab + 14.0f * bb - 5.0f * cb;
-                kb[0][d] += dtf * (-2.0f * ab + 5.0f * bb - 4.0f * cb + db);
-                kb[6][d] += dtf * (2.0f * ab - 3.0f * bb + cb);
+                kb.set(0, d, kb.get(0, d) + dtf * (-2.0f * ab + 5.0f * bb - 4.0f * cb + db));
+                kb.set(6, d, kb.get(6, d) + dtf * (2.0f * ab - 3.0f * bb + cb));
 #pragma unroll
-                for (int i = 0; i < 7; ++i) kb[i][d] = fmaf(mul_rn(dtf, T.c_mid[i]), ymb, kb[i][d]);
+                for (int i = 0; i < 7; ++i) kb.set(i, d, fmaf(mul_rn(dtf, T.c_mid[i]), ymb, kb.get(i, d)));
             }
             --j;
         }
         // k7 = f(prev(t1), y1)
-        F::template vjp<EG>(sp, t_prev(t1f), ds, y1, k[6], kb[6], g, acc);
+        stage_row<D>(k, 6, kr);
+        stage_row<D>(kb, 6, lr);
+        F::template vjp<EG>(sp, t_prev(t1f), ds, y1, kr, lr, g, acc);
 #pragma unroll
         for (int d = 0; d < D; ++d) yb1[d] += g[d];
         // y1 = y0 + sum_{j<6} k_j * (beta[5][j]*dt)
@@ -424,7 +429,7 @@ HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t 
         for (int d = 0; d < D; ++d) {
             yb0[d] += yb1[d];
 #pragma unroll
-            for (int jj = 0; jj < 6; ++jj) kb[jj][d] = fmaf(mul_rn(T.beta[5][jj], dtf), yb1[d], kb[jj][d]);
+            for (int jj = 0; jj < 6; ++jj) kb.set(jj, d, fmaf(mul_rn(T.beta[5][jj], dtf), yb1[d], kb.get(jj, d)));
         }
         // stages k6 .. k2  (k[i] = f(t_i, Y_i), Y_i = y0 + sum_{j<i} k_j * (beta[i-1][j]*dt))
 #pragma unroll
@@ -437,24 +442,28 @@ HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t 
             for (int d = 0; d < D; ++d) {
                 float s = 0.0f;
 #pragma unroll
-                for (int jj = 0; jj < i; ++jj) s = fmaf(k[jj][d], mul_rn(T.beta[i - 1][jj], dtf), s);
+                for (int jj = 0; jj < i; ++jj) s = fmaf(k.get(jj, d), mul_rn(T.beta[i - 1][jj], dtf), s);
                 Yi[d] = y0[d] + s;
             }
-            F::template vjp<EG>(sp, ti, ds, Yi, k[i], kb[i], g, acc);
+            stage_row<D>(k, i, kr);
+            stage_row<D>(kb, i, lr);
+            F::template vjp<EG>(sp, ti, ds, Yi, kr, lr, g, acc);
 #pragma unroll
             for (int d = 0; d < D; ++d) {
                 yb0[d] += g[d];
 #pragma unroll
-                for (int jj = 0; jj < i; ++jj) kb[jj][d] = fmaf(mul_rn(T.beta[i - 1][jj], dtf), g[d], kb[jj][d]);
+                for (int jj = 0; jj < i; ++jj) kb.set(jj, d, fmaf(mul_rn(T.beta[i - 1][jj], dtf), g[d], kb.get(jj, d)));
             }
         }
         if (n == 0) {
-            F::template vjp<EG>(sp, t0f, ds, y0, k[0], kb[0], g, acc);
+            stage_row<D>(k, 0, kr);
+            stage_row<D>(kb, 0, lr);
+            F::template vjp<EG>(sp, t0f, ds, y0, kr, lr, g, acc);
 #pragma unroll
             for (int d = 0; d < D; ++d) yb0[d] += g[d];
         } else {
 #pragma unroll
-            for (int d = 0; d < D; ++d) phi[d] = kb[0][d];
+            for (int d = 0; d < D; ++d) phi[d] = kb.get(0, d);
         }
 #pragma unroll
         for (int d = 0; d < D; ++d) lam[d] = yb0[d];
@@ -468,6 +477,13 @@ HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t 
         for (int d = 0; d < D; ++d) lam[d] = nanf("");
     }
     store_vec<D>(a.grad_y0 + idx * D, lam);
+}
+
+// register-resident stage storage (the default)
+template <class F, bool EG, class PS, class Dose>
+HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t idx, int64_t ctrl, float* acc) {
+    StageRegs<F::D> k, kb;
+    dopri5_bwd_traj<F, EG>(a, sp, ds, idx, ctrl, acc, k, kb);
 }
 
 }  // namespace hode

@@ -537,25 +537,55 @@ HODE_HD double optimal_step(double last, float ratio, double safety, double ifac
     return last * factor;
 }
 
-// The 7 stages of one attempt.  k[0] must hold f0 on entry.  On exit k[1..6] are filled and y1 is the last stage input.
-template <class F, class PS, class Dose>
-HODE_HD void dopri5_stages(PS sp, const Dose& ds, const Dopri5Tab& T, float t0f, float dtf,
-                           float t1f, const float (&y0)[F::D], float (&k)[7][F::D], float (&y1)[F::D]) {
+// Storage of the 7 stage derivatives (and of their adjoints in the reverse sweep).  StageRegs keeps them in registers;
+// StageSmem keeps them in the thread's column of a shared-memory array (element (i, d) at p[(i * D + d) * stride],
+// stride = threads per CTA: conflict-free) -- used where 2 x 7 x D floats on top of the parameter-gradient
+// accumulators do not fit the register file (dopri5 reverse sweep, D >= 12).
+template <int D>
+struct StageRegs {
+    float v[7][D];
+    HODE_HD float get(int i, int d) const { return v[i][d]; }
+    HODE_HD void set(int i, int d, float x) { v[i][d] = x; }
+};
+template <int D>
+struct StageSmem {
+    float* p;
+    int stride;
+    HODE_HD float get(int i, int d) const { return p[(i * D + d) * stride]; }
+    HODE_HD void set(int i, int d, float x) { p[(i * D + d) * stride] = x; }
+};
+template <int D, class KS>
+HODE_HD void stage_row(const KS& k, int i, float (&out)[D]) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) out[d] = k.get(i, d);
+}
+template <int D, class KS>
+HODE_HD void stage_set_row(KS& k, int i, const float (&in)[D]) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) k.set(i, d, in[d]);
+}
+
+// The 7 stages of one attempt.  Stage 0 of `k` must hold f0 on entry.  On exit stages 1..6 are filled and y1 is the last
+// stage input.
+template <class F, class PS, class Dose, class KS>
+HODE_HD void dopri5_stages(PS sp, const Dose& ds, const Dopri5Tab& T, float t0f, float dtf, float t1f,
+                           const float (&y0)[F::D], KS& k, float (&y1)[F::D]) {
     constexpr int D = F::D;
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
         float ti;
         if (T.alpha[i] == 1.0f) ti = t_prev(t1f);
         else ti = add_rn(t0f, mul_rn(T.alpha[i], dtf));
-        float yi[D];
+        float yi[D], kn[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             float a = 0.0f;
 #pragma unroll
-            for (int j = 0; j <= i; ++j) a = fmaf(k[j][d], mul_rn(T.beta[i][j], dtf), a);
+            for (int j = 0; j <= i; ++j) a = fmaf(k.get(j, d), mul_rn(T.beta[i][j], dtf), a);
             yi[d] = y0[d] + a;
         }
-        F::eval(sp, ti, ds, yi, k[i + 1]);
+        F::eval(sp, ti, ds, yi, kn);
+        stage_set_row<D>(k, i + 1, kn);
         if (i == 5) {
 #pragma unroll
             for (int d = 0; d < D; ++d) y1[d] = yi[d];

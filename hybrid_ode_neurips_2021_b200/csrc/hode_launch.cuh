@@ -309,6 +309,16 @@ __global__ void __launch_bounds__(128) dopri5_fwd_seg_kernel(const SolveArgs a) 
     else { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F>(a, cm, (const float*)smem, ds, idx, true, group, cm.rel == 0, count))); }
 }
 
+// Where do the 7 stage derivatives and their 7 adjoints live in the reverse sweep?  In registers.  At D = 12 (2 x 84
+// floats on top of 104 parameter-gradient accumulators) ptxas spills ~1.5 KB per thread; moving the stages to shared
+// memory (StageSmem, kSmem = true) was measured 2.4x SLOWER on B200 (C3 shape: 30.0 vs 12.6 ms) because the spills do
+// not go away (the accumulators are what overflows) and every stage access becomes an LDS.  Kept as a switch.
+template <class F>
+struct Dopri5BwdStore {
+    static constexpr bool kSmem = false;
+    static constexpr int floats_per_thread = kSmem ? 2 * 7 * F::D : 0;
+};
+
 template <class F, bool EG, int ND, bool CP>
 __global__ void __launch_bounds__(128) dopri5_bwd_kernel(const SolveArgs a, int tiles_per_group) {
     extern __shared__ float smem[];
@@ -321,8 +331,16 @@ __global__ void __launch_bounds__(128) dopri5_bwd_kernel(const SolveArgs a, int 
     if (tl.b < a.batch) {
         const int64_t idx = tl.group * a.batch + tl.b;
         const int64_t ctrl = a.per_traj ? idx : (a.ctrl_batch > 0 ? idx / a.ctrl_batch : tl.group);
-        if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, ParamConst(), ds, idx, ctrl, acc))); }
-        else { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, (const float*)sp, ds, idx, ctrl, acc))); }
+        if constexpr (Dopri5BwdStore<F>::kSmem) {
+            float* base = sred + F::P + threadIdx.x;
+            StageSmem<F::D> k{base, (int)blockDim.x};
+            StageSmem<F::D> kb{base + 7 * F::D * blockDim.x, (int)blockDim.x};
+            if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, ParamConst(), ds, idx, ctrl, acc, k, kb))); }
+            else { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, (const float*)sp, ds, idx, ctrl, acc, k, kb))); }
+        } else {
+            if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, ParamConst(), ds, idx, ctrl, acc))); }
+            else { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, (const float*)sp, ds, idx, ctrl, acc))); }
+        }
     }
     reduce_param_grads<F>(a, tl.group, acc, sred);
 }
@@ -465,8 +483,13 @@ int launch_dopri5_bwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t s
     const int64_t nblk = a.n_groups * tiles;
     const bool nd1 = cfg.n_dose == 1;
     const bool eg = cfg.expert_grads != 0;
-#define HODE_DB(EG, ND, CP) \
-    dopri5_bwd_kernel<F, EG, ND, CP><<<(unsigned)nblk, threads, ((CP ? 0 : F::SP) + F::P) * sizeof(float), st>>>(a, tiles)
+#define HODE_DB(EG, ND, CP)                                                                                              \
+    do {                                                                                                                 \
+        const size_t sh_ = ((CP ? 0 : F::SP) + F::P + (size_t)Dopri5BwdStore<F>::floats_per_thread * threads) * sizeof(float); \
+        if (sh_ > 48 * 1024)                                                                                             \
+            cudaFuncSetAttribute(dopri5_bwd_kernel<F, EG, ND, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_); \
+        dopri5_bwd_kernel<F, EG, ND, CP><<<(unsigned)nblk, threads, sh_, st>>>(a, tiles);                                \
+    } while (0)
 #define HODE_DB_CP(CP)                                                         \
     do {                                                                       \
         if (eg) { if (nd1) HODE_DB(true, 1, CP); else HODE_DB(true, 0, CP); }  \
