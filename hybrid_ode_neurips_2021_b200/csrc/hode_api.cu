@@ -118,7 +118,7 @@ static int check_common(const hode_cfg* cfg, int64_t n_groups, int64_t batch, co
     if (!cfg) return fail(HODE_ERR_ARG, "cfg is NULL");
     if (n_groups < 0 || batch < 0) return fail(HODE_ERR_ARG, "negative n_groups/batch");
     if (n_groups * batch > 0 && (!dose_amt || !params)) return fail(HODE_ERR_ARG, "NULL dose_amt/params");
-    if (cfg->n_dose < 0 || (cfg->n_dose > 0 && (!dose_t || dose_t_stride < cfg->n_dose)))
+    if (cfg->n_dose < 0 || (cfg->n_dose > 0 && n_groups * batch > 0 && (!dose_t || dose_t_stride < cfg->n_dose)))
         return fail(HODE_ERR_ARG, "bad dose_t / dose_t_stride / n_dose");
     if (n_t < 1) return fail(HODE_ERR_ARG, "n_t must be >= 1");
     if (n_groups > 0x7fffffffLL) return fail(HODE_ERR_ARG, "too many groups");

@@ -53,6 +53,8 @@ class _DoseMixin:
     """Vectorised ``set_action``: ``dosage [B]``, ``times [B, n_dose]`` (same attributes as the reference)."""
 
     def set_action(self, action):
+        if action.shape[1] == 0:  # the reference's torch.stack over an empty list of patients (model.py:507)
+            raise RuntimeError("stack expects a non-empty TensorList")
         if action.is_cuda:
             amt, idx, cnt = ops.dose_schedule(L.get_lib(), action if action.dtype == torch.float32 else action.float())
             lo, hi = (int(v) for v in torch.stack(torch.aminmax(cnt)).tolist())

@@ -479,3 +479,34 @@ def test_mc_evaluation_chunk_equals_separate_solves():
         xh = dec(y0.to(DEV), a)[0][t0:]
     se = torch.sum((x[t0:] - xh) ** 2 * mask[t0:], dim=(0, 2)) / torch.sum(mask[t0:], dim=(0, 2))
     assert torch.allclose(res["se_x"], se)
+
+
+def test_edge_cases_empty_cohort_single_time_and_empty_mask():
+    D, obs = 6, 20
+    dec = H.RocheExpertDecoder(obs, D, 1, 14, 1, method="rk4", device=DEV, solver_options={"step_size": 0.25})
+    # empty cohort: the reference fails in set_action (torch.stack of an empty list, model.py:507) -- same error here;
+    # the C ABI itself accepts zero trajectories (no launch) and the fused loss of an empty cohort is exactly zero
+    with pytest.raises(RuntimeError, match="non-empty"):
+        dec.solve(torch.zeros(0, D, device=DEV), torch.zeros(15, 0, 1, device=DEV))
+    from hybrid_ode_neurips_2021_b200 import _lib as L, ops, solver
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.RK4_38, n_dose=1)
+    pb = ops.Problem(cfg, 1, 0, torch.zeros(0, device=DEV), torch.zeros(0, 1, device=DEV),
+                     solver.pack_params(dec.ode, L.FIELD_ROCHE).detach()[None].contiguous(), None)
+    tt = torch.arange(0, 15.0, device=DEV)
+    h, tape = ops.fixed_fwd(L.get_lib(), pb, torch.zeros(0, D, device=DEV), tt, tt, True)
+    assert tuple(h.shape) == (15, 0, D)
+    x = torch.zeros(15, 0, obs, device=DEV)
+    assert float(H.masked_sse(dec, h, x, x, n_norm=1)) == 0.0
+    # a single output time returns the initial state (torchdiffeq: solution[0] = y0), for both solver families
+    y0, act, xx, mm = make_cohort(5, D, obs=obs, seed=31)
+    dec.ode.set_action(act.to(DEV))
+    for method in ("rk4", "dopri5"):
+        out = H.odeint(dec.ode, y0.to(DEV), torch.tensor([3.0], device=DEV), method=method)
+        assert torch.equal(out[0].cpu(), y0)
+    # all observations masked out: zero loss and zero gradients (not NaN)
+    zz = y0.clone().to(DEV).requires_grad_(True)
+    hh = dec.solve(zz, act.to(DEV))
+    l0 = H.masked_sse(dec, hh, xx.to(DEV), torch.zeros_like(mm).to(DEV))
+    l0.backward()
+    assert float(l0) == 0.0 and float(zz.grad.abs().max()) == 0.0
+    assert float(dec.output_function[0].weight.grad.abs().max()) == 0.0
