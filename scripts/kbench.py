@@ -20,12 +20,14 @@ ap.add_argument("--eg", type=int, default=0)
 ap.add_argument("--reps", type=int, default=5)
 ap.add_argument("--lib", default=None)
 ap.add_argument("--hill2", type=int, default=1)
+ap.add_argument("--field", default="roche")
 args = ap.parse_args()
 dev = "cuda:0"
 lib = L.get_lib() if args.lib is None else L.HodeLib(args.lib)
 B, D, obs = args.patients, args.D, args.obs
 torch.manual_seed(0)
-m = H.RocheODE(D, 1, 14, 1, device=dev)
+FIELD = L.FIELD_ROCHE if args.field == "roche" else L.FIELD_NEURAL
+m = H.RocheODE(D, 1, 14, 1, device=dev) if args.field == "roche" else H.NeuralODE(D, 1, 14, 1, device=dev)
 y0 = torch.empty(B, D, device=dev).exponential_(100.0)
 a = torch.zeros(15, B, 1, device=dev)
 a[torch.randint(0, 14, (B,), device=dev), torch.arange(B, device=dev), 0] = torch.rand(B, device=dev) * 10 + 1e-3
@@ -35,8 +37,8 @@ mask = (torch.rand(15, B, obs, device=dev) < 0.5).float()
 lin = torch.nn.Linear(D, obs).to(dev)
 tt = torch.arange(0, 15.0, device=dev)
 grid = solver.fixed_grid_points(tt.cpu(), args.h).to(dev)
-cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.METHODS[args.method], n_dose=1, expert_grads=bool(args.eg), hill2=bool(args.hill2))
-pb = ops.Problem(cfg, 1, B, m.dosage, m._dose_t_f32, solver.pack_params(m, L.FIELD_ROCHE).detach()[None].contiguous(), None)
+cfg = ops.make_cfg(FIELD, D, L.METHODS[args.method], n_dose=1, expert_grads=bool(args.eg), hill2=bool(args.hill2) and args.field == "roche")
+pb = ops.Problem(cfg, 1, B, m.dosage, m._dose_t_f32, solver.pack_params(m, FIELD).detach()[None].contiguous(), None)
 
 
 def ev(fn):

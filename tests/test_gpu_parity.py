@@ -510,3 +510,30 @@ def test_edge_cases_empty_cohort_single_time_and_empty_mask():
     l0.backward()
     assert float(l0) == 0.0 and float(zz.grad.abs().max()) == 0.0
     assert float(dec.output_function[0].weight.grad.abs().max()) == 0.0
+
+
+def test_two_streams_share_the_constant_bank_safely():
+    """Single-parameter-set launches keep their parameters in one per-device __constant__ array; launches from
+    different streams (and different models) must be ordered by the library, not corrupt each other."""
+    D, B = 8, 4096
+    pairs = [build_pair(D, seed=50 + i) for i in range(2)]
+    y0, a, _, _ = make_cohort(B, D, seed=23)
+    t = torch.arange(0, 15.0).to(DEV)
+    refs = []
+    for _, m in pairs:
+        m.set_action(a.to(DEV))
+        with torch.no_grad():
+            refs.append(H.odeint(m, y0.to(DEV), t, method="rk4", options={"step_size": 0.0625}))
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    outs = [[], []]
+    y0d = y0.to(DEV)
+    for rep in range(6):
+        for i, (_, m) in enumerate(pairs):
+            with torch.cuda.stream(streams[i]), torch.no_grad():
+                outs[i].append(H.odeint(m, y0d, t, method="rk4", options={"step_size": 0.0625}))
+    torch.cuda.synchronize()
+    for i in range(2):
+        for o in outs[i]:
+            assert torch.equal(o, refs[i])
+    assert not torch.equal(refs[0], refs[1])
