@@ -389,10 +389,12 @@ def run_ours(args):
         hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s"
         bwd_flops = B * N_STEPS * FLOPS_BWD_STEP
         fwd_flops = B * N_STEPS * FLOPS_FWD_STEP
+        traffic, traffic_src = ncu_traffic("r01_fixed_bwd_kernel.txt", B)
         roof = {
             "bound": "fp32_fma", "kernel": "fixed_bwd_kernel<Roche<8>, RK4_38> (reverse sweep; largest share of the step)",
             "achieved": bwd_flops / (t_bwd * 1e-3) / 1e12, "peak": fma_peak, "unit": "TFLOP/s",
-            "frac": bwd_flops / (t_bwd * 1e-3) / 1e12 / fma_peak, "traffic": None,
+            "frac": bwd_flops / (t_bwd * 1e-3) / 1e12 / fma_peak, "traffic": traffic, "traffic_source": traffic_src,
+            "algorithmic_bytes_per_launch": B * 4 * D * (N_STEPS + T + 1),  # tape + grad_h read, grad_y0 written
             "peak_source": "FFMA probe kernel timed in this run ({} SMs; nominal 148 x 128 lanes x 2 x 1.965 GHz = 74.5)".format(sms),
             "algorithmic_flops_per_traj_step": FLOPS_BWD_STEP, "launch_ms": t_bwd,
         }
@@ -445,6 +447,23 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def ncu_traffic(kernel_file, patients):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/), scaled from
+    the 2^17-patient capture to this run's cohort (trajectories are independent: traffic is linear in patients)."""
+    path = os.path.join(ROOT, "profiles", kernel_file)
+    try:
+        tot = 0.0
+        for ln in open(path):
+            f = ln.split()
+            if len(f) >= 3 and f[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(f[1]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}[f[2]]
+        if tot <= 0:
+            return None, None
+        return tot * patients / 131072.0, "profiles/{} (2^17-patient capture x {:.0f})".format(kernel_file, patients / 131072.0)
+    except Exception:
+        return None, None
 
 
 def dopri5_extras(lib, dev):

@@ -20,6 +20,8 @@ ROOT = os.path.dirname(HERE)
 
 ROCHE_DIMS = (4, 6, 8, 12)
 NEURAL_DIMS = (4, 6, 8, 12)
+# real-data fields: (hode_field, latent width) -- RocheODEReal 4 / 20, NeuralODEReal 4 / 20, NeuralODEReal2nd 8 / 40
+REAL_UNITS = ((2, 4), (2, 20), (3, 4), (3, 20), (4, 8), (4, 40))
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -43,6 +45,9 @@ def _units():
         for hill2 in (0, 1):
             units.append(("inst_roche_d{}_h{}.o".format(d, hill2), "inst_roche.cu",
                           ["-DHODE_INST_D={}".format(d), "-DHODE_INST_HILL2={}".format(hill2)]))
+    for field, z in REAL_UNITS:
+        units.append(("inst_real_f{}_z{}.o".format(field, z), "inst_real.cu",
+                      ["-DHODE_REAL_FIELD={}".format(field), "-DHODE_REAL_Z={}".format(z)]))
     if os.path.exists(os.path.join(CSRC, "inst_neural.cu")):
         for d in NEURAL_DIMS:
             units.append(("inst_neural_d{}.o".format(d), "inst_neural.cu", ["-DHODE_INST_D={}".format(d)]))

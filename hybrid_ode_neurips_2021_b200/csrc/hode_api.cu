@@ -4,6 +4,7 @@
 #include <string.h>
 
 #include "hode_bodies.cuh"
+#include "hode_real_args.cuh"
 
 namespace hode {
 template <class F> int launch_fixed_fwd(const hode_cfg&, const SolveArgs&, cudaStream_t);
@@ -15,13 +16,6 @@ int launch_decode_sse(int32_t, int32_t, int32_t, int64_t, double, const float*, 
                       const float*, const float*, int64_t, int64_t, int64_t, float*, float*, float*, float*,
                       cudaStream_t);
 int launch_ffma_probe(int, int, float*, cudaStream_t);
-struct RealArgs {
-    SolveArgs a;
-    const float* tab;
-    int32_t T;
-    int32_t hidden;
-    int32_t P;
-};
 int real_param_count(int, int, int);
 int launch_real_dose_table(int, const float*, int64_t, int64_t, int32_t, int64_t, const float*, float*, cudaStream_t);
 int launch_real_fixed(bool, int, int, int, const RealArgs&, cudaStream_t);
