@@ -137,9 +137,10 @@ HODE_HD void fixed_fwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t i
     }
 }
 
-template <class F, int METHOD, bool EG, class PS, class Dose>
-HODE_HD void fixed_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t idx,
-                            float* acc) {
+// `valid` = false: a padding lane that only keeps a warp-cooperative accumulator (NeuralCoop) company: it follows the
+// control flow on a clamped trajectory with zero incoming gradients (so it contributes exactly 0) and writes nothing.
+template <class F, int METHOD, bool EG, class PS, class Dose, class ACC>
+HODE_HD void fixed_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t idx, ACC acc, bool valid = true) {
     constexpr int D = F::D;
     const int64_t n_traj = a.n_groups * a.batch;
     float lam[D];
@@ -166,6 +167,10 @@ HODE_HD void fixed_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t i
                 const float te = a.t_eval_f[j];
                 float g[D];
                 load_vec<D>(a.grad_h + ((int64_t)j * n_traj + idx) * D, g);
+                if (!valid) {
+#pragma unroll
+                    for (int d = 0; d < D; ++d) g[d] = 0.0f;
+                }
                 if (te == t1) {
 #pragma unroll
                     for (int d = 0; d < D; ++d) lam[d] += g[d];
@@ -186,6 +191,7 @@ HODE_HD void fixed_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t i
         for (int d = 0; d < D; ++d) lam[d] = lam0[d] + yb0[d];
         t1 = t0;
     }
+    if (!valid) return;
     float g0[D];
     load_vec<D>(a.grad_h + idx * D, g0);
 #pragma unroll
@@ -372,9 +378,9 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds
 // dopri5 reverse sweep over the tape (discrete adjoint of the accepted-step map with constant step sizes, through
 // FSAL and the quartic dense output).  SURVEY.md Appendix D.4.
 // ==============================================================================================================
-template <class F, bool EG, class PS, class Dose, class KS>
-HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t idx, int64_t ctrl, float* acc, KS& k,
-                             KS& kb) {
+template <class F, bool EG, class PS, class Dose, class KS, class ACC>
+HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t idx, int64_t ctrl, ACC acc, KS& k,
+                             KS& kb, bool valid = true) {
     constexpr int D = F::D;
     const int64_t n_traj = a.n_groups * a.batch;
     const Dopri5Tab T = dopri5_tab();
@@ -405,6 +411,10 @@ HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t 
             const float x = (float)((a.t_eval_d[j] - t0) / (t1 - t0));
             const float x2 = x * x, x3 = x2 * x, x4 = x3 * x;
             load_vec<D>(a.grad_h + ((int64_t)j * n_traj + idx) * D, g);
+            if (!valid) {  // padding lane of a warp-cooperative accumulator: follows the control flow, contributes 0
+#pragma unroll
+                for (int d = 0; d < D; ++d) g[d] = 0.0f;
+            }
 #pragma unroll
             for (int d = 0; d < D; ++d) {
                 const float eb = g[d], db = x * g[d], cb = x2 * g[d], bb = x3 * g[d], ab = x4 * g[d];
@@ -468,6 +478,7 @@ HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t 
 #pragma unroll
         for (int d = 0; d < D; ++d) lam[d] = yb0[d];
     }
+    if (!valid) return;
     float g0[D];
     load_vec<D>(a.grad_h + idx * D, g0);
 #pragma unroll
@@ -480,10 +491,11 @@ HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t 
 }
 
 // register-resident stage storage (the default)
-template <class F, bool EG, class PS, class Dose>
-HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t idx, int64_t ctrl, float* acc) {
+template <class F, bool EG, class PS, class Dose, class ACC>
+HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t idx, int64_t ctrl, ACC acc,
+                             bool valid = true) {
     StageRegs<F::D> k, kb;
-    dopri5_bwd_traj<F, EG>(a, sp, ds, idx, ctrl, acc, k, kb);
+    dopri5_bwd_traj<F, EG>(a, sp, ds, idx, ctrl, acc, k, kb, valid);
 }
 
 }  // namespace hode

@@ -277,6 +277,24 @@ struct Roche {
 // staged layout: one 16-byte aligned record per hidden unit j: {W1[j][0..D], b1[j], W2[0..D-1][j], pad}, then b2 --
 // every weight the j-th unit needs is contiguous, so the broadcast reads are LDS.128.
 // ------------------------------------------------------------------------------------------------------------
+// Warp-cooperative parameter-gradient accumulation for the NeuralODE field (846 - 3 132 parameters: per-thread
+// accumulators would live in local memory and make the reverse sweep ~35x slower than the forward sweep).
+// Every lane still integrates its own trajectory, but the weight gradients are owned by HIDDEN UNIT: lane L keeps the
+// rows of dW1 / db1 / dW2 of the units j = 32 c + L in registers.  Per vjp call and per chunk of 32 units every lane
+// publishes its (delta_j, a_j) -- and once per call its (input, output-adjoint) vectors -- to a warp-private staging area
+// in shared memory; after a __syncwarp each lane walks the 32 trajectories of the warp and accumulates the outer
+// products of ITS unit.  The call sites must be warp-converged (fixed-grid sweeps, batch-coupled dopri5).
+template <int D_>
+struct NeuralCoop {
+    static constexpr int H = 10 * D_, IN = D_ + 1, NJ = (H + 31) / 32;
+    static constexpr int kStageFloats = (IN + D_) * 32 + 2 * 32 * 33;  // per warp
+    float* stage;          // warp-private: S_in [IN][32], S_u [D][32], S_del [32][33], S_a [32][33]
+    int lane;
+    float w1[NJ][IN + 1];  // rows of dW1 (IN) and db1 (1) of the owned units
+    float w2[NJ][D_];      // columns of dW2 of the owned units
+    float b2[D_];          // this lane's own contribution to db2 (reduced over the warp at the end)
+};
+
 template <int D_>
 struct Neural {
     static constexpr int D = D_;
@@ -370,6 +388,73 @@ struct Neural {
             acc[OFF_B1 + j] += del;
         }
     }
+
+#if HODE_DEVICE_BUILD && defined(__CUDA_ARCH__)
+    // same VJP, parameter gradients accumulated warp-cooperatively (NeuralCoop above); all 32 lanes must call together
+    template <bool EG, class Dose>
+    HODE_D static void vjp(const float* __restrict__ sp, float t, const Dose& ds, const float (&y)[D_], const float* k,
+                           const float (&l)[D_], float (&gy)[D_], NeuralCoop<D_>* cp) {
+        float in[IN], u[D_];
+#pragma unroll
+        for (int i = 0; i < D_; ++i) in[i] = y[i];
+        in[D_] = neural_dose(ds, t);
+        if (k != nullptr) {
+#pragma unroll
+            for (int d = 0; d < D_; ++d) u[d] = l[d] * (1.0f - k[d] * k[d]);
+        } else {
+            float s2[D_];
+            eval(sp, t, ds, y, s2);
+#pragma unroll
+            for (int d = 0; d < D_; ++d) u[d] = l[d] * (1.0f - s2[d] * s2[d]);
+        }
+        float* S_in = cp->stage;
+        float* S_u = S_in + IN * 32;
+        float* S_del = S_u + D_ * 32;
+        float* S_a = S_del + 32 * 33;
+        const int lane = cp->lane;
+        __syncwarp();  // the previous call's owner phase has finished reading the staging area
+#pragma unroll
+        for (int i = 0; i < IN; ++i) S_in[i * 32 + lane] = in[i];
+#pragma unroll
+        for (int d = 0; d < D_; ++d) { S_u[d * 32 + lane] = u[d]; cp->b2[d] += u[d]; gy[d] = 0.0f; }
+#pragma unroll
+        for (int c = 0; c < NeuralCoop<D_>::NJ; ++c) {
+            // producer phase: this lane's trajectory, hidden units 32 c .. 32 c + 31
+#pragma unroll 1
+            for (int jj = 0; jj < 32; ++jj) {
+                const int j = c * 32 + jj;
+                float del = 0.0f, a = 0.0f;
+                if (j < H) {
+                    const float* rec = sp + j * R;
+                    a = rec[IN];
+#pragma unroll
+                    for (int i = 0; i < IN; ++i) a = fmaf(rec[i], in[i], a);
+                    a = tanh_f(a);
+                    float cc = 0.0f;
+#pragma unroll
+                    for (int d = 0; d < D_; ++d) cc = fmaf(rec[IN + 1 + d], u[d], cc);
+                    del = cc * (1.0f - a * a);
+#pragma unroll
+                    for (int i = 0; i < D_; ++i) gy[i] = fmaf(rec[i], del, gy[i]);
+                }
+                S_del[jj * 33 + lane] = del;
+                S_a[jj * 33 + lane] = a;
+            }
+            __syncwarp();
+            // owner phase: unit j = 32 c + lane, all 32 trajectories of the warp
+#pragma unroll 4
+            for (int tt = 0; tt < 32; ++tt) {
+                const float del = S_del[lane * 33 + tt], a = S_a[lane * 33 + tt];
+#pragma unroll
+                for (int i = 0; i < IN; ++i) cp->w1[c][i] = fmaf(del, S_in[i * 32 + tt], cp->w1[c][i]);
+                cp->w1[c][IN] += del;
+#pragma unroll
+                for (int d = 0; d < D_; ++d) cp->w2[c][d] = fmaf(S_u[d * 32 + tt], a, cp->w2[c][d]);
+            }
+            __syncwarp();
+        }
+    }
+#endif
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -416,9 +501,9 @@ HODE_HD void fixed_step(PS sp, const Dose& ds, float t0, float t1, float dt, boo
 
 // reverse of one fixed-grid step:  lam0 = lam1 + (d dy/d y0)^T lam1 ; acc += (d dy/d theta)^T lam1.
 // Stages are recomputed from y0 (the tape holds only the state at the start of the step).
-template <class F, int METHOD, bool EG, class PS, class Dose>
+template <class F, int METHOD, bool EG, class PS, class Dose, class ACC>
 HODE_HD void fixed_step_vjp(PS sp, const Dose& ds, float t0, float t1, float dt, bool perturb,
-                            const float (&y0)[F::D], const float (&lam1)[F::D], float (&lam0)[F::D], float* acc) {
+                            const float (&y0)[F::D], const float (&lam1)[F::D], float (&lam0)[F::D], ACC acc) {
     constexpr int D = F::D;
     const float ta = perturb ? t_next(t0) : t0;
     float kb[D], g[D];

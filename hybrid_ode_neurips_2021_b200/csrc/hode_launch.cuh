@@ -243,6 +243,54 @@ __global__ void __launch_bounds__(128, HODE_FWD_MINBLOCKS) fixed_fwd_kernel(cons
     else { HODE_WITH_DOSE(ND, a, idx, (fixed_fwd_traj<F, METHOD>(a, (const float*)smem, ds, idx))); }
 }
 
+// does the field accumulate its parameter gradients warp-cooperatively (NeuralCoop) in the fixed-grid reverse sweep?
+template <class F> struct CoopOf { static constexpr bool value = false; };
+template <int D> struct CoopOf<Neural<D>> { static constexpr bool value = true; };
+
+template <int D>
+__device__ __forceinline__ void coop_init(NeuralCoop<D>& cp, float* stage_base) {
+    cp.lane = threadIdx.x & 31;
+    cp.stage = stage_base + (threadIdx.x >> 5) * NeuralCoop<D>::kStageFloats;
+#pragma unroll
+    for (int c = 0; c < NeuralCoop<D>::NJ; ++c) {
+#pragma unroll
+        for (int i = 0; i <= NeuralCoop<D>::IN; ++i) cp.w1[c][i] = 0.0f;
+#pragma unroll
+        for (int d = 0; d < D; ++d) cp.w2[c][d] = 0.0f;
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) cp.b2[d] = 0.0f;
+}
+// owned rows -> shared accumulator (one atomic per parameter per warp) -> global
+template <int D>
+__device__ __forceinline__ void coop_flush(const SolveArgs& a, int64_t group, NeuralCoop<D>& cp, float* sred) {
+    using F = Neural<D>;
+    for (int i = threadIdx.x; i < F::P; i += blockDim.x) sred[i] = 0.0f;
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < NeuralCoop<D>::NJ; ++c) {
+        const int j = c * 32 + cp.lane;
+        if (j < F::H) {
+#pragma unroll
+            for (int i = 0; i < F::IN; ++i) atomicAdd(&sred[F::OFF_W1 + j * F::IN + i], cp.w1[c][i]);
+            atomicAdd(&sred[F::OFF_B1 + j], cp.w1[c][F::IN]);
+#pragma unroll
+            for (int d = 0; d < D; ++d) atomicAdd(&sred[F::OFF_W2 + d * F::H + j], cp.w2[c][d]);
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        float v = cp.b2[d];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (cp.lane == 0) atomicAdd(&sred[F::OFF_B2 + d], v);
+    }
+    __syncthreads();
+    const int set = a.pset ? a.pset[group] : 0;
+    float* dst = a.grad_params + (int64_t)set * F::P;
+    for (int i = threadIdx.x; i < F::P; i += blockDim.x) atomicAdd(&dst[i], sred[i]);
+}
+
 template <class F, int METHOD, bool EG, int ND, bool CP>
 __global__ void __launch_bounds__(128, HODE_BWD_MINBLOCKS) fixed_bwd_kernel(const SolveArgs a, int tiles_per_group) {
     extern __shared__ float smem[];
@@ -250,14 +298,25 @@ __global__ void __launch_bounds__(128, HODE_BWD_MINBLOCKS) fixed_bwd_kernel(cons
     float* sred = smem + (CP ? 0 : F::SP);
     const Tile tl = tile_of(a, tiles_per_group);
     if constexpr (!CP) stage_params<F>(a, tl.group, sp);
-    float acc[F::P];
-    zero_acc<F>(acc);
-    if (tl.b < a.batch) {
-        const int64_t idx = tl.group * a.batch + tl.b;
-        if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (fixed_bwd_traj<F, METHOD, EG>(a, ParamConst(), ds, idx, acc))); }
-        else { HODE_WITH_DOSE(ND, a, idx, (fixed_bwd_traj<F, METHOD, EG>(a, (const float*)sp, ds, idx, acc))); }
+    if constexpr (CoopOf<F>::value) {
+        // every lane of every warp runs the sweep (padding lanes on a clamped trajectory with zero gradients): the
+        // parameter-gradient accumulation is a warp-wide cooperation
+        NeuralCoop<F::D> cp;
+        coop_init(cp, sred + F::P);
+        const bool valid = tl.b < a.batch;
+        const int64_t idx = tl.group * a.batch + (valid ? tl.b : a.batch - 1);
+        HODE_WITH_DOSE(ND, a, idx, (fixed_bwd_traj<F, METHOD, EG>(a, (const float*)sp, ds, idx, &cp, valid)));
+        coop_flush(a, tl.group, cp, sred);
+    } else {
+        float acc[F::P];
+        zero_acc<F>(acc);
+        if (tl.b < a.batch) {
+            const int64_t idx = tl.group * a.batch + tl.b;
+            if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (fixed_bwd_traj<F, METHOD, EG>(a, ParamConst(), ds, idx, (float*)acc))); }
+            else { HODE_WITH_DOSE(ND, a, idx, (fixed_bwd_traj<F, METHOD, EG>(a, (const float*)sp, ds, idx, (float*)acc))); }
+        }
+        reduce_param_grads<F>(a, tl.group, acc, sred);
     }
-    reduce_param_grads<F>(a, tl.group, acc, sred);
 }
 
 // MAXT: launch bound.  128 for per-trajectory control and small groups (up to 255 registers per thread);
@@ -326,6 +385,19 @@ __global__ void __launch_bounds__(128) dopri5_bwd_kernel(const SolveArgs a, int 
     float* sred = smem + (CP ? 0 : F::SP);
     const Tile tl = tile_of(a, tiles_per_group);
     if constexpr (!CP) stage_params<F>(a, tl.group, sp);
+    if constexpr (CoopOf<F>::value) {
+        if (!a.per_traj) {
+            // batch-coupled groups (one group per CTA, never flattened for this field): every lane of the CTA reverses
+            // the same number of accepted steps, so the warp-cooperative accumulation applies
+            NeuralCoop<F::D> cp;
+            coop_init(cp, sred + F::P);
+            const bool valid = tl.b < a.batch;
+            const int64_t idx = tl.group * a.batch + (valid ? tl.b : a.batch - 1);
+            HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, (const float*)sp, ds, idx, tl.group, &cp, valid)));
+            coop_flush(a, tl.group, cp, sred);
+            return;
+        }
+    }
     float acc[F::P];
     zero_acc<F>(acc);
     if (tl.b < a.batch) {
@@ -335,11 +407,11 @@ __global__ void __launch_bounds__(128) dopri5_bwd_kernel(const SolveArgs a, int 
             float* base = sred + F::P + threadIdx.x;
             StageSmem<F::D> k{base, (int)blockDim.x};
             StageSmem<F::D> kb{base + 7 * F::D * blockDim.x, (int)blockDim.x};
-            if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, ParamConst(), ds, idx, ctrl, acc, k, kb))); }
-            else { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, (const float*)sp, ds, idx, ctrl, acc, k, kb))); }
+            if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, ParamConst(), ds, idx, ctrl, (float*)acc, k, kb))); }
+            else { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, (const float*)sp, ds, idx, ctrl, (float*)acc, k, kb))); }
         } else {
-            if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, ParamConst(), ds, idx, ctrl, acc))); }
-            else { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, (const float*)sp, ds, idx, ctrl, acc))); }
+            if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, ParamConst(), ds, idx, ctrl, (float*)acc))); }
+            else { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, (const float*)sp, ds, idx, ctrl, (float*)acc))); }
         }
     }
     reduce_param_grads<F>(a, tl.group, acc, sred);
@@ -370,6 +442,12 @@ inline int round_up32(int64_t n) { return (int)(((n + 31) / 32) * 32); }
         }                                                                \
         LAUNCH(false);                                                   \
     } while (0)
+
+template <class F>
+constexpr size_t coop_stage_floats() {
+    if constexpr (CoopOf<F>::value) return NeuralCoop<F::D>::kStageFloats;
+    else return 0;
+}
 
 // With ONE parameter set nothing ties a CTA to a group: threads enumerate all trajectories ("flat"), so small groups do
 // not leave lanes idle.  The trajectory index is unchanged (group * batch + b).
@@ -413,8 +491,13 @@ int launch_fixed_bwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st
     const int64_t nblk = a.n_groups * tiles;
     const bool nd1 = cfg.n_dose == 1;
     const bool eg = cfg.expert_grads != 0;
-#define HODE_FB(M, EG, ND, CP) \
-    fixed_bwd_kernel<F, M, EG, ND, CP><<<(unsigned)nblk, threads, ((CP ? 0 : F::SP) + F::P) * sizeof(float), st>>>(a, tiles)
+#define HODE_FB(M, EG, ND, CP)                                                                                        \
+    do {                                                                                                           \
+        const size_t sh_ = ((CP ? 0 : F::SP) + F::P + coop_stage_floats<F>() * (size_t)(threads / 32)) * sizeof(float); \
+        if (sh_ > 48 * 1024)                                                                                       \
+            cudaFuncSetAttribute(fixed_bwd_kernel<F, M, EG, ND, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_); \
+        fixed_bwd_kernel<F, M, EG, ND, CP><<<(unsigned)nblk, threads, sh_, st>>>(a, tiles);                        \
+    } while (0)
 #define HODE_FB_M(M, CP)                                                           \
     do {                                                                           \
         if (eg) { if (nd1) HODE_FB(M, true, 1, CP); else HODE_FB(M, true, 0, CP); } \
@@ -477,7 +560,7 @@ int launch_dopri5_fwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t s
 
 template <class F>
 int launch_dopri5_bwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st) {
-    const SolveArgs a = flatten(a_in);
+    const SolveArgs a = (CoopOf<F>::value && !a_in.per_traj) ? a_in : flatten(a_in);
     const int threads = a.batch >= 128 ? 128 : round_up32(a.batch);
     const int tiles = (int)((a.batch + threads - 1) / threads);
     const int64_t nblk = a.n_groups * tiles;
@@ -485,7 +568,8 @@ int launch_dopri5_bwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t s
     const bool eg = cfg.expert_grads != 0;
 #define HODE_DB(EG, ND, CP)                                                                                              \
     do {                                                                                                                 \
-        const size_t sh_ = ((CP ? 0 : F::SP) + F::P + (size_t)Dopri5BwdStore<F>::floats_per_thread * threads) * sizeof(float); \
+        const size_t sh_ = ((CP ? 0 : F::SP) + F::P + (size_t)Dopri5BwdStore<F>::floats_per_thread * threads +           \
+                            coop_stage_floats<F>() * (size_t)(threads / 32)) * sizeof(float);                            \
         if (sh_ > 48 * 1024)                                                                                             \
             cudaFuncSetAttribute(dopri5_bwd_kernel<F, EG, ND, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_); \
         dopri5_bwd_kernel<F, EG, ND, CP><<<(unsigned)nblk, threads, sh_, st>>>(a, tiles);                                \
