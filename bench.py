@@ -233,6 +233,8 @@ def run_ours(args):
     from hybrid_ode_neurips_2021_b200 import dist as hd
 
     world, rank, local = dist_setup(args.gpus)
+    # torchrun pins OMP_NUM_THREADS=1: give every rank its share of the host cores for the synthetic-cohort generation
+    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     lib = L.get_lib()  # raises if the CUDA extension is missing: no fallback
