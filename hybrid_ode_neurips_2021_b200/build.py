@@ -42,7 +42,7 @@ def _units():
     """(object name, source, extra defines)"""
     units = [("hode_api.o", "hode_api.cu", []), ("hode_aux.o", "hode_aux.cu", []), ("hode_eval.o", "hode_eval.cu", []), ("hode_real.o", "hode_real.cu", [])]
     for d in ROCHE_DIMS:
-        for hill2 in (0, 1):
+        for hill2 in (0, 1, 2):  # 2 = the ablation field
             units.append(("inst_roche_d{}_h{}.o".format(d, hill2), "inst_roche.cu",
                           ["-DHODE_INST_D={}".format(d), "-DHODE_INST_HILL2={}".format(hill2)]))
     for field, z in REAL_UNITS:

@@ -51,13 +51,20 @@ static int dispatch(Op op, const hode_cfg& cfg, const SolveArgs& a, cudaStream_t
     int rc = -1;
     if (cfg.field == HODE_FIELD_ROCHE) {
         const bool hill2 = (cfg.flags & HODE_FLAG_HILL2) != 0;
+        const bool ablate = (cfg.flags & HODE_FLAG_ABLATE) != 0;
+#define HODE_ROCHE_CASE(DD)                                                                  \
+    case DD:                                                                                 \
+        rc = ablate ? run<Roche<DD, true, true>>(op, cfg, a, st)                             \
+                    : (hill2 ? run<Roche<DD, true>>(op, cfg, a, st) : run<Roche<DD>>(op, cfg, a, st)); \
+        break
         switch (cfg.latent_dim) {
-            case 4: rc = hill2 ? run<Roche<4, true>>(op, cfg, a, st) : run<Roche<4>>(op, cfg, a, st); break;
-            case 6: rc = hill2 ? run<Roche<6, true>>(op, cfg, a, st) : run<Roche<6>>(op, cfg, a, st); break;
-            case 8: rc = hill2 ? run<Roche<8, true>>(op, cfg, a, st) : run<Roche<8>>(op, cfg, a, st); break;
-            case 12: rc = hill2 ? run<Roche<12, true>>(op, cfg, a, st) : run<Roche<12>>(op, cfg, a, st); break;
+            HODE_ROCHE_CASE(4);
+            HODE_ROCHE_CASE(6);
+            HODE_ROCHE_CASE(8);
+            HODE_ROCHE_CASE(12);
             default: return fail(HODE_ERR_UNSUPPORTED, "RocheODE latent_dim %s%lld is not compiled in (4, 6, 8, 12)", "", cfg.latent_dim);
         }
+#undef HODE_ROCHE_CASE
     } else if (cfg.field == HODE_FIELD_NEURAL) {
         switch (cfg.latent_dim) {
             case 4: rc = run<Neural<4>>(op, cfg, a, st); break;
@@ -85,7 +92,8 @@ const char* hode_last_error(void) { return g_err; }
 int64_t hode_param_count(const hode_cfg* cfg) {
     if (!cfg) return -1;
     const int64_t d = cfg->latent_dim;
-    if (cfg->field == HODE_FIELD_ROCHE) return d >= 4 ? 13 + (d - 4) * d + (d - 4) : -1;
+    if (cfg->field == HODE_FIELD_ROCHE)
+        return d >= 4 ? 13 + (d - 4) * d + (d - 4) + ((cfg->flags & HODE_FLAG_ABLATE) ? 2 : 0) : -1;
     if (cfg->field == HODE_FIELD_NEURAL) return d >= 1 ? 1 + 10 * d * (d + 1) + 10 * d + d * 10 * d + d : -1;
     return -1;
 }

@@ -156,14 +156,18 @@ enum RocheIdx {
     R_NSCALAR
 };
 
-template <int D_, bool HILL2_ = false>
+// ABLATE_: the ablation study's expert part (model.py:545-549): dx = (R, -D theta_1, Q, -I theta_2); theta_1, theta_2 are
+// appended to the packed parameters.
+template <int D_, bool HILL2_ = false, bool ABLATE_ = false>
 struct Roche {
     static constexpr int D = D_;
     static constexpr bool HILL2 = HILL2_;  // caller guarantees HillCure == HillPatho == 2 (checked on the device)
+    static constexpr bool ABLATE = ABLATE_;
     static constexpr int ML = D_ - 4;
-    static constexpr int P = R_NSCALAR + ML * D_ + ML;  // packed parameter count
     static constexpr int OFF_W = R_NSCALAR;
     static constexpr int OFF_B = R_NSCALAR + ML * D_;
+    static constexpr int OFF_TH = OFF_B + ML;                 // theta_1, theta_2 (ABLATE only)
+    static constexpr int P = OFF_TH + (ABLATE_ ? 2 : 0);      // packed parameter count
     // staged copy appends derived constants
     static constexpr int OFF_ECP = P;       // ec50 ** HillPatho
     static constexpr int OFF_KL2 = P + 1;   // kel * log2(e)
@@ -175,7 +179,7 @@ struct Roche {
     // With HODE_FOLD_TANH the ml_net weights and biases are pre-multiplied by 2 log2(e): W y + b is then directly the
     // argument of the ex2 inside tanh_pre().
     HODE_HD static void stage(const float* __restrict__ src, float* sp, int tid, int nthr) {
-        for (int i = tid; i < P; i += nthr) sp[i] = (i >= OFF_W) ? src[i] * kTanhPre : src[i];
+        for (int i = tid; i < P; i += nthr) sp[i] = (i >= OFF_W && i < OFF_TH) ? src[i] * kTanhPre : src[i];
     }
     HODE_HD static void prepare(float* sp) {
         sp[OFF_ECP] = pow_hill(sp[R_EC50], sp[R_HP]);
@@ -183,7 +187,7 @@ struct Roche {
     }
     // false if this instantiation may not be used with the staged parameters (HILL2 kernels with other exponents)
     template <class PS>
-    HODE_HD static bool params_ok(PS sp) { return !HILL2 || (sp[R_HC] == 2.0f && sp[R_HP] == 2.0f); }
+    HODE_HD static bool params_ok(PS sp) { return ABLATE || !HILL2 || (sp[R_HC] == 2.0f && sp[R_HP] == 2.0f); }
     HODE_HD static float hpow(float x, float p) { return HILL2 ? x * x : pow_hill(x, p); }
     HODE_HD static float hdpow(float x, float p) { return HILL2 ? 2.0f * x : dpow_hill(x, p); }
 
@@ -192,13 +196,20 @@ struct Roche {
     template <class PS, class Dose>
     HODE_HD static void eval(PS sp, float t, const Dose& ds, const float (&y)[D_], float (&dy)[D_]) {
         const float dis = y[0], react = y[1], imm = y[2], dose2 = y[3];
-        const float ip = hpow(imm, sp[R_HC]);
-        const float rp = hpow(react, sp[R_HP]);
-        dy[0] = dis * fmaf(-react, sp[R_KDCIR], fmaf(-ip, sp[R_KDCI], sp[R_KDISPROG]));
-        const float hill = (rp * sp[R_EMAX]) * rcp_f(sp[OFF_ECP] + rp);
-        dy[1] = fmaf(dis, fmaf(react, sp[R_KFB], sp[R_KID]), fmaf(-react, fmaf(dose2, sp[R_KDEXA], sp[R_KOFF]), hill));
-        dy[2] = react * sp[R_KIM];
-        dy[3] = sp[R_KEL] * (roche_dose(ds, t, sp[R_KEL], sp[OFF_KL2]) - dose2);
+        if (ABLATE) {
+            dy[0] = react;
+            dy[1] = -dis * sp[OFF_TH];
+            dy[2] = dose2;
+            dy[3] = -imm * sp[OFF_TH + 1];
+        } else {
+            const float ip = hpow(imm, sp[R_HC]);
+            const float rp = hpow(react, sp[R_HP]);
+            dy[0] = dis * fmaf(-react, sp[R_KDCIR], fmaf(-ip, sp[R_KDCI], sp[R_KDISPROG]));
+            const float hill = (rp * sp[R_EMAX]) * rcp_f(sp[OFF_ECP] + rp);
+            dy[1] = fmaf(dis, fmaf(react, sp[R_KFB], sp[R_KID]), fmaf(-react, fmaf(dose2, sp[R_KDEXA], sp[R_KOFF]), hill));
+            dy[2] = react * sp[R_KIM];
+            dy[3] = sp[R_KEL] * (roche_dose(ds, t, sp[R_KEL], sp[OFF_KL2]) - dose2);
+        }
 #pragma unroll
         for (int j = 0; j < ML; ++j) {
             float a = sp[OFF_B + j];
@@ -213,40 +224,53 @@ struct Roche {
     template <bool EG, class PS, class Dose>
     HODE_HD static void vjp(PS sp, float t, const Dose& ds, const float (&y)[D_], const float* k,
                             const float (&l)[D_], float (&gy)[D_], float* acc) {
-        const float dis = y[0], react = y[1], imm = y[2], dose2 = y[3];
-        const float hc = sp[R_HC], hp = sp[R_HP], em = sp[R_EMAX], ecp = sp[OFF_ECP];
-        const float kdci = sp[R_KDCI], kdcir = sp[R_KDCIR], kfb = sp[R_KFB], kdexa = sp[R_KDEXA];
-        const float kel = sp[R_KEL];
-        const float ip = hpow(imm, hc);
-        const float rp = hpow(react, hp);
-        const float inv_den = rcp_f(ecp + rp);
-        const float l0 = l[0], l1 = l[1], l2 = l[2], l3 = l[3];
-        const float l0d = l0 * dis;
-        const float hill_d = (em * ecp) * hdpow(react, hp) * (inv_den * inv_den);  // d/dR of the Hill term
-        gy[0] = fmaf(l0, fmaf(-react, kdcir, fmaf(-ip, kdci, sp[R_KDISPROG])), l1 * fmaf(react, kfb, sp[R_KID]));
-        gy[1] = fmaf(-l0d, kdcir, fmaf(l1, fmaf(dis, kfb, hill_d) - fmaf(dose2, kdexa, sp[R_KOFF]), l2 * sp[R_KIM]));
-        gy[2] = -l0d * kdci * hdpow(imm, hc);
-        gy[3] = fmaf(-l1 * react, kdexa, -l3 * kel);
+        if (ABLATE) {
+            gy[0] = -l[1] * sp[OFF_TH];
+            gy[1] = l[0];
+            gy[2] = -l[3] * sp[OFF_TH + 1];
+            gy[3] = l[2];
 #pragma unroll
-        for (int d = 4; d < D_; ++d) gy[d] = 0.0f;
-        if (EG) {
-            const float ec50 = sp[R_EC50];
-            acc[R_KDISPROG] += l0d;
-            acc[R_KDCI] -= l0d * ip;
-            acc[R_KDCIR] -= l0d * react;
-            acc[R_HC] -= l0d * kdci * dpow_hill_exp(imm, ip, hc);
-            acc[R_KID] += l1 * dis;
-            acc[R_KOFF] -= l1 * react;
-            acc[R_KFB] += l1 * dis * react;
-            acc[R_EMAX] += l1 * rp * inv_den;
-            // d/d ec50 and d/d hp of  em*rp/(ec50**hp + rp)
-            acc[R_EC50] -= l1 * em * rp * dpow_hill(ec50, hp) * inv_den * inv_den;
-            acc[R_HP] += l1 * em * (dpow_hill_exp(react, rp, hp) * ecp - rp * dpow_hill_exp(ec50, ecp, hp)) * inv_den *
-                         inv_den;
-            acc[R_KDEXA] -= l1 * dose2 * react;
-            acc[R_KIM] += l2 * react;
-            const float dose = roche_dose(ds, t, kel, sp[OFF_KL2]);
-            acc[R_KEL] += l3 * (dose - dose2 + kel * roche_dose_dkel(ds, t, kel, sp[OFF_KL2]));
+            for (int d = 4; d < D_; ++d) gy[d] = 0.0f;
+            if (EG) {
+                acc[OFF_TH] -= l[1] * y[0];
+                acc[OFF_TH + 1] -= l[3] * y[2];
+            }
+        } else {
+            const float dis = y[0], react = y[1], imm = y[2], dose2 = y[3];
+            const float hc = sp[R_HC], hp = sp[R_HP], em = sp[R_EMAX], ecp = sp[OFF_ECP];
+            const float kdci = sp[R_KDCI], kdcir = sp[R_KDCIR], kfb = sp[R_KFB], kdexa = sp[R_KDEXA];
+            const float kel = sp[R_KEL];
+            const float ip = hpow(imm, hc);
+            const float rp = hpow(react, hp);
+            const float inv_den = rcp_f(ecp + rp);
+            const float l0 = l[0], l1 = l[1], l2 = l[2], l3 = l[3];
+            const float l0d = l0 * dis;
+            const float hill_d = (em * ecp) * hdpow(react, hp) * (inv_den * inv_den);  // d/dR of the Hill term
+            gy[0] = fmaf(l0, fmaf(-react, kdcir, fmaf(-ip, kdci, sp[R_KDISPROG])), l1 * fmaf(react, kfb, sp[R_KID]));
+            gy[1] = fmaf(-l0d, kdcir, fmaf(l1, fmaf(dis, kfb, hill_d) - fmaf(dose2, kdexa, sp[R_KOFF]), l2 * sp[R_KIM]));
+            gy[2] = -l0d * kdci * hdpow(imm, hc);
+            gy[3] = fmaf(-l1 * react, kdexa, -l3 * kel);
+    #pragma unroll
+            for (int d = 4; d < D_; ++d) gy[d] = 0.0f;
+            if (EG) {
+                const float ec50 = sp[R_EC50];
+                acc[R_KDISPROG] += l0d;
+                acc[R_KDCI] -= l0d * ip;
+                acc[R_KDCIR] -= l0d * react;
+                acc[R_HC] -= l0d * kdci * dpow_hill_exp(imm, ip, hc);
+                acc[R_KID] += l1 * dis;
+                acc[R_KOFF] -= l1 * react;
+                acc[R_KFB] += l1 * dis * react;
+                acc[R_EMAX] += l1 * rp * inv_den;
+                // d/d ec50 and d/d hp of  em*rp/(ec50**hp + rp)
+                acc[R_EC50] -= l1 * em * rp * dpow_hill(ec50, hp) * inv_den * inv_den;
+                acc[R_HP] += l1 * em * (dpow_hill_exp(react, rp, hp) * ecp - rp * dpow_hill_exp(ec50, ecp, hp)) * inv_den *
+                             inv_den;
+                acc[R_KDEXA] -= l1 * dose2 * react;
+                acc[R_KIM] += l2 * react;
+                const float dose = roche_dose(ds, t, kel, sp[OFF_KL2]);
+                acc[R_KEL] += l3 * (dose - dose2 + kel * roche_dose_dkel(ds, t, kel, sp[OFF_KL2]));
+            }
         }
 #pragma unroll
         for (int j = 0; j < ML; ++j) {

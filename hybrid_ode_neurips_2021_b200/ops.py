@@ -33,9 +33,9 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 def make_cfg(field, latent_dim, method, *, controller=L.CTRL_BATCH, perturb=False, n_dose=1, expert_grads=True,
              rtol=1e-7, atol=1e-9, safety=0.9, ifactor=10.0, dfactor=0.2, first_step=None,
-             max_num_steps=2 ** 31 - 1, attempt_cap=ATTEMPT_CAP_DEFAULT, hill2=False) -> L.HodeCfg:
+             max_num_steps=2 ** 31 - 1, attempt_cap=ATTEMPT_CAP_DEFAULT, hill2=False, ablate=False) -> L.HodeCfg:
     cfg = L.HodeCfg()
-    cfg.flags = L.FLAG_HILL2 if hill2 else 0
+    cfg.flags = (L.FLAG_HILL2 if hill2 else 0) | (L.FLAG_ABLATE if ablate else 0)
     cfg.field, cfg.latent_dim, cfg.method, cfg.controller = int(field), int(latent_dim), int(method), int(controller)
     cfg.perturb, cfg.n_dose, cfg.expert_grads = int(bool(perturb)), int(n_dose), int(bool(expert_grads))
     cfg.rtol, cfg.atol, cfg.safety, cfg.ifactor, cfg.dfactor = float(rtol), float(atol), float(safety), float(ifactor), float(dfactor)

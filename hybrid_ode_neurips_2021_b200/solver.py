@@ -84,8 +84,6 @@ def _is_neural(func) -> bool:
 def field_kind(func):
     if isinstance(func, torch.nn.Module):
         if _is_roche(func):
-            if getattr(func, "ablate", False):
-                raise NotImplementedError("RocheODE(ablate=True) has no fused kernel")
             return L.FIELD_ROCHE
         if _is_neural(func):
             return L.FIELD_NEURAL
@@ -102,6 +100,8 @@ def pack_params(func, kind) -> torch.Tensor:
         if int(func.latent_dim) > 4:
             lin = func.ml_net[0]
             parts += [lin.weight.reshape(-1), lin.bias.reshape(-1)]
+        if getattr(func, "ablate", False):  # the ablation field's two scalars go last (include/hode.h)
+            parts += [func.theta_1.reshape(1), func.theta_2.reshape(1)]
     else:
         l1, l2 = func.ml_net[0], func.ml_net[2]
         parts = [func.kel.reshape(1), l1.weight.reshape(-1), l1.bias.reshape(-1), l2.weight.reshape(-1), l2.bias.reshape(-1)]
@@ -368,6 +368,9 @@ def _odeint_impl(funcs, y0, t, rtol, atol, method, options, event_fn):
     need_grad = torch.is_grad_enabled() and (
         y0.requires_grad or any(p.requires_grad for f in funcs for p in f.parameters())
     )
+    ablate = kind == L.FIELD_ROCHE and bool(getattr(func, "ablate", False))
+    if kind == L.FIELD_ROCHE and any(bool(getattr(f, "ablate", False)) != ablate for f in funcs):
+        raise ValueError("ensemble members must all be ablation fields or none")
     cfg = ops.make_cfg(
         kind, D, L.METHODS[method],
         controller=L.CTRL_TRAJ if ctrl_name == "trajectory" else L.CTRL_BATCH,
@@ -379,6 +382,7 @@ def _odeint_impl(funcs, y0, t, rtol, atol, method, options, event_fn):
         attempt_cap=int(options.get("attempt_cap", ops.ATTEMPT_CAP_DEFAULT)),
         hill2=(kind == L.FIELD_ROCHE and bool(options.get("hill2_kernels", True))
                and all(hill_exponents_are_two(f) for f in funcs)),
+        ablate=ablate,
     )
     if M == 1:
         packed = pack_params(func, kind)

@@ -84,8 +84,11 @@ typedef struct hode_stats {
 /* hode_cfg.flags.  HODE_FLAG_HILL2: the caller guarantees HillCure == HillPatho == 2.0 exactly (the RochConfig
  * defaults, sim_config.py:5-6; never trained by the simulation experiments) in EVERY parameter set of the call; the
  * library then runs kernels in which x**Hill is a multiply (model.py:529, 537-538).  A violated guarantee is detected on
- * the device and reported loudly: NaN in the solution / gradients (dopri5: status HODE_SOLVE_NONFINITE). */
-typedef enum hode_flags { HODE_FLAG_HILL2 = 1 } hode_flags;
+ * the device and reported loudly: NaN in the solution / gradients (dopri5: status HODE_SOLVE_NONFINITE).
+ * HODE_FLAG_ABLATE: RocheODE(ablate=True), the ablation study's expert part (model.py:545-549):
+ * dx = (ImmuneReact, -Disease theta_1, Dose2, -Immunity theta_2); the packed parameters gain theta_1, theta_2 at the END
+ * (after ml_net's bias); the dose schedule is unused. */
+typedef enum hode_flags { HODE_FLAG_HILL2 = 1, HODE_FLAG_ABLATE = 2 } hode_flags;
 
 typedef struct hode_cfg {
     int32_t field;        /* hode_field */

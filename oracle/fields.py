@@ -50,15 +50,20 @@ def dose_schedule(action: torch.Tensor, step_size):
 
 
 class OracleRocheODE(nn.Module):
-    """Expert PK/PD field + optional latent MLP (model.py:446-555), ``ablate=False`` branch."""
+    """Expert PK/PD field + optional latent MLP (model.py:446-555); ``ablate=True`` is the ablation study's expert part
+    (model.py:545-549)."""
 
-    def __init__(self, latent_dim, step_size=1, dtype=torch.float32):
+    def __init__(self, latent_dim, step_size=1, dtype=torch.float32, ablate=False):
         super().__init__()
         self.latent_dim = int(latent_dim)
         self.ml_dim = self.latent_dim - 4
         self.step_size = step_size
+        self.ablate = bool(ablate)
         for name, val in zip(EXPERT_NAMES, EXPERT_DEFAULTS):
             setattr(self, name, nn.Parameter(torch.tensor(val, dtype=dtype)))
+        if self.ablate:
+            self.theta_1 = nn.Parameter(torch.tensor(1.0, dtype=dtype))
+            self.theta_2 = nn.Parameter(torch.tensor(2.0, dtype=dtype))
         if self.ml_dim > 0:
             self.ml_net = nn.Sequential(nn.Linear(self.latent_dim, self.ml_dim), nn.Tanh()).to(dtype)
         else:
@@ -75,6 +80,11 @@ class OracleRocheODE(nn.Module):
 
     def forward(self, t, y):
         dis, react, imm, dose2 = y[:, 0], y[:, 1], y[:, 2], y[:, 3]
+        if self.ablate:
+            d1, d2, d3, d4 = react, -1.0 * dis * self.theta_1, dose2, -1.0 * imm * self.theta_2
+            if self.ml_dim > 0:
+                return torch.cat([d1[..., None], d2[..., None], d3[..., None], d4[..., None], self.ml_net(y)], dim=-1)
+            return torch.stack([d1, d2, d3, d4], dim=-1)
         dose = self.dose_at_time(t)
         d1 = (
             dis * self.k_disprog

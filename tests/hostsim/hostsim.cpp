@@ -142,6 +142,14 @@ int run(Op op, const hode_cfg& cfg, const SolveArgs& a) {
 int dispatch(Op op, const hode_cfg& cfg, const SolveArgs& a) {
     if (cfg.field == HODE_FIELD_ROCHE) {
         const bool h2 = (cfg.flags & HODE_FLAG_HILL2) != 0;
+        if (cfg.flags & HODE_FLAG_ABLATE) {
+            switch (cfg.latent_dim) {
+                case 4: return run<Roche<4, true, true>>(op, cfg, a);
+                case 6: return run<Roche<6, true, true>>(op, cfg, a);
+                case 8: return run<Roche<8, true, true>>(op, cfg, a);
+                case 12: return run<Roche<12, true, true>>(op, cfg, a);
+            }
+        }
         switch (cfg.latent_dim) {
             case 4: return h2 ? run<Roche<4, true>>(op, cfg, a) : run<Roche<4>>(op, cfg, a);
             case 6: return h2 ? run<Roche<6, true>>(op, cfg, a) : run<Roche<6>>(op, cfg, a);
@@ -163,7 +171,7 @@ int dispatch(Op op, const hode_cfg& cfg, const SolveArgs& a) {
 }
 int64_t pcount(const hode_cfg* cfg) {
     const int64_t d = cfg->latent_dim;
-    if (cfg->field == HODE_FIELD_ROCHE) return 13 + (d - 4) * d + (d - 4);
+    if (cfg->field == HODE_FIELD_ROCHE) return 13 + (d - 4) * d + (d - 4) + ((cfg->flags & HODE_FLAG_ABLATE) ? 2 : 0);
     return 1 + 10 * d * (d + 1) + 10 * d + d * 10 * d + d;
 }
 }  // namespace

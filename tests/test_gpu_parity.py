@@ -537,3 +537,31 @@ def test_two_streams_share_the_constant_bank_safely():
         for o in outs[i]:
             assert torch.equal(o, refs[i])
     assert not torch.equal(refs[0], refs[1])
+
+
+def test_ablation_decoder_drop_in():
+    """RocheExpertDecoder(ablate=True) (run_simulation.py --ablate; model_name '...Ablate'): same state_dict keys as the
+    reference class, fused kernels for the ablation field, parity with the oracle."""
+    D, obs, B = 6, 20, 12
+    torch.manual_seed(9)
+    dec = H.RocheExpertDecoder(obs, D, 1, 14, 1, ablate=True, method="dopri5", device=DEV)
+    assert dec.model_name == "HybridDecoderAblate"
+    od = OF.OracleDecoder(obs, D, method="dopri5", options={"differentiable_first_step": False})
+    od.ode = OF.OracleRocheODE(D, ablate=True)
+    assert set(od.state_dict().keys()) == set(dec.state_dict().keys())
+    od.load_state_dict(dec.state_dict())
+    y0, a, x, mask = make_cohort(B, D, obs=obs, seed=33)
+    z = y0.clone().requires_grad_(True)
+    xh, _ = od(z, a)
+    lref = OF.masked_sse(x, xh, mask)
+    lref.backward()
+    zg = y0.clone().to(DEV).requires_grad_(True)
+    h = dec.solve(zg, a.to(DEV))
+    loss = H.masked_sse(dec, h, x.to(DEV), mask.to(DEV))
+    loss.backward()
+    assert abs(loss.item() - lref.item()) <= 1e-5 * abs(lref.item())
+    assert relerr(zg.grad, z.grad) < 1e-4
+    assert relerr(dec.ode.ml_net[0].weight.grad, od.ode.ml_net[0].weight.grad) < 1e-4
+    for n in ("theta_1", "theta_2"):
+        go, gm = getattr(od.ode, n).grad.item(), getattr(dec.ode, n).grad.item()
+        assert abs(gm - go) <= 1e-4 * max(1.0, abs(go)), n

@@ -128,6 +128,43 @@ def test_dopri5_first_attempt_is_exactly_the_oracle_attempt(lib):
     assert abs(tape[0][0, 1, 1].item() - tr.attempts[1][1]) <= 1e-3 * tr.attempts[1][1]
 
 
+@pytest.mark.parametrize("D", [4, 8])
+@pytest.mark.parametrize("method", ["rk4", "dopri5"])
+def test_ablation_field(lib, D, method):
+    """RocheODE(ablate=True) (model.py:545-549): dx = (R, -D theta_1, Q, -I theta_2) + ml_net; theta's packed last."""
+    B = 5
+    torch.manual_seed(D)
+    o = OF.OracleRocheODE(D, ablate=True)
+    with torch.no_grad():
+        o.theta_1.fill_(0.8); o.theta_2.fill_(1.7)
+    y0, a, _, _ = make_cohort(B, D, seed=60 + D)
+    o.set_action(a)
+    t = torch.arange(0, 15.0)
+    W = torch.randn(15, B, D, generator=torch.Generator().manual_seed(2))
+    z = y0.clone().requires_grad_(True)
+    kw = dict(options={"step_size": 0.125}) if method == "rk4" else dict(rtol=1e-6, atol=1e-7, options={"differentiable_first_step": False})
+    ref = OI.odeint(o, z, t, method=method, **kw)
+    (ref * W).sum().backward()
+    params = torch.cat([pack_roche(o)[0], o.theta_1.detach().reshape(1), o.theta_2.detach().reshape(1)])[None].contiguous()
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.METHODS[method], n_dose=1, ablate=True, rtol=1e-6, atol=1e-7)
+    assert params.shape[1] == lib.hode_param_count(cfg)
+    pb = ops.Problem(cfg, 1, B, o.dosage.float().contiguous(), o.times.float().contiguous(), params, None)
+    if method == "rk4":
+        grid = OI.fixed_grid_points(t, 0.125).contiguous()
+        h, tape = ops.fixed_fwd(lib, pb, y0, grid, t, True)
+        gy0, gp = ops.fixed_bwd(lib, pb, grid, t, W, tape)
+    else:
+        h, stats, tape = ops.dopri5_fwd(lib, pb, y0, t.double(), 512)
+        assert int(stats[0, 3]) == 0
+        gy0, gp = ops.dopri5_bwd(lib, pb, t.double(), W, tape, stats)
+    tol = 5e-6 if method == "rk4" else 1e-4
+    assert relerr(h, ref) < tol and relerr(gy0, z.grad) < 4 * tol
+    assert abs(gp[0, -2].item() - o.theta_1.grad.item()) < 10 * tol * max(1.0, abs(o.theta_1.grad.item()))
+    assert abs(gp[0, -1].item() - o.theta_2.grad.item()) < 10 * tol * max(1.0, abs(o.theta_2.grad.item()))
+    if D > 4:
+        assert relerr(gp[0, 13:-2], torch.cat([o.ml_net[0].weight.grad.reshape(-1), o.ml_net[0].bias.grad])) < 10 * tol
+
+
 def test_hill2_kernels_refuse_other_exponents(lib):
     """HODE_FLAG_HILL2 is a caller guarantee; a violated guarantee must fail loudly (NaN / NONFINITE), not silently."""
     D, B = 6, 3
