@@ -334,43 +334,47 @@ __global__ void __launch_bounds__(TR * SPLIT) decode_sse_fast_kernel(
                         w[i][4 * v] = wv.x; w[i][4 * v + 1] = wv.y; w[i][4 * v + 2] = wv.z; w[i][4 * v + 3] = wv.w;
                     }
             };
-            float4 xn, mn, bn;
-            float wn[2][DP];
-            if (q_lo < q_hi) {
-                xn = xr[q_lo]; mn = mr[q_lo]; bn = sB4[q_lo];
-                load_wpair(q_lo * 4, wn);
-            }
-            for (int q = q_lo; q < q_hi; ++q) {
-                const float4 xv = xn, mv = mn, bv = bn;
-                if (q + 1 < q_hi) { xn = xr[q + 1]; mn = mr[q + 1]; bn = sB4[q + 1]; }
+            // two W-pair buffers (A: observation columns 4q, 4q+1; B: 4q+2, 4q+3) and two x / mask / bias chunk buffers are
+            // filled one step ahead and used alternately: no register-to-register copies between iterations
+            float wA[2][DP], wB[2][DP];
+            auto two_columns = [&](const float (&w)[2][DP], const float* xs, const float* ms, const float* bs, float* cs) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    float xh = bs[i];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) xh = fmaf(w[i][d], hv[d], xh);
+                    const float diff = xs[i] - xh;
+                    const float dm = diff * ms[i];
+                    lsum = fmaf(diff, dm, lsum);
+                    const float c = scale * dm;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) gh[d] = fmaf(c, w[i][d], gh[d]);
+                    cs[i] = c;
+                }
+            };
+            auto chunk = [&](int q, const float4& xv, const float4& mv, const float4& bv) {  // wA holds columns 4q, 4q+1
                 const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, ms[4] = {mv.x, mv.y, mv.z, mv.w};
                 const float bs[4] = {bv.x, bv.y, bv.z, bv.w};
                 float cs[4];
-#pragma unroll
-                for (int pr = 0; pr < 2; ++pr) {
-                    float w[2][DP];
-#pragma unroll
-                    for (int i = 0; i < 2; ++i)
-#pragma unroll
-                        for (int d = 0; d < DP; ++d) w[i][d] = wn[i][d];
-                    if (pr == 0) load_wpair(q * 4 + 2, wn);
-                    else if (q + 1 < q_hi) load_wpair(q * 4 + 4, wn);
-#pragma unroll
-                    for (int i = 0; i < 2; ++i) {
-                        const int e = 2 * pr + i;
-                        float xh = bs[e];
-#pragma unroll
-                        for (int d = 0; d < D; ++d) xh = fmaf(w[i][d], hv[d], xh);
-                        const float diff = xs[e] - xh;
-                        const float dm = diff * ms[e];
-                        lsum = fmaf(diff, dm, lsum);
-                        const float c = scale * dm;
-#pragma unroll
-                        for (int d = 0; d < D; ++d) gh[d] = fmaf(c, w[i][d], gh[d]);
-                        cs[e] = c;
-                    }
-                }
+                load_wpair(q * 4 + 2, wB);
+                two_columns(wA, xs, ms, bs, cs);
+                if (q + 1 < q_hi) load_wpair(q * 4 + 4, wA);
+                two_columns(wB, xs + 2, ms + 2, bs + 2, cs + 2);
                 xr[q] = make_float4(cs[0], cs[1], cs[2], cs[3]);
+            };
+            float4 x0, m0, b0v, x1, m1, b1v;
+            int q = q_lo;
+            if (q < q_hi) {
+                x0 = xr[q]; m0 = mr[q]; b0v = sB4[q];
+                load_wpair(q * 4, wA);
+            }
+            while (q < q_hi) {
+                if (q + 1 < q_hi) { x1 = xr[q + 1]; m1 = mr[q + 1]; b1v = sB4[q + 1]; }
+                chunk(q, x0, m0, b0v);
+                if (q + 1 >= q_hi) break;
+                if (q + 2 < q_hi) { x0 = xr[q + 2]; m0 = mr[q + 2]; b0v = sB4[q + 2]; }
+                chunk(q + 1, x1, m1, b1v);
+                q += 2;
             }
             if (SPLIT > 1 && part != 0) {
 #pragma unroll
@@ -398,15 +402,8 @@ __global__ void __launch_bounds__(TR * SPLIT) decode_sse_fast_kernel(
                     hr[4 * v] = q4.x; hr[4 * v + 1] = q4.y; hr[4 * v + 2] = q4.z; hr[4 * v + 3] = q4.w;
                 }
             };
-            float4 cn;
-            float hnx[DP];
-            if (sub2 < rows) load_row(sub2, cn, hnx);
-            for (int r = sub2; r < rows; r += nsub) {  // one row ahead
-                const float4 cv = cn;
-                float hr[DP];
-#pragma unroll
-                for (int d = 0; d < DP; ++d) hr[d] = hnx[d];
-                if (r + nsub < rows) load_row(r + nsub, cn, hnx);
+            // two rows in flight, processed alternately (no register-to-register copies between iterations)
+            auto accum = [&](const float4& cv, const float (&hr)[DP]) {
                 const float cs[4] = {cv.x, cv.y, cv.z, cv.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -414,6 +411,20 @@ __global__ void __launch_bounds__(TR * SPLIT) decode_sse_fast_kernel(
 #pragma unroll
                     for (int d = 0; d < D; ++d) gw[i][d] = fmaf(cs[i], hr[d], gw[i][d]);
                 }
+            };
+            float4 c0, c1;
+            float h0[DP], h1[DP];
+            int r = sub2;
+            if (r < rows) load_row(r, c0, h0);
+            while (r < rows) {
+                const int r1 = r + nsub;
+                if (r1 < rows) load_row(r1, c1, h1);
+                accum(c0, h0);
+                if (r1 >= rows) break;
+                const int r2 = r1 + nsub;
+                if (r2 < rows) load_row(r2, c0, h0);
+                accum(c1, h1);
+                r = r2;
             }
         }
 #pragma unroll
