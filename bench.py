@@ -414,6 +414,10 @@ def run_ours(args):
         if not args.no_extras:
             try:
                 extra["other_configs"] = dopri5_extras(lib, dev)
+                cpu = dopri5_cpu_baselines()
+                for k, v in cpu.items():
+                    if k in extra["other_configs"] and "error" not in extra["other_configs"][k]:
+                        extra["other_configs"][k]["cpu_baseline"] = v
             except Exception as e:  # secondary figures must never take the headline down
                 extra["other_configs"] = {"error": repr(e)}
 
@@ -514,6 +518,35 @@ def dopri5_extras(lib, dev):
                      "accepted_per_call": float(st[:, 0].float().mean()), "rejected_per_call": float(st[:, 1].float().mean()),
                      "latent_dim": Dd, "batch_per_odeint_call": batch}
         del h, tape, gh
+    return out
+
+
+def dopri5_cpu_baselines():
+    """The reference's CPU path (oracle port) for the two secondary shapes: ONE odeint call of the reference's batch size,
+    forward + read-out/masked SSE + autograd backward, trajectory-step attempts counted by the solver itself."""
+    from oracle import fields as OF
+    from oracle import odeint as OI
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    out = {}
+    for name, Dd, obs, batch in (("C3_dim12_dopri5_groups_of_10", 12, 80, 10), ("C1_dim6_dopri5_groups_of_50", 6, 20, 50)):
+        torch.manual_seed(666)
+        dec = OF.OracleDecoder(obs, Dd, method="dopri5")
+        g = torch.Generator().manual_seed(5)
+        y0 = torch.empty(batch, Dd).exponential_(100.0, generator=g)
+        a = torch.zeros(T, batch, 1)
+        a[torch.randint(0, T_MAX, (batch,), generator=g), torch.arange(batch), 0] = torch.rand(batch, generator=g) * 10 + 1e-3
+        x = torch.randn(T, batch, obs, generator=g)
+        mask = (torch.rand(T, batch, obs, generator=g) < 0.5).float()
+        tr = OI.SolveTrace()
+        z = y0.clone().requires_grad_(True)
+        t0 = time.perf_counter()
+        xh, _ = dec(z, a, trace=tr)
+        OF.masked_sse(x, xh, mask).backward()
+        el = time.perf_counter() - t0
+        att = (tr.accepted + tr.rejected) * batch
+        out[name] = {"value": att / el, "unit": UNIT, "seconds": el, "accepted": tr.accepted, "rejected": tr.rejected,
+                     "cores": torch.get_num_threads(), "kind": "port", "sample": "one odeint call of {} patients".format(batch)}
     return out
 
 

@@ -104,41 +104,44 @@ HODE_HD void fixed_fwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t i
     float* tp = a.tape_y != nullptr ? a.tape_y + idx * D : nullptr;
     const int64_t tape_stride = n_traj * D;
     float tj = (j < a.n_t) ? a.t_eval_f[j] : INFINITY;
-    for (int s = 0; s + 1 < a.n_grid; ++s) {
+    // one grid step ya -> yb, with the outputs it emits
+    auto one_step = [&](int s, float (&ya)[D], float (&yb)[D]) {
         const float t1 = a.grid[s + 1];
         const float dt = sub_rn(t1, t0);
         if (tp != nullptr) {
-            store_vec<D>(tp, y);
+            store_vec<D>(tp, ya);
             tp += tape_stride;
         }
-        fixed_step<F, METHOD>(sp, ds, t0, t1, dt, perturb, y, y1);
+        fixed_step<F, METHOD>(sp, ds, t0, t1, dt, perturb, ya, yb);
         if (t1 >= tj) {  // rare: an output time is reached (false for NaN times, like the reference's `while`)
             while (j < a.n_t && t1 >= a.t_eval_f[j]) {
                 const float te = a.t_eval_f[j];
                 float* o = a.h_out + ((int64_t)j * n_traj + idx) * D;
                 if (te == t0) {
-                    store_vec<D>(o, y);
+                    store_vec<D>(o, ya);
                 } else if (te == t1) {
-                    store_vec<D>(o, y1);
+                    store_vec<D>(o, yb);
                 } else {  // _linear_interp
                     const float slope = div_rn(sub_rn(te, t0), sub_rn(t1, t0));
                     float v[D];
 #pragma unroll
-                    for (int d = 0; d < D; ++d) v[d] = y[d] + slope * (y1[d] - y[d]);
+                    for (int d = 0; d < D; ++d) v[d] = ya[d] + slope * (yb[d] - ya[d]);
                     store_vec<D>(o, v);
                 }
                 ++j;
             }
             tj = (j < a.n_t) ? a.t_eval_f[j] : INFINITY;
         }
+        t0 = t1;
+    };
+    // (a two-steps-per-trip variant with y / y1 swapping roles was measured: no difference)
+    for (int s = 0; s + 1 < a.n_grid; ++s) {
+        one_step(s, y, y1);
 #pragma unroll
         for (int d = 0; d < D; ++d) y[d] = y1[d];
-        t0 = t1;
     }
 }
 
-// `valid` = false: a padding lane that only keeps a warp-cooperative accumulator (NeuralCoop) company: it follows the
-// control flow on a clamped trajectory with zero incoming gradients (so it contributes exactly 0) and writes nothing.
 template <class F, int METHOD, bool EG, class PS, class Dose, class ACC>
 HODE_HD void fixed_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t idx, ACC acc, bool valid = true) {
     constexpr int D = F::D;

@@ -341,7 +341,7 @@ class AdaptiveRK:
         ratio = _compute_error_ratio(y1_error, self.rtol, self.atol, y0, y1, self.norm)
         accept = bool(ratio <= 1)
         if self.trace is not None:
-            self.trace.attempts.append((float(t0), float(dt.detach()), float(ratio.detach()), accept))
+            self.trace.attempts.append((float(t0.detach() if isinstance(t0, torch.Tensor) else t0), float(dt.detach()), float(ratio.detach()), accept))
             if accept:
                 self.trace.accepted += 1
             else:
