@@ -29,8 +29,9 @@ struct CommNone {
     __device__ __forceinline__ void sum2(float&, float&) {}
 };
 struct CommCta {
-    float* red;  // 2 * 32 floats of shared memory
+    float* red;  // 2 buffers x (2 * 32) floats of shared memory, used alternately: ONE barrier per reduction
     int nwarps;
+    int phase = 0;
     __device__ __forceinline__ void sum2(float& a, float& b) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -39,11 +40,14 @@ struct CommCta {
         }
         if (nwarps > 1) {
             const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-            if (lane == 0) { red[2 * wid] = a; red[2 * wid + 1] = b; }
+            float* r = red + phase * 64;
+            if (lane == 0) { r[2 * wid] = a; r[2 * wid + 1] = b; }
             __syncthreads();
             float sa = 0.0f, sb = 0.0f;
-            for (int i = 0; i < nwarps; ++i) { sa += red[2 * i]; sb += red[2 * i + 1]; }
-            __syncthreads();
+            for (int i = 0; i < nwarps; ++i) { sa += r[2 * i]; sb += r[2 * i + 1]; }
+            // no second barrier: the next reduction writes the OTHER buffer, and the one after that is separated from these
+            // reads by the next reduction's barrier
+            phase ^= 1;
             a = sa; b = sb;
         }
     }
@@ -340,7 +344,7 @@ __global__ void __launch_bounds__(MAXT) dopri5_fwd_kernel(const SolveArgs a, int
         if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F>(a, cm, ParamConst(), ds, idx, valid, ctrl, leader, count))); }
         else { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F>(a, cm, (const float*)sp, ds, idx, valid, ctrl, leader, count))); }
     } else {
-        CommCta cm{red, (int)(blockDim.x >> 5)};
+        CommCta cm{red, (int)(blockDim.x >> 5), 0};
         if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F>(a, cm, ParamConst(), ds, idx, valid, ctrl, leader, count))); }
         else { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F>(a, cm, (const float*)sp, ds, idx, valid, ctrl, leader, count))); }
     }
@@ -544,7 +548,7 @@ int launch_dopri5_fwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t s
     const int tiles = a.per_traj ? (int)((a.batch + threads - 1) / threads) : 1;
     const int64_t nblk = a.n_groups * tiles;
 #define HODE_DF(PT, ND, MAXT, CP) \
-    dopri5_fwd_kernel<F, PT, ND, MAXT, CP><<<(unsigned)nblk, threads, ((CP ? 0 : F::SP) + 64) * sizeof(float), st>>>(a, tiles)
+    dopri5_fwd_kernel<F, PT, ND, MAXT, CP><<<(unsigned)nblk, threads, ((CP ? 0 : F::SP) + 128) * sizeof(float), st>>>(a, tiles)
 #define HODE_DF_CP(CP)                                                                                       \
     do {                                                                                                     \
         if (a.per_traj) { if (nd1) HODE_DF(true, 1, 128, CP); else HODE_DF(true, 0, 128, CP); }              \
