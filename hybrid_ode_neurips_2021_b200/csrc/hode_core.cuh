@@ -2,7 +2,7 @@
 // fixed-grid step functions, the dopri5 attempt, dense output, and their reverse sweeps.
 //
 // Everything here is written per trajectory ("one thread = one patient, state in registers") and is shared by the
-// sm_100a kernels in hode_kernels.cu.  It also compiles as plain C++ (HODE_HOSTSIM) for tests/hostsim, a TEST-ONLY
+// sm_100a kernels in hode_launch.cuh (instantiated in inst_*.cu).  It also compiles as plain C++ (HODE_HOSTSIM) for tests/hostsim, a TEST-ONLY
 // thread-emulation used to debug the derivations in a container that has no GPU; the product never loads that.
 //
 // Reference semantics followed (file:line into the reference; "tde" = torchdiffeq 0.2.2, restated in oracle/odeint.py):
