@@ -9,6 +9,7 @@
 namespace hode {
 template <class F> int launch_fixed_fwd(const hode_cfg&, const SolveArgs&, cudaStream_t);
 template <class F> int launch_fixed_bwd(const hode_cfg&, const SolveArgs&, cudaStream_t);
+template <class F> int launch_fixed_adj(const hode_cfg&, const SolveArgs&, cudaStream_t);
 template <class F> int launch_dopri5_fwd(const hode_cfg&, const SolveArgs&, cudaStream_t);
 template <class F> int launch_dopri5_bwd(const hode_cfg&, const SolveArgs&, cudaStream_t);
 int launch_dose_schedule(const float*, int64_t, int64_t, int32_t, int64_t, float*, int32_t*, int32_t*, cudaStream_t);
@@ -32,7 +33,7 @@ static int fail(int code, const char* fmt, const char* a = "", long long b = 0) 
     return code;
 }
 
-enum Op { OP_FIXED_FWD, OP_FIXED_BWD, OP_DOPRI5_FWD, OP_DOPRI5_BWD };
+enum Op { OP_FIXED_FWD, OP_FIXED_BWD, OP_DOPRI5_FWD, OP_DOPRI5_BWD, OP_FIXED_ADJ };
 
 template <class F>
 static int run(Op op, const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) {
@@ -41,6 +42,7 @@ static int run(Op op, const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) 
         case OP_FIXED_BWD: return launch_fixed_bwd<F>(cfg, a, st);
         case OP_DOPRI5_FWD: return launch_dopri5_fwd<F>(cfg, a, st);
         case OP_DOPRI5_BWD: return launch_dopri5_bwd<F>(cfg, a, st);
+        case OP_FIXED_ADJ: return launch_fixed_adj<F>(cfg, a, st);
     }
     return -1;
 }
@@ -186,6 +188,29 @@ int32_t hode_fixed_bwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, con
     a.grid = grid; a.n_grid = n_grid; a.t_eval_f = t_eval; a.n_t = n_t;
     a.grad_h = grad_h; a.tape_y = const_cast<float*>(tape); a.grad_y0 = grad_y0; a.grad_params = grad_params;
     return dispatch(OP_FIXED_BWD, *cfg, a, (cudaStream_t)stream);
+}
+
+int32_t hode_fixed_adjoint(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,
+                           const float* dose_t, int64_t dose_t_stride, const float* params,
+                           const int32_t* param_set_of_group, int32_t n_param_sets, const float* adj_grid,
+                           int32_t n_adj_grid, const int32_t* adj_count, int32_t n_t, const float* h,
+                           const float* grad_h, float* grad_y0, float* grad_params, void* stream) {
+    int rc = check_common(cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, n_t);
+    if (rc) return rc;
+    if (cfg->method == HODE_DOPRI5) return fail(HODE_ERR_UNSUPPORTED, "the continuous adjoint is built for the fixed-grid methods only (method %s%lld)", "", cfg->method);
+    if (n_adj_grid < 0 || n_param_sets < 1 || !grad_params || (n_t > 1 && (!adj_grid || !adj_count)))
+        return fail(HODE_ERR_ARG, "bad adj_grid / adj_count / grad_params");
+    const int64_t P = hode_param_count(cfg);
+    cudaError_t e = cudaMemsetAsync(grad_params, 0, sizeof(float) * (size_t)P * (size_t)n_param_sets, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(HODE_ERR_CUDA, "CUDA error: %s (%lld)", cudaGetErrorString(e), (long long)e);
+    if (n_groups * batch == 0) return HODE_OK;
+    if (!h || !grad_h || !grad_y0) return fail(HODE_ERR_ARG, "NULL h / grad_h / grad_y0");
+    SolveArgs a;
+    fill_common(a, cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, param_set_of_group);
+    a.n_param_sets = n_param_sets;
+    a.grid = adj_grid; a.n_grid = n_adj_grid; a.adj_cnt = adj_count; a.n_t = n_t;
+    a.h_out = const_cast<float*>(h); a.grad_h = grad_h; a.grad_y0 = grad_y0; a.grad_params = grad_params;
+    return dispatch(OP_FIXED_ADJ, *cfg, a, (cudaStream_t)stream);
 }
 
 int32_t hode_dopri5_fwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* y0,

@@ -40,6 +40,9 @@ struct SolveArgs {
     const float* grad_h;
     float* grad_y0;
     float* grad_params;
+    // continuous adjoint: `grid` holds the n_t - 1 reversed-time interval grids back to back (n_grid points in total),
+    // adj_cnt[iv] = number of grid points of interval iv (iv = 0 is the LAST output interval)
+    const int32_t* adj_cnt;
 };
 
 // ---- vector load/store of one trajectory's D contiguous floats ------------------------------------------------
@@ -193,6 +196,48 @@ HODE_HD void fixed_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t i
 #pragma unroll
         for (int d = 0; d < D; ++d) lam[d] = lam0[d] + yb0[d];
         t1 = t0;
+    }
+    if (!valid) return;
+    float g0[D];
+    load_vec<D>(a.grad_h + idx * D, g0);
+#pragma unroll
+    for (int d = 0; d < D; ++d) lam[d] += g0[d];
+    if (!F::params_ok(sp)) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) lam[d] = nanf("");
+    }
+    store_vec<D>(a.grad_y0 + idx * D, lam);
+}
+
+// ==============================================================================================================
+// continuous adjoint of a fixed-grid solve (tde adjoint.py OdeintAdjointMethod.backward): for i = n_t-1 .. 1 the
+// augmented state (y = h[i], a, g_theta) is integrated from t[i] back to t[i-1] on the solver grid of the NEGATED
+// interval; then a += grad_h[i-1] and y is reset to the forward solution h[i-1].  O(1) memory: no tape.
+// ==============================================================================================================
+template <class F, int METHOD, bool EG, class PS, class Dose, class ACC>
+HODE_HD void fixed_adj_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t idx, ACC acc, bool valid = true) {
+    constexpr int D = F::D;
+    const int64_t n_traj = a.n_groups * a.batch;
+    const bool perturb = a.perturb != 0;
+    float lam[D], y[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) lam[d] = 0.0f;
+    const float* gp = a.grid;
+    for (int iv = 0; iv + 1 < a.n_t; ++iv) {
+        const int i = a.n_t - 1 - iv;
+        float g[D];
+        load_vec<D>(a.grad_h + ((int64_t)i * n_traj + idx) * D, g);
+        load_vec<D>(a.h_out + ((int64_t)i * n_traj + idx) * D, y);
+#pragma unroll
+        for (int d = 0; d < D; ++d) lam[d] += valid ? g[d] : 0.0f;
+        const int cnt = a.adj_cnt[iv];
+        float s0 = gp[0];
+        for (int s = 0; s + 1 < cnt; ++s) {
+            const float s1 = gp[s + 1];
+            fixed_adjoint_step<F, METHOD, EG>(sp, ds, s0, s1, sub_rn(s1, s0), perturb, y, lam, acc);
+            s0 = s1;
+        }
+        gp += cnt;
     }
     if (!valid) return;
     float g0[D];

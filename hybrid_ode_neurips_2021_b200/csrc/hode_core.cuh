@@ -317,6 +317,7 @@ struct NeuralCoop {
     float w1[NJ][IN + 1];  // rows of dW1 (IN) and db1 (1) of the owned units
     float w2[NJ][D_];      // columns of dW2 of the owned units
     float b2[D_];          // this lane's own contribution to db2 (reduced over the warp at the end)
+    bool mute;             // true: the call only needs J^T l (zero-weight stage of the continuous adjoint)
 };
 
 template <int D_>
@@ -440,7 +441,7 @@ struct Neural {
 #pragma unroll
         for (int i = 0; i < IN; ++i) S_in[i * 32 + lane] = in[i];
 #pragma unroll
-        for (int d = 0; d < D_; ++d) { S_u[d * 32 + lane] = u[d]; cp->b2[d] += u[d]; gy[d] = 0.0f; }
+        for (int d = 0; d < D_; ++d) { S_u[d * 32 + lane] = u[d]; cp->b2[d] += cp->mute ? 0.0f : u[d]; gy[d] = 0.0f; }
 #pragma unroll
         for (int c = 0; c < NeuralCoop<D_>::NJ; ++c) {
             // producer phase: this lane's trajectory, hidden units 32 c .. 32 c + 31
@@ -465,6 +466,7 @@ struct Neural {
                 S_a[jj * 33 + lane] = a;
             }
             __syncwarp();
+            if (cp->mute) { __syncwarp(); continue; }  // warp-uniform
             // owner phase: unit j = 32 c + lane, all 32 trajectories of the warp
 #pragma unroll 4
             for (int tt = 0; tt < 32; ++tt) {
@@ -601,6 +603,103 @@ HODE_HD void fixed_step_vjp(PS sp, const Dose& ds, float t0, float t1, float dt,
         F::template vjp<EG>(sp, ta, ds, y0, k1, kb, g, acc);
 #pragma unroll
         for (int d = 0; d < D; ++d) lam0[d] += g[d];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// continuous adjoint (tde adjoint.py OdeintAdjointMethod.backward): the augmented system (y, a, g_theta) is integrated
+// BACKWARDS over every output interval with the same fixed-grid method.  tde reverses time by negation
+// (odeint.py _ReverseFunc): in s = -t the system is  dy/ds = -f(-s, y),  da/ds = +J^T a,  dg/ds = +(df/dtheta)^T a.
+// ------------------------------------------------------------------------------------------------------------
+// J^T l only (a stage whose quadrature weight is zero): the parameter part goes to a dead local array / a muted
+// cooperative accumulator
+template <class F, class PS, class Dose>
+HODE_HD void vjp_state_only(PS sp, float t, const Dose& ds, const float (&y)[F::D], const float* k,
+                            const float (&l)[F::D], float (&gy)[F::D], float* /*acc*/) {
+    float dead[F::P];
+#pragma unroll
+    for (int p = 0; p < F::P; ++p) dead[p] = 0.0f;
+    F::template vjp<false>(sp, t, ds, y, k, l, gy, (float*)dead);
+}
+#if HODE_DEVICE_BUILD && defined(__CUDA_ARCH__)
+template <class F, class PS, class Dose, int DD>
+HODE_D void vjp_state_only(PS sp, float t, const Dose& ds, const float (&y)[F::D], const float* k,
+                           const float (&l)[F::D], float (&gy)[F::D], NeuralCoop<DD>* cp) {
+    cp->mute = true;
+    F::template vjp<false>(sp, t, ds, y, k, l, gy, cp);
+    cp->mute = false;
+}
+#endif
+
+// One step s0 -> s1 (ds = s1 - s0 > 0) of the augmented system in negated time; y and a are updated in place and
+// acc += ds * sum_i b_i (df/dtheta(y_i))^T a_i.  The vjp is linear in its cotangent, so stage i is called with
+// l_i = (b_i ds) a_i: the accumulators then receive the quadrature-weighted term directly and the returned
+// g_i = (b_i ds) J_i^T a_i enters the next stage adjoints with dt-free constant ratios (a_ij / b_j).
+template <class F, int METHOD, bool EG, class PS, class Dose, class ACC>
+HODE_HD void fixed_adjoint_step(PS sp, const Dose& ds, float s0, float s1, float dt, bool perturb,
+                                float (&y)[F::D], float (&a)[F::D], ACC acc) {
+    constexpr int D = F::D;
+    const float ta = -(perturb ? t_next(s0) : s0);
+    float k1[D], l[D], g1[D];
+    F::eval(sp, ta, ds, y, k1);
+    if (METHOD == M_EULER) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) l[d] = dt * a[d];
+        F::template vjp<EG>(sp, ta, ds, y, k1, l, g1, acc);
+#pragma unroll
+        for (int d = 0; d < D; ++d) { y[d] = fmaf(-dt, k1[d], y[d]); a[d] += g1[d]; }
+    } else if (METHOD == M_MIDPOINT) {
+        const float half_dt = mul_rn(0.5f, dt);
+        const float tm = -add_rn(s0, half_dt);
+        float ym[D], am[D], k2[D], g2[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) l[d] = half_dt * a[d];
+        vjp_state_only<F>(sp, ta, ds, y, k1, l, g1, acc);  // b_1 = 0
+#pragma unroll
+        for (int d = 0; d < D; ++d) { ym[d] = fmaf(-half_dt, k1[d], y[d]); am[d] = a[d] + g1[d]; }
+        F::eval(sp, tm, ds, ym, k2);
+#pragma unroll
+        for (int d = 0; d < D; ++d) l[d] = dt * am[d];
+        F::template vjp<EG>(sp, tm, ds, ym, k2, l, g2, acc);
+#pragma unroll
+        for (int d = 0; d < D; ++d) { y[d] = fmaf(-dt, k2[d], y[d]); a[d] += g2[d]; }
+    } else {  // 3/8 rule: A = [[],[1/3],[-1/3,1],[1,-1,1]], b = [1/8,3/8,3/8,1/8]
+        const float tb = -add_rn(s0, mul_rn(dt, HODE_ONE_THIRD));
+        const float tc = -add_rn(s0, mul_rn(dt, HODE_TWO_THIRDS));
+        const float td = -(perturb ? t_prev(s1) : s1);
+        const float c13 = dt * HODE_ONE_THIRD, w1 = dt * 0.125f, w3 = dt * 0.375f;
+        constexpr float r83 = (float)(8.0 / 3.0);
+        float Y[D], k2[D], k3[D], g2[D], g3[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) l[d] = w1 * a[d];
+        F::template vjp<EG>(sp, ta, ds, y, k1, l, g1, acc);
+        // stage 2: y2 = y - ds/3 k1 ; a2 = a + ds/3 J1^T a = a + 8/3 g1
+#pragma unroll
+        for (int d = 0; d < D; ++d) { Y[d] = fmaf(-c13, k1[d], y[d]); l[d] = w3 * fmaf(r83, g1[d], a[d]); }
+        F::eval(sp, tb, ds, Y, k2);
+        F::template vjp<EG>(sp, tb, ds, Y, k2, l, g2, acc);
+        // stage 3: y3 = y - ds (k2 - k1/3) ; a3 = a + 8/3 (g2 - g1)
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            Y[d] = fmaf(-dt, k2[d], fmaf(c13, k1[d], y[d]));
+            l[d] = w3 * fmaf(r83, g2[d] - g1[d], a[d]);
+        }
+        F::eval(sp, tc, ds, Y, k3);
+        F::template vjp<EG>(sp, tc, ds, Y, k3, l, g3, acc);
+        // stage 4: y4 = y - ds (k1 - k2 + k3) ; a4 = a + 8 g1 - 8/3 g2 + 8/3 g3
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            Y[d] = fmaf(-dt, (k1[d] - k2[d]) + k3[d], y[d]);
+            l[d] = w1 * fmaf(8.0f, g1[d], fmaf(r83, g3[d] - g2[d], a[d]));
+        }
+        float k4[D], g4[D];
+        F::eval(sp, td, ds, Y, k4);
+        F::template vjp<EG>(sp, td, ds, Y, k4, l, g4, acc);
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            y[d] = fmaf(-w1, k1[d] + k4[d], fmaf(-w3, k2[d] + k3[d], y[d]));
+            a[d] += (g1[d] + g4[d]) + (g2[d] + g3[d]);
+        }
     }
 }
 

@@ -264,6 +264,7 @@ __device__ __forceinline__ void coop_init(NeuralCoop<D>& cp, float* stage_base) 
     }
 #pragma unroll
     for (int d = 0; d < D; ++d) cp.b2[d] = 0.0f;
+    cp.mute = false;
 }
 // owned rows -> shared accumulator (one atomic per parameter per warp) -> global
 template <int D>
@@ -318,6 +319,33 @@ __global__ void __launch_bounds__(128, HODE_BWD_MINBLOCKS) fixed_bwd_kernel(cons
             const int64_t idx = tl.group * a.batch + tl.b;
             if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (fixed_bwd_traj<F, METHOD, EG>(a, ParamConst(), ds, idx, (float*)acc))); }
             else { HODE_WITH_DOSE(ND, a, idx, (fixed_bwd_traj<F, METHOD, EG>(a, (const float*)sp, ds, idx, (float*)acc))); }
+        }
+        reduce_param_grads<F>(a, tl.group, acc, sred);
+    }
+}
+
+// continuous adjoint of a fixed-grid solve: same shape as the reverse sweep, no tape (fixed_adj_traj)
+template <class F, int METHOD, bool EG, int ND, bool CP>
+__global__ void __launch_bounds__(128, HODE_BWD_MINBLOCKS) fixed_adj_kernel(const SolveArgs a, int tiles_per_group) {
+    extern __shared__ float smem[];
+    float* sp = smem;
+    float* sred = smem + (CP ? 0 : F::SP);
+    const Tile tl = tile_of(a, tiles_per_group);
+    if constexpr (!CP) stage_params<F>(a, tl.group, sp);
+    if constexpr (CoopOf<F>::value) {
+        NeuralCoop<F::D> cp;
+        coop_init(cp, sred + F::P);
+        const bool valid = tl.b < a.batch;
+        const int64_t idx = tl.group * a.batch + (valid ? tl.b : a.batch - 1);
+        HODE_WITH_DOSE(ND, a, idx, (fixed_adj_traj<F, METHOD, EG>(a, (const float*)sp, ds, idx, &cp, valid)));
+        coop_flush(a, tl.group, cp, sred);
+    } else {
+        float acc[F::P];
+        zero_acc<F>(acc);
+        if (tl.b < a.batch) {
+            const int64_t idx = tl.group * a.batch + tl.b;
+            if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (fixed_adj_traj<F, METHOD, EG>(a, ParamConst(), ds, idx, (float*)acc))); }
+            else { HODE_WITH_DOSE(ND, a, idx, (fixed_adj_traj<F, METHOD, EG>(a, (const float*)sp, ds, idx, (float*)acc))); }
         }
         reduce_param_grads<F>(a, tl.group, acc, sred);
     }
@@ -518,6 +546,41 @@ int launch_fixed_bwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st
 #undef HODE_FB_CP
 #undef HODE_FB_M
 #undef HODE_FB
+    HODE_LAUNCH_CHECK();
+    return 0;
+}
+
+template <class F>
+int launch_fixed_adj(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st) {
+    const SolveArgs a = flatten(a_in);
+    const int threads = a.batch >= 128 ? 128 : round_up32(a.batch);
+    const int tiles = (int)((a.batch + threads - 1) / threads);
+    const int64_t nblk = a.n_groups * tiles;
+    const bool nd1 = cfg.n_dose == 1;
+    const bool eg = cfg.expert_grads != 0;
+#define HODE_FA(M, EG, ND, CP)                                                                                        \
+    do {                                                                                                           \
+        const size_t sh_ = ((CP ? 0 : F::SP) + F::P + coop_stage_floats<F>() * (size_t)(threads / 32)) * sizeof(float); \
+        if (sh_ > 48 * 1024)                                                                                       \
+            cudaFuncSetAttribute(fixed_adj_kernel<F, M, EG, ND, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_); \
+        fixed_adj_kernel<F, M, EG, ND, CP><<<(unsigned)nblk, threads, sh_, st>>>(a, tiles);                        \
+    } while (0)
+#define HODE_FA_M(M, CP)                                                           \
+    do {                                                                           \
+        if (eg) { if (nd1) HODE_FA(M, true, 1, CP); else HODE_FA(M, true, 0, CP); } \
+        else    { if (nd1) HODE_FA(M, false, 1, CP); else HODE_FA(M, false, 0, CP); } \
+    } while (0)
+#define HODE_FA_CP(CP)                                      \
+    switch (cfg.method) {                                   \
+        case HODE_EULER: HODE_FA_M(M_EULER, CP); break;     \
+        case HODE_MIDPOINT: HODE_FA_M(M_MIDPOINT, CP); break; \
+        case HODE_RK4_38: HODE_FA_M(M_RK4_38, CP); break;   \
+        default: return -1;                                 \
+    }
+    HODE_DISPATCH_CP(F, a, st, HODE_FA_CP);
+#undef HODE_FA_CP
+#undef HODE_FA_M
+#undef HODE_FA
     HODE_LAUNCH_CHECK();
     return 0;
 }

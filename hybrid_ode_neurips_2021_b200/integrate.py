@@ -2,7 +2,8 @@
 
 ``install_as_torchdiffeq()`` registers a module named ``torchdiffeq`` whose ``odeint`` is the fused solver, so that
 ``from torchdiffeq import odeint as dto`` (``/root/reference/model.py:10``) binds to it: the reference's own
-``RocheODE`` / ``NeuralODE`` instances are recognised by structure and integrated by the sm_100a kernels.
+``RocheODE`` / ``NeuralODE`` instances are recognised by structure and integrated by the sm_100a kernels
+(``odeint_adjoint``, the import the reference keeps commented out at ``model.py:9``, is provided as well).
 ``patch_model(module)`` additionally swaps the three hot-path classes of an imported reference ``model`` module for
 the drop-ins (vectorised ``set_action``).
 """
@@ -12,7 +13,7 @@ import sys
 import types
 
 from . import model as _model
-from .solver import odeint
+from .solver import odeint, odeint_adjoint
 
 
 def install_as_torchdiffeq(force: bool = False):
@@ -20,6 +21,7 @@ def install_as_torchdiffeq(force: bool = False):
         raise RuntimeError("a real torchdiffeq is already imported; pass force=True to shadow it")
     m = types.ModuleType("torchdiffeq")
     m.odeint = odeint
+    m.odeint_adjoint = odeint_adjoint  # the alternative import the reference keeps commented out (model.py:9)
     m.__hode_shim__ = True
     sys.modules["torchdiffeq"] = m
     return m

@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from . import ops
-from .solver import odeint
+from .solver import odeint, odeint_adjoint
 
 DTYPE = torch.float32
 
@@ -149,8 +149,9 @@ class NeuralODE(_DoseMixin, nn.Module):
 
 class RocheExpertDecoder(nn.Module):
     def __init__(self, obs_dim, latent_dim, action_dim, t_max, step_size, roche=True, ablate=False, method="dopri5",
-                 ode_step_size=None, device=None, dtype=DTYPE, solver_options=None):
+                 ode_step_size=None, device=None, dtype=DTYPE, solver_options=None, adjoint=False):
         super().__init__()
+        self.adjoint = bool(adjoint)  # True: backward by the continuous adjoint (model.py:9's alternative import)
         self.time_dim = int(t_max / step_size)
         self.obs_dim = obs_dim
         self.latent_dim = latent_dim
@@ -184,8 +185,9 @@ class RocheExpertDecoder(nn.Module):
     def solve(self, init, a):
         """Latent trajectories ``h [T, B, D]`` only (no read-out)."""
         self.ode.set_action(a)
-        return odeint(self.ode, init, self.t, rtol=self.options["rtol"], atol=self.options["atol"],
-                      method=self.options["method"], options=self.solver_options)
+        solve = odeint_adjoint if self.adjoint else odeint
+        return solve(self.ode, init, self.t, rtol=self.options["rtol"], atol=self.options["atol"],
+                     method=self.options["method"], options=self.solver_options)
 
     def forward(self, init, a):
         h = self.solve(init, a)

@@ -102,6 +102,22 @@ def fixed_bwd(lib, pb: Problem, grid, t_eval, grad_h, tape):
     return gy0, gp
 
 
+def fixed_adjoint(lib, pb: Problem, adj_grid, adj_count, h, grad_h):
+    """Continuous adjoint of a fixed-grid solve (``hode_fixed_adjoint``): no tape, needs the forward solution ``h``."""
+    D = pb.cfg.latent_dim
+    grad_h, h = _f32c(grad_h), _f32c(h)
+    dev = grad_h.device
+    n_t = h.shape[0]
+    gy0 = torch.empty(pb.n_traj, D, dtype=torch.float32, device=dev)
+    gp = torch.empty_like(pb.params)
+    rc = lib.hode_fixed_adjoint(C.byref(pb.cfg), pb.n_groups, pb.batch, _ptr(pb.dose_amt), _ptr(pb.dose_t),
+                                pb.dose_t.stride(0), _ptr(pb.params), _ptr(pb.pset), pb.params.shape[0],
+                                _ptr(adj_grid), adj_grid.numel(), _ptr(adj_count), n_t, _ptr(h), _ptr(grad_h),
+                                _ptr(gy0), _ptr(gp), _stream(grad_h))
+    lib.check(rc, "hode_fixed_adjoint")
+    return gy0, gp
+
+
 def dopri5_fwd(lib, pb: Problem, y0, t_eval64, tape_capacity):
     """Returns ``h, stats [n_ctrl, 4] i32, (tape_t, tape_y) or None``."""
     D = pb.cfg.latent_dim

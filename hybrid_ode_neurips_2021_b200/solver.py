@@ -26,7 +26,7 @@ import torch
 from . import _lib as L
 from . import ops
 
-__all__ = ["odeint", "odeint_ensemble", "SolveInfo", "last_solve_info", "fixed_grid_points"]
+__all__ = ["odeint", "odeint_adjoint", "odeint_ensemble", "SolveInfo", "last_solve_info", "fixed_grid_points"]
 
 EXPERT_NAMES = (
     "HillCure", "HillPatho", "ec50_patho", "emax_patho", "k_dexa", "k_discure_immunereact", "k_discure_immunity",
@@ -175,6 +175,38 @@ def _times_for(t: torch.Tensor, step_size, device, fixed: bool):
     return out
 
 
+def adjoint_grid_points(t: torch.Tensor, step_size):
+    """Solver grids of the continuous adjoint: torchdiffeq integrates interval ``i`` from ``t[i]`` back to ``t[i-1]`` by
+    negating time (``odeint.py`` ``_check_inputs``), so the grid is the fixed grid of ``[-t[i], -t[i-1]]``.  Returns the
+    grids back to back (last interval first) and the number of points of each."""
+    parts, counts = [], []
+    for i in range(t.numel() - 1, 0, -1):
+        g = fixed_grid_points(-(t[i - 1:i + 1].flip(0)), step_size)
+        assert g[0] == -t[i] and g[-1] == -t[i - 1]
+        parts.append(g)
+        counts.append(g.numel())
+    grid = torch.cat(parts) if parts else torch.zeros(0, dtype=t.dtype)
+    return grid, torch.tensor(counts, dtype=torch.int32)
+
+
+_adj_time_cache = {}
+
+
+def _adjoint_times_for(t: torch.Tensor, step_size, device):
+    key = (id(t), step_size, str(device))
+    hit = _adj_time_cache.get(key)
+    if hit is not None:
+        ref, version, out = hit
+        if ref() is t and version == t._version:
+            return out
+    grid, counts = adjoint_grid_points(t.detach().cpu(), step_size)
+    out = (grid.to(device).contiguous(), counts.to(device).contiguous())
+    if len(_adj_time_cache) > 64:
+        _adj_time_cache.clear()
+    _adj_time_cache[key] = (weakref.ref(t), t._version, out)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------------
 class _FixedSolve(torch.autograd.Function):
     @staticmethod
@@ -191,6 +223,27 @@ class _FixedSolve(torch.autograd.Function):
             raise RuntimeError("backward through a solve that was run without a tape")
         gy0, gp = ops.fixed_bwd(L.get_lib(), ctx.pb, ctx.grid, ctx.t_eval, grad_h, ctx.tape)
         return gy0, gp.reshape(-1), None, None, None, None
+
+
+class _FixedAdjointSolve(torch.autograd.Function):
+    """torchdiffeq's ``OdeintAdjointMethod`` for the fixed-grid methods: forward without a tape, backward = ONE launch
+    integrating the augmented system backwards over every output interval (``hode_fixed_adjoint``)."""
+
+    @staticmethod
+    def forward(ctx, y0, packed, pb, grid, t_eval, adj_pb, adj_grid, adj_count):
+        lib = L.get_lib()
+        pb.params = packed.detach().reshape(pb.params_shape).contiguous()
+        adj_pb.params = pb.params
+        h, _ = ops.fixed_fwd(lib, pb, y0.detach(), grid, t_eval, False)
+        ctx.adj_pb, ctx.adj_grid, ctx.adj_count = adj_pb, adj_grid, adj_count
+        ctx.save_for_backward(h)
+        return h
+
+    @staticmethod
+    def backward(ctx, grad_h):
+        (h,) = ctx.saved_tensors
+        gy0, gp = ops.fixed_adjoint(L.get_lib(), ctx.adj_pb, ctx.adj_grid, ctx.adj_count, h, grad_h)
+        return gy0, gp.reshape(-1), None, None, None, None, None, None
 
 
 class _Dopri5Solve(torch.autograd.Function):
@@ -260,6 +313,39 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
     return _odeint_impl([func], y0, t, rtol, atol, method, options, event_fn)
 
 
+def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None, adjoint_rtol=None,
+                   adjoint_atol=None, adjoint_method=None, adjoint_options=None, adjoint_params=None):
+    """torchdiffeq's ``odeint_adjoint`` (the import the reference keeps commented out at ``model.py:9``): same forward
+    result as :func:`odeint`, but the backward pass is the CONTINUOUS adjoint -- no tape, O(1) memory in the number of
+    solver steps.  Built for the fixed-grid methods (``euler`` / ``midpoint`` / ``rk4``); the adjoint solve uses the
+    forward method and options unless ``adjoint_method`` / ``adjoint_options`` say otherwise (torchdiffeq's defaults).
+    ``adjoint_params`` must be the vector field's own parameters (the default): gradients are produced for the packed
+    parameter vector as a whole.  Gradients differ from :func:`odeint`'s discrete backprop by the method's
+    discretisation error, exactly as they do in torchdiffeq."""
+    if adjoint_params is not None:
+        own = {id(p) for p in func.parameters()}
+        if {id(p) for p in adjoint_params} - own:
+            raise NotImplementedError("adjoint_params must be parameters of the vector field")
+    method = "dopri5" if method is None else method
+    adjoint_method = method if adjoint_method is None else adjoint_method
+    for m in (method, adjoint_method):
+        if m not in L.METHODS:
+            raise ValueError('Invalid method "{}". Must be one of {}'.format(m, "{" + ", ".join(L.METHODS) + "}"))
+    if method == "dopri5" or adjoint_method == "dopri5":
+        raise NotImplementedError(
+            "odeint_adjoint has fused kernels for the fixed-grid methods only; dopri5 trains through odeint's discrete "
+            "backprop over the tape of accepted steps")
+    if adjoint_options is None:  # torchdiffeq: the forward options (minus a user norm) drive the adjoint solve too
+        adjoint_options = {k: v for k, v in options.items() if k != "norm"} if options is not None else {}
+    else:
+        adjoint_options = dict(adjoint_options)
+        unused = {k: v for k, v in adjoint_options.items() if k not in (_FIXED_KEYS | _OUR_KEYS)}
+        if unused:
+            warnings.warn("{}: Unexpected arguments {}".format(_NAMES[adjoint_method], unused))
+    adjoint = {"method": adjoint_method, "options": adjoint_options}
+    return _odeint_impl([func], y0, t, rtol, atol, method, options, event_fn, adjoint=adjoint)
+
+
 def odeint_ensemble(funcs, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None):
     """``M`` independent ``odeint`` calls -- one per ensemble member / restart, each with its OWN parameters -- in ONE
     kernel launch (BASELINE config 4; the reference runs restarts and methods one after the other:
@@ -303,7 +389,7 @@ def _odeint_real(func, kind, y0, t, method, options):
     return h
 
 
-def _odeint_impl(funcs, y0, t, rtol, atol, method, options, event_fn):
+def _odeint_impl(funcs, y0, t, rtol, atol, method, options, event_fn, adjoint=None):
     global _last_info
     func = funcs[0]
     M = len(funcs)
@@ -315,6 +401,8 @@ def _odeint_impl(funcs, y0, t, rtol, atol, method, options, event_fn):
     if rk is not None:
         if M != 1:
             raise NotImplementedError("odeint_ensemble is built for the simulation fields only")
+        if adjoint is not None:
+            raise NotImplementedError("odeint_adjoint is built for the simulation fields (RocheODE / NeuralODE) only")
         return _odeint_real(func, rk, y0, t, method, options)
     kind = field_kind(func)
     for f in funcs[1:]:
@@ -399,7 +487,17 @@ def _odeint_impl(funcs, y0, t, rtol, atol, method, options, event_fn):
         if options.get("interp", "linear") != "linear":
             raise ValueError("Unknown interpolation method {}".format(options.get("interp")))
         t_dev, grid = _times_for(t, options.get("step_size"), y0.device, True)
-        h = _FixedSolve.apply(y0, packed, pb, grid, t_dev, need_grad)
+        if adjoint is not None and need_grad:
+            aopt = adjoint["options"]
+            if aopt.get("grid_constructor") is not None or aopt.get("interp", "linear") != "linear":
+                raise NotImplementedError("adjoint_options: only step_size / perturb are built")
+            acfg = L.HodeCfg.from_buffer_copy(cfg)
+            acfg.method, acfg.perturb = L.METHODS[adjoint["method"]], int(bool(aopt.get("perturb", False)))
+            adj_pb = ops.Problem(acfg, n_groups, batch, dose_amt, dose_t, None, pset)
+            adj_grid, adj_count = _adjoint_times_for(t, aopt.get("step_size"), y0.device)
+            h = _FixedAdjointSolve.apply(y0, packed, pb, grid, t_dev, adj_pb, adj_grid, adj_count)
+        else:
+            h = _FixedSolve.apply(y0, packed, pb, grid, t_dev, need_grad)
         _last_info = SolveInfo(None, (grid.numel() - 1) * B)
         return h
 

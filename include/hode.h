@@ -141,6 +141,21 @@ int32_t hode_fixed_bwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, con
                        const float* t_eval, int32_t n_t, const float* grad_h, const float* tape, float* grad_y0,
                        float* grad_params, void* stream);
 
+/* continuous adjoint (torchdiffeq odeint_adjoint -> OdeintAdjointMethod.backward; the import the reference keeps
+ * commented out at model.py:9 and north_star's "or the adjoint"): O(1)-memory backward of a fixed-grid solve, no tape.
+ * For i = n_t-1 .. 1 the augmented state (y = h[i], a, g_params) is integrated from t[i] back to t[i-1] with the SAME
+ * method on torchdiffeq's grid of the negated interval [-t[i], -t[i-1]]; then a += grad_h[i-1], y = h[i-1].
+ * h [n_t, n_traj, D]: the forward solution (hode_fixed_fwd's h_out, tape = NULL).
+ * adj_grid: the n_t-1 interval grids (negated time, ascending, float32, host-built like `grid` above) back to back,
+ * last output interval first; adj_count[iv]: points of interval iv; n_adj_grid = sum(adj_count).
+ * grad_y0 / grad_params as in hode_fixed_bwd.  These are the CONTINUOUS-adjoint gradients: they agree with
+ * hode_fixed_bwd's discrete gradients to the order of the method, not to rounding. */
+int32_t hode_fixed_adjoint(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,
+                           const float* dose_t, int64_t dose_t_stride, const float* params,
+                           const int32_t* param_set_of_group, int32_t n_param_sets, const float* adj_grid,
+                           int32_t n_adj_grid, const int32_t* adj_count, int32_t n_t, const float* h,
+                           const float* grad_h, float* grad_y0, float* grad_params, void* stream);
+
 /* ---- dopri5: torchdiffeq Dopri5Solver (RKAdaptiveStepsizeODESolver.integrate), model.py:1116 ------------------
  * t_eval is float64 (torchdiffeq casts `t` to float64).  controller BATCH: one controller per group
  * (batch <= hode_dopri5_max_batch()); TRAJ: one per trajectory.  n_ctrl = n_groups (BATCH) or n_traj (TRAJ).

@@ -17,6 +17,7 @@ here from the package's documented behaviour (module names below are the package
 * ``_impl/fixed_grid.py``  -> ``euler`` / ``midpoint`` / ``rk4`` (3/8 rule) step functions
 * ``_impl/solvers.py``     -> :class:`FixedGrid` (grid construction, linear interpolation to output times)
 * ``_impl/interp.py``      -> :func:`_quartic_fit`, :func:`_quartic_eval`
+* ``_impl/adjoint.py``     -> :func:`odeint_adjoint` (``OdeintAdjointMethod``; fixed-grid methods only)
 
 PARITY UNPINNED BY THE REFERENCE: the reference repository has no tests and no golden vectors at the solver boundary
 (SURVEY.md section 4).  The restatement is pinned instead by (i) closed-form ODEs and order-of-convergence checks,
@@ -39,7 +40,7 @@ from typing import Callable, List, Optional
 
 import torch
 
-__all__ = ["odeint", "SolveTrace", "DOPRI5", "SOLVERS"]
+__all__ = ["odeint", "odeint_adjoint", "SolveTrace", "DOPRI5", "SOLVERS"]
 
 NEXT, PREV, NONE = 1, -1, 0
 
@@ -522,3 +523,94 @@ def odeint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, even
     else:
         solver = FixedGrid(wrapped, y0, method, trace=trace, **options)
     return solver.integrate(t)
+
+
+# --------------------------------------------------------------------------------------------------------------
+# adjoint.py
+# --------------------------------------------------------------------------------------------------------------
+class _AdjointMethod(torch.autograd.Function):
+    """``OdeintAdjointMethod``: forward = plain ``odeint`` under ``no_grad``; backward integrates the augmented system
+    ``(vjp_t, y, adj_y, *adj_params)`` backwards over every output interval with ``odeint`` itself (decreasing ``t`` ->
+    the time-negation path of :func:`odeint`), resetting ``y`` to the stored forward solution at every output time."""
+
+    @staticmethod
+    def forward(ctx, func, y0, t, rtol, atol, method, options, adj_rtol, adj_atol, adj_method, adj_options, n_params,
+                *adjoint_params):
+        ctx.func, ctx.cfg = func, (adj_rtol, adj_atol, adj_method, adj_options)
+        with torch.no_grad():
+            y = odeint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options)
+        ctx.save_for_backward(t, y, *adjoint_params)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        func = ctx.func
+        adj_rtol, adj_atol, adj_method, adj_options = ctx.cfg
+        t, y, *adjoint_params = ctx.saved_tensors
+        adjoint_params = tuple(adjoint_params)
+        with torch.no_grad():
+            # the package keeps a tuple state and flattens it (``_TupleFunc``) before the solver sees it
+            state = [torch.zeros((), dtype=y.dtype, device=y.device), y[-1], grad_y[-1]]
+            state.extend(torch.zeros_like(p) for p in adjoint_params)
+            shapes = [s.shape for s in state]
+            sizes = [s.numel() for s in state]
+
+            def flatten(parts):
+                return torch.cat([p.reshape(-1) for p in parts])
+
+            def unflatten(flat):
+                out, off = [], 0
+                for shp, n in zip(shapes, sizes):
+                    out.append(flat[off:off + n].view(shp))
+                    off += n
+                return out
+
+            def augmented_dynamics(tt, flat):
+                parts = unflatten(flat)
+                yy, adj_y = parts[1], parts[2]
+                with torch.enable_grad():
+                    t_ = tt.detach()
+                    yy = yy.detach().requires_grad_(True)
+                    func_eval = func(t_, yy)
+                    vjps = torch.autograd.grad(func_eval, (yy,) + adjoint_params, -adj_y, allow_unused=True,
+                                               retain_graph=True)
+                vjp_y = torch.zeros_like(yy) if vjps[0] is None else vjps[0]
+                vjp_params = [torch.zeros_like(p) if v is None else v for p, v in zip(adjoint_params, vjps[1:])]
+                # vjp_t: t carries no gradient request (t_requires_grad is False at every reference call site)
+                return flatten([torch.zeros_like(t_).to(yy.dtype), func_eval.detach(), vjp_y] + vjp_params)
+
+            for i in range(len(t) - 1, 0, -1):
+                sol = odeint(augmented_dynamics, flatten(state), t[i - 1:i + 1].flip(0), rtol=adj_rtol, atol=adj_atol,
+                             method=adj_method, options=adj_options)
+                state = unflatten(sol[1])
+                state[1] = y[i - 1]
+                state[2] = state[2] + grad_y[i - 1]
+            adj_y, adj_params = state[2], state[3:]
+        return (None, adj_y, None, None, None, None, None, None, None, None, None, None, *adj_params)
+
+
+def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None, adjoint_rtol=None,
+                   adjoint_atol=None, adjoint_method=None, adjoint_options=None, adjoint_params=None):
+    """``torchdiffeq.odeint_adjoint`` (the import the reference keeps commented out at ``model.py:9``), restated for the
+    fixed-grid methods: the adaptive adjoint's mixed norm over the tuple state is not restated.  Defaults follow the
+    package: the adjoint solve uses the forward method / tolerances / options unless overridden; ``adjoint_params``
+    defaults to ``func.parameters()``, filtered to those that require grad."""
+    if event_fn is not None:
+        raise NotImplementedError("event handling is not used by the reference and not restated")
+    if adjoint_params is None and not isinstance(func, torch.nn.Module):
+        raise ValueError("func must be an instance of nn.Module to specify the adjoint parameters; alternatively they "
+                         "can be specified explicitly via the `adjoint_params` argument.")
+    method = "dopri5" if method is None else method
+    adjoint_rtol = rtol if adjoint_rtol is None else adjoint_rtol
+    adjoint_atol = atol if adjoint_atol is None else adjoint_atol
+    adjoint_method = method if adjoint_method is None else adjoint_method
+    if adjoint_method == "dopri5":
+        raise NotImplementedError("the adaptive adjoint (mixed norm over the augmented tuple state) is not restated")
+    if adjoint_options is None:
+        adjoint_options = {k: v for k, v in options.items() if k != "norm"} if options is not None else {}
+    else:
+        adjoint_options = dict(adjoint_options)
+    adjoint_params = tuple(func.parameters()) if adjoint_params is None else tuple(adjoint_params)
+    adjoint_params = tuple(p for p in adjoint_params if p.requires_grad)
+    return _AdjointMethod.apply(func, y0, t, rtol, atol, method, options, adjoint_rtol, adjoint_atol, adjoint_method,
+                                adjoint_options, len(adjoint_params), *adjoint_params)

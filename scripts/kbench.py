@@ -56,5 +56,11 @@ t_fwd, (h, tape) = ev(lambda: ops.fixed_fwd(lib, pb, y0, grid, tt, True))
 t_dec, (loss, gh, gw, gb) = ev(lambda: ops.decode_sse(lib, h, lin.weight.detach(), lin.bias.detach(), x, mask, B))
 t_bwd, _ = ev(lambda: ops.fixed_bwd(lib, pb, grid, tt, gh, tape))
 n = grid.numel() - 1
+adj_grid, adj_count = solver.adjoint_grid_points(tt.cpu(), args.h)
+adj_grid, adj_count = adj_grid.to(dev), adj_count.to(dev)
+t_adj, (gy0_a, gp_a) = ev(lambda: ops.fixed_adjoint(lib, pb, adj_grid, adj_count, h, gh))
+gy0_d, gp_d = ops.fixed_bwd(lib, pb, grid, tt, gh, tape)
+gap = ((gy0_a - gy0_d).abs().max() / gy0_d.abs().max()).item()
 print(json.dumps({"B": B, "D": D, "method": args.method, "steps": n, "fwd_notape_ms": t_fwd0, "fwd_ms": t_fwd, "dec_ms": t_dec,
-                  "bwd_ms": t_bwd, "fwd_Gsteps": B * n / t_fwd / 1e6, "bwd_Gsteps": B * n / t_bwd / 1e6}))
+                  "bwd_ms": t_bwd, "adjoint_ms": t_adj, "adjoint_vs_discrete_dy0": gap, "fwd_Gsteps": B * n / t_fwd / 1e6,
+                  "bwd_Gsteps": B * n / t_bwd / 1e6, "adjoint_Gsteps": B * n / t_adj / 1e6}))

@@ -78,6 +78,20 @@ void fixed_bwd(const SolveArgs& a, bool eg) {
         for (int i = 0; i < F::P; ++i) a.grad_params[(int64_t)set * F::P + i] += acc[i];
     }
 }
+template <class F, int M>
+void fixed_adj(const SolveArgs& a, bool eg) {
+    for (int64_t g = 0; g < a.n_groups; ++g) {
+        auto sp = stage<F>(a, g);
+        std::vector<float> acc(F::P, 0.f);
+        for (int64_t b = 0; b < a.batch; ++b) {
+            const int64_t idx = g * a.batch + b;
+            if (eg) fixed_adj_traj<F, M, true>(a, sp.data(), dose(a, idx), idx, acc.data());
+            else fixed_adj_traj<F, M, false>(a, sp.data(), dose(a, idx), idx, acc.data());
+        }
+        const int set = a.pset ? a.pset[g] : 0;
+        for (int i = 0; i < F::P; ++i) a.grad_params[(int64_t)set * F::P + i] += acc[i];
+    }
+}
 template <class F>
 void dopri5_fwd(const SolveArgs& a) {
     for (int64_t g = 0; g < a.n_groups; ++g) {
@@ -119,7 +133,7 @@ void dopri5_bwd(const SolveArgs& a, bool eg) {
     }
 }
 
-enum Op { FF, FB, DF, DB };
+enum Op { FF, FB, DF, DB, FA };
 template <class F>
 int run(Op op, const hode_cfg& cfg, const SolveArgs& a) {
     const bool eg = cfg.expert_grads != 0;
@@ -133,6 +147,11 @@ int run(Op op, const hode_cfg& cfg, const SolveArgs& a) {
             if (cfg.method == HODE_EULER) fixed_bwd<F, M_EULER>(a, eg);
             else if (cfg.method == HODE_MIDPOINT) fixed_bwd<F, M_MIDPOINT>(a, eg);
             else fixed_bwd<F, M_RK4_38>(a, eg);
+            return 0;
+        case FA:
+            if (cfg.method == HODE_EULER) fixed_adj<F, M_EULER>(a, eg);
+            else if (cfg.method == HODE_MIDPOINT) fixed_adj<F, M_MIDPOINT>(a, eg);
+            else fixed_adj<F, M_RK4_38>(a, eg);
             return 0;
         case DF: dopri5_fwd<F>(a); return 0;
         case DB: dopri5_bwd<F>(a, eg); return 0;
@@ -199,6 +218,16 @@ int32_t hode_fixed_bwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, con
     a.grad_h = grad_h; a.tape_y = const_cast<float*>(tape); a.grad_y0 = grad_y0; a.grad_params = grad_params;
     memset(grad_params, 0, sizeof(float) * pcount(cfg) * n_param_sets);
     return dispatch(FB, *cfg, a);
+}
+int32_t hode_fixed_adjoint(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,
+                           const float* dose_t, int64_t dose_t_stride, const float* params, const int32_t* pset,
+                           int32_t n_param_sets, const float* adj_grid, int32_t n_adj_grid, const int32_t* adj_count,
+                           int32_t n_t, const float* h, const float* grad_h, float* grad_y0, float* grad_params, void*) {
+    SolveArgs a; fill(a, cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, pset);
+    a.n_param_sets = n_param_sets; a.grid = adj_grid; a.n_grid = n_adj_grid; a.adj_cnt = adj_count; a.n_t = n_t;
+    a.h_out = const_cast<float*>(h); a.grad_h = grad_h; a.grad_y0 = grad_y0; a.grad_params = grad_params;
+    memset(grad_params, 0, sizeof(float) * pcount(cfg) * n_param_sets);
+    return dispatch(FA, *cfg, a);
 }
 int32_t hode_dopri5_fwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* y0, const float* dose_amt,
                         const float* dose_t, int64_t dose_t_stride, const float* params, const int32_t* pset,

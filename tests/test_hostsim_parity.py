@@ -256,3 +256,100 @@ def test_parameter_sets_per_group(lib):
                      torch.cat([pack_roche(o) for o in os_]).contiguous(), torch.arange(G, dtype=torch.int32))
     h, _ = ops.fixed_fwd(lib, pb, y0, grid, t, False)
     assert relerr(h, torch.cat(refs, dim=1)) < 2e-6
+
+
+# ---- continuous adjoint (torchdiffeq odeint_adjoint) ----------------------------------------------
+ADJ_SYMS = SYMS + ["hode_fixed_adjoint"]
+
+
+@pytest.fixture(scope="module")
+def lib_adj():
+    subprocess.run(["make", "-C", HS_DIR], check=True, capture_output=True)
+    return L.HodeLib(HS, required=ADJ_SYMS)
+
+
+@pytest.mark.parametrize("D", [4, 6, 8, 12])
+@pytest.mark.parametrize("method,opts", [("rk4", {"step_size": 0.0625}), ("rk4", {"step_size": 0.3, "perturb": True}),
+                                         ("rk4", {}), ("midpoint", {"step_size": 0.125, "perturb": True}),
+                                         ("euler", {"step_size": 0.0625})])
+def test_fixed_grid_continuous_adjoint(lib_adj, D, method, opts):
+    """hode_fixed_adjoint against the restated ``odeint_adjoint`` (same augmented system, same reversed-time grids):
+    rounding-level agreement.  Tolerance: 2e-5 norm-wise (the adjoint solve is ~2x as long as the forward one)."""
+    from hybrid_ode_neurips_2021_b200.solver import adjoint_grid_points
+
+    lib = lib_adj
+    B = 6
+    o = oracle_roche(D, 1, True)
+    y0, a, _, _ = make_cohort(B, D, seed=D)
+    o.set_action(a)
+    # no step_size: the solver grid is t itself (one step per output interval; h = 1 diverges, so a finer t)
+    t = torch.arange(0, 15.0) if "step_size" in opts else torch.arange(0, 41.0) * 0.125
+    n_t = t.numel()
+    W = torch.randn(n_t, B, D, generator=torch.Generator().manual_seed(0))
+    z = y0.clone().requires_grad_(True)
+    ref = OI.odeint_adjoint(o, z, t, method=method, options=opts)
+    (ref * W).sum().backward()
+    grid = OI.fixed_grid_points(t, opts.get("step_size")).contiguous()
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.METHODS[method], perturb=opts.get("perturb", False), n_dose=1, hill2=True)
+    pb = problem(o, cfg, B)
+    h, _ = ops.fixed_fwd(lib, pb, y0, grid, t, False)
+    assert relerr(h, ref) < 2e-6
+    adj_grid, adj_count = adjoint_grid_points(t, opts.get("step_size"))
+    assert adj_count.numel() == n_t - 1 and int(adj_count.sum()) == adj_grid.numel()
+    gy0, gp = ops.fixed_adjoint(lib, pb, adj_grid.contiguous(), adj_count, h, W)
+    assert relerr(gy0, z.grad) < 2e-5
+    gref = grads_vec(o, False)
+    ok = ~torch.isnan(gref)
+    assert torch.equal(torch.isnan(gp[0]), ~ok)
+    assert relerr(gp[0][ok], gref[ok]) < 5e-5
+
+
+def test_continuous_adjoint_converges_to_the_discrete_gradients(lib_adj):
+    """adjoint (optimise-then-discretise) vs reverse sweep (discretise-then-optimise): the gap shrinks with the step."""
+    from hybrid_ode_neurips_2021_b200.solver import adjoint_grid_points
+
+    lib = lib_adj
+    D, B = 8, 5
+    o = oracle_roche(D, 1, True)
+    y0, a, _, _ = make_cohort(B, D, seed=D)
+    o.set_action(a)
+    t = torch.arange(0, 15.0)
+    W = torch.randn(15, B, D, generator=torch.Generator().manual_seed(3))
+    gaps = []
+    for hstep in (0.25, 0.0625):
+        grid = OI.fixed_grid_points(t, hstep).contiguous()
+        cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.RK4_38, n_dose=1, hill2=True)
+        pb = problem(o, cfg, B)
+        h, tape = ops.fixed_fwd(lib, pb, y0, grid, t, True)
+        gy0_d, gp_d = ops.fixed_bwd(lib, pb, grid, t, W, tape)
+        adj_grid, adj_count = adjoint_grid_points(t, hstep)
+        gy0_a, gp_a = ops.fixed_adjoint(lib, pb, adj_grid.contiguous(), adj_count, h, W)
+        gaps.append((relerr(gy0_a, gy0_d), relerr(gp_a[0][13:], gp_d[0][13:])))
+    assert gaps[1][0] < gaps[0][0] and gaps[1][1] < gaps[0][1]
+    assert gaps[1][0] < 2e-3 and gaps[1][1] < 2e-3
+
+
+@pytest.mark.parametrize("method,opts", [("rk4", {"step_size": 0.25}), ("midpoint", {"step_size": 0.125})])
+def test_neural_field_continuous_adjoint(lib_adj, method, opts):
+    from hybrid_ode_neurips_2021_b200.solver import adjoint_grid_points
+
+    lib = lib_adj
+    D, B = 6, 4
+    torch.manual_seed(4)
+    o = OF.OracleNeuralODE(D)
+    y0, a, _, _ = make_cohort(B, D, seed=11)
+    o.set_action(a)
+    t = torch.arange(0, 15.0)
+    W = torch.randn(15, B, D, generator=torch.Generator().manual_seed(2))
+    z = y0.clone().requires_grad_(True)
+    ref = OI.odeint_adjoint(o, z, t, method=method, options=opts,
+                            adjoint_params=[p for n, p in o.named_parameters() if n != "kel"])
+    (ref * W).sum().backward()
+    grid = OI.fixed_grid_points(t, opts.get("step_size")).contiguous()
+    cfg = ops.make_cfg(L.FIELD_NEURAL, D, L.METHODS[method], n_dose=1)
+    pb = problem(o, cfg, B, neural=True)
+    h, _ = ops.fixed_fwd(lib, pb, y0, grid, t, False)
+    adj_grid, adj_count = adjoint_grid_points(t, opts.get("step_size"))
+    gy0, gp = ops.fixed_adjoint(lib, pb, adj_grid.contiguous(), adj_count, h, W)
+    assert relerr(gy0, z.grad) < 2e-5
+    assert relerr(gp[0], grads_vec(o, True)) < 5e-5
