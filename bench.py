@@ -375,6 +375,11 @@ def run_ours(args):
         t_fwd, (h, tape) = ev_time(lambda: ops.fixed_fwd(lib, pb, y0, grid, tt, True))
         t_dec, (loss, gh, gw, gb) = ev_time(lambda: ops.decode_sse(lib, h, lin.weight.detach(), lin.bias.detach(), x, mask, B))
         t_bwd, _ = ev_time(lambda: ops.fixed_bwd(lib, pb, grid, tt, gh, tape))
+        # tape-free alternative: forward without a tape + the continuous adjoint (odeint_adjoint)
+        adj_grid, adj_count = solver.adjoint_grid_points(tt.cpu(), STEP)
+        adj_grid, adj_count = adj_grid.to(dev), adj_count.to(dev)
+        t_fwd_nt, _ = ev_time(lambda: ops.fixed_fwd(lib, pb, y0, grid, tt, False))
+        t_adj, _ = ev_time(lambda: ops.fixed_adjoint(lib, pb, adj_grid, adj_count, h, gh))
         # FP32 FMA peak, measured in this run (MEASURED_PEAKS.json carries HBM and bf16 only)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         out = torch.zeros(1, device=dev)
@@ -402,7 +407,13 @@ def run_ours(args):
         }
         dec_bytes = T * B * (2 * OBS + 2 * D) * 4
         extra = {
-            "kernels_ms": {"fixed_fwd(+tape)": t_fwd, "decode_sse": t_dec, "fixed_bwd": t_bwd},
+            "kernels_ms": {"fixed_fwd(+tape)": t_fwd, "decode_sse": t_dec, "fixed_bwd": t_bwd,
+                           "fixed_fwd(no tape)": t_fwd_nt, "fixed_adjoint(no tape)": t_adj},
+            "adjoint_path": {"note": "odeint_adjoint: forward without a tape + continuous adjoint sweep (4 evals + 4 VJPs "
+                                     "per step, same flop count as the reverse sweep); saves the {:.2f} GB tape".format(
+                                         B * N_STEPS * D * 4 / 1e9),
+                             "value": B * N_STEPS / ((t_fwd_nt + t_dec + t_adj) * 1e-3), "unit": "trajectory-steps/s",
+                             "roofline_frac": bwd_flops / (t_adj * 1e-3) / 1e12 / fma_peak},
             "roofline_fwd": {"bound": "fp32_fma", "achieved": fwd_flops / (t_fwd * 1e-3) / 1e12, "peak": fma_peak,
                              "unit": "TFLOP/s", "frac": fwd_flops / (t_fwd * 1e-3) / 1e12 / fma_peak,
                              "algorithmic_flops_per_traj_step": FLOPS_FWD_STEP},

@@ -10,6 +10,7 @@ from .model import RocheODE, NeuralODE, RocheExpertDecoder, RochConfig  # noqa: 
 from .real import RocheODEReal, NeuralODEReal, NeuralODEReal2nd, DecoderReal  # noqa: F401
 from .loss import masked_sse, decode_sse_loss  # noqa: F401
 from .integrate import install_as_torchdiffeq, patch_model  # noqa: F401
+from .datagen import DataGeneratorRoche  # noqa: F401
 from .evaluation import crps_ensemble, mc_solve, decode_crps, evaluate_chunk  # noqa: F401
 
 __version__ = "0.1.0"
