@@ -80,6 +80,78 @@ static constexpr float kTanhPre = 2.8853900817779268f, kTanhPreInv = 0.346573590
 static constexpr float kTanhPre = 1.0f, kTanhPreInv = 1.0f;
 #endif
 
+// ------------------------------------------------------------------------------------------------------------
+// Packed FP32 pairs.  sm_100a has FFMA2 / FADD2 / FMUL2 (fma.rn.f32x2 ...): two IEEE operations per lane in ONE issue slot,
+// with a scalar-broadcast operand form (R.F32) and a uniform-register pair form (UR.F32x2) for constant-bank weights.
+// The solver kernels are issue-bound, so the per-dimension loops are written on pairs
+// (v[2i], v[2i+1]).  Every packed operation is the same correctly rounded fma / add / mul per element as the scalar code
+// it replaces (the host build below IS that scalar code): results do not change, only the number of issue slots.
+// ------------------------------------------------------------------------------------------------------------
+#ifndef HODE_PACKED
+#define HODE_PACKED 1
+#endif
+#if HODE_PACKED && HODE_DEVICE_BUILD && defined(__CUDA_ARCH__)
+// o = s * b + c   (s broadcast)
+HODE_D void fma2s(float s, float b0, float b1, float c0, float c1, float& o0, float& o1) {
+    const float2 r = __ffma2_rn(make_float2(s, s), make_float2(b0, b1), make_float2(c0, c1));
+    o0 = r.x; o1 = r.y;
+}
+HODE_D void fma2(float a0, float a1, float b0, float b1, float c0, float c1, float& o0, float& o1) {
+    const float2 r = __ffma2_rn(make_float2(a0, a1), make_float2(b0, b1), make_float2(c0, c1));
+    o0 = r.x; o1 = r.y;
+}
+HODE_D void add2(float a0, float a1, float b0, float b1, float& o0, float& o1) {
+    const float2 r = __fadd2_rn(make_float2(a0, a1), make_float2(b0, b1));
+    o0 = r.x; o1 = r.y;
+}
+HODE_D void mul2(float a0, float a1, float b0, float b1, float& o0, float& o1) {
+    const float2 r = __fmul2_rn(make_float2(a0, a1), make_float2(b0, b1));
+    o0 = r.x; o1 = r.y;
+}
+#else
+HODE_HD void fma2s(float s, float b0, float b1, float c0, float c1, float& o0, float& o1) { o0 = fmaf(s, b0, c0); o1 = fmaf(s, b1, c1); }
+HODE_HD void fma2(float a0, float a1, float b0, float b1, float c0, float c1, float& o0, float& o1) { o0 = fmaf(a0, b0, c0); o1 = fmaf(a1, b1, c1); }
+HODE_HD void add2(float a0, float a1, float b0, float b1, float& o0, float& o1) { o0 = add_rn(a0, b0); o1 = add_rn(a1, b1); }
+HODE_HD void mul2(float a0, float a1, float b0, float b1, float& o0, float& o1) { o0 = mul_rn(a0, b0); o1 = mul_rn(a1, b1); }
+#endif
+
+// element-wise vector helpers over the D state dimensions (D is even for every compiled field)
+template <int D>  // o = s * a + c
+HODE_HD void v_axpy(float (&o)[D], float s, const float (&a)[D], const float (&c)[D]) {
+#pragma unroll
+    for (int i = 0; i + 1 < D; i += 2) fma2s(s, a[i], a[i + 1], c[i], c[i + 1], o[i], o[i + 1]);
+    if (D & 1) o[D - 1] = fmaf(s, a[D - 1], c[D - 1]);
+}
+template <int D>  // o = a + b
+HODE_HD void v_add(float (&o)[D], const float (&a)[D], const float (&b)[D]) {
+#pragma unroll
+    for (int i = 0; i + 1 < D; i += 2) add2(a[i], a[i + 1], b[i], b[i + 1], o[i], o[i + 1]);
+    if (D & 1) o[D - 1] = add_rn(a[D - 1], b[D - 1]);
+}
+template <int D>  // o = a - b
+HODE_HD void v_sub(float (&o)[D], const float (&a)[D], const float (&b)[D]) {
+#pragma unroll
+    for (int i = 0; i + 1 < D; i += 2) add2(a[i], a[i + 1], -b[i], -b[i + 1], o[i], o[i + 1]);
+    if (D & 1) o[D - 1] = sub_rn(a[D - 1], b[D - 1]);
+}
+template <int D>  // o = s * a
+HODE_HD void v_scale(float (&o)[D], float s, const float (&a)[D]) {
+#pragma unroll
+    for (int i = 0; i + 1 < D; i += 2) mul2(s, s, a[i], a[i + 1], o[i], o[i + 1]);
+    if (D & 1) o[D - 1] = mul_rn(s, a[D - 1]);
+}
+
+// two tanh_pre at once: the add and the final fma are packed
+#if HODE_FAST_MATH && HODE_DEVICE_BUILD && defined(__CUDA_ARCH__)
+HODE_D void tanh_pre2(float x0, float x1, float& o0, float& o1) {
+    float q0, q1;
+    add2(ex2_approx(x0), ex2_approx(x1), 1.0f, 1.0f, q0, q1);
+    fma2s(-2.0f, rcp_approx(q0), rcp_approx(q1), 1.0f, 1.0f, o0, o1);
+}
+#else
+HODE_HD void tanh_pre2(float x0, float x1, float& o0, float& o1) { o0 = tanh_pre(x0); o1 = tanh_pre(x1); }
+#endif
+
 // x ** p with a float32 tensor exponent (model.py:529, 537-538).  p == 2 (RochConfig default) is a multiply.
 HODE_HD float pow_hill(float x, float p) { return (p == 2.0f) ? x * x : powf(x, p); }
 // d/dx x**p = p * x**(p-1)   (autograd pow_backward_self; zero where p == 0)
@@ -168,10 +240,16 @@ struct Roche {
     static constexpr int OFF_B = R_NSCALAR + ML * D_;
     static constexpr int OFF_TH = OFF_B + ML;                 // theta_1, theta_2 (ABLATE only)
     static constexpr int P = OFF_TH + (ABLATE_ ? 2 : 0);      // packed parameter count
-    // staged copy appends derived constants
+    // staged copy appends derived constants, then 8-byte aligned copies of the ml_net weights for the packed (FFMA2)
+    // loops: WR = W row-major [ML][D] (pairs over d: the VJP's J^T product), BT = b [ML], WT = W interleaved by unit
+    // pairs [ML/2][D][2] (pairs over units: the forward mat-vec keeps each unit's accumulation order)
     static constexpr int OFF_ECP = P;       // ec50 ** HillPatho
     static constexpr int OFF_KL2 = P + 1;   // kel * log2(e)
-    static constexpr int SP = P + 2;
+    static constexpr int OFF_WR = ((P + 2 + 3) / 4) * 4;
+    static constexpr int OFF_BT = OFF_WR + ML * D_;
+    static constexpr int OFF_WT = OFF_BT + ML;
+    static constexpr int SP = OFF_WT + ML * D_;
+    static_assert(ML % 2 == 0 && D_ % 2 == 0, "packed loops assume even D and ML");
     static constexpr bool kAccInRegs = true;  // per-thread gradient accumulators fit in registers
     static constexpr bool kConstBank = true;  // staged parameters may be read from the constant bank (hode_launch.cuh)
 
@@ -180,6 +258,13 @@ struct Roche {
     // argument of the ex2 inside tanh_pre().
     HODE_HD static void stage(const float* __restrict__ src, float* sp, int tid, int nthr) {
         for (int i = tid; i < P; i += nthr) sp[i] = (i >= OFF_W && i < OFF_TH) ? src[i] * kTanhPre : src[i];
+        for (int i = tid; i < ML * D_; i += nthr) {
+            const int j = i / D_, d = i % D_;
+            const float w = src[OFF_W + i] * kTanhPre;
+            sp[OFF_WR + i] = w;
+            sp[OFF_WT + ((j >> 1) * D_ + d) * 2 + (j & 1)] = w;
+        }
+        for (int j = tid; j < ML; j += nthr) sp[OFF_BT + j] = src[OFF_B + j] * kTanhPre;
     }
     HODE_HD static void prepare(float* sp) {
         sp[OFF_ECP] = pow_hill(sp[R_EC50], sp[R_HP]);
@@ -210,12 +295,14 @@ struct Roche {
             dy[2] = react * sp[R_KIM];
             dy[3] = sp[R_KEL] * (roche_dose(ds, t, sp[R_KEL], sp[OFF_KL2]) - dose2);
         }
+        // ml_net: two hidden units per packed FMA (weights interleaved by unit pair), same accumulation order per unit
 #pragma unroll
-        for (int j = 0; j < ML; ++j) {
-            float a = sp[OFF_B + j];
+        for (int j = 0; j < ML; j += 2) {
+            float a0 = sp[OFF_BT + j], a1 = sp[OFF_BT + j + 1];
 #pragma unroll
-            for (int d = 0; d < D_; ++d) a = fmaf(sp[OFF_W + j * D_ + d], y[d], a);
-            dy[4 + j] = tanh_pre(a);
+            for (int d = 0; d < D_; ++d)
+                fma2s(y[d], sp[OFF_WT + ((j >> 1) * D_ + d) * 2], sp[OFF_WT + ((j >> 1) * D_ + d) * 2 + 1], a0, a1, a0, a1);
+            tanh_pre2(a0, a1, dy[4 + j], dy[4 + j + 1]);
         }
     }
 
@@ -273,24 +360,35 @@ struct Roche {
             }
         }
 #pragma unroll
-        for (int j = 0; j < ML; ++j) {
-            float s;
+        for (int j = 0; j < ML; j += 2) {
+            float s0, s1;
             if (k != nullptr) {
-                s = k[4 + j];
+                s0 = k[4 + j]; s1 = k[4 + j + 1];
             } else {
-                float a = sp[OFF_B + j];
+                float a0 = sp[OFF_BT + j], a1 = sp[OFF_BT + j + 1];
 #pragma unroll
-                for (int d = 0; d < D_; ++d) a = fmaf(sp[OFF_W + j * D_ + d], y[d], a);
-                s = tanh_pre(a);
+                for (int d = 0; d < D_; ++d)
+                    fma2s(y[d], sp[OFF_WT + ((j >> 1) * D_ + d) * 2], sp[OFF_WT + ((j >> 1) * D_ + d) * 2 + 1], a0, a1, a0, a1);
+                tanh_pre2(a0, a1, s0, s1);
             }
-            const float u = l[4 + j] * fmaf(-s, s, 1.0f);
-            const float uw = u * kTanhPreInv;  // the staged weights carry the factor kTanhPre
+            // u = l (1 - s^2);  uw = u / kTanhPre (the staged weights carry the factor kTanhPre)
+            float q0, q1, u0, u1, uw0, uw1;
+            fma2(-s0, -s1, s0, s1, 1.0f, 1.0f, q0, q1);
+            mul2(l[4 + j], l[4 + j + 1], q0, q1, u0, u1);
+            mul2(u0, u1, kTanhPreInv, kTanhPreInv, uw0, uw1);
 #pragma unroll
-            for (int d = 0; d < D_; ++d) {
-                gy[d] = fmaf(sp[OFF_W + j * D_ + d], uw, gy[d]);
-                acc[OFF_W + j * D_ + d] = fmaf(u, y[d], acc[OFF_W + j * D_ + d]);
+            for (int d = 0; d < D_; d += 2) {
+                fma2s(uw0, sp[OFF_WR + j * D_ + d], sp[OFF_WR + j * D_ + d + 1], gy[d], gy[d + 1], gy[d], gy[d + 1]);
+                fma2s(u0, y[d], y[d + 1], acc[OFF_W + j * D_ + d], acc[OFF_W + j * D_ + d + 1],
+                      acc[OFF_W + j * D_ + d], acc[OFF_W + j * D_ + d + 1]);
             }
-            acc[OFF_B + j] += u;
+#pragma unroll
+            for (int d = 0; d < D_; d += 2) {
+                fma2s(uw1, sp[OFF_WR + (j + 1) * D_ + d], sp[OFF_WR + (j + 1) * D_ + d + 1], gy[d], gy[d + 1], gy[d], gy[d + 1]);
+                fma2s(u1, y[d], y[d + 1], acc[OFF_W + (j + 1) * D_ + d], acc[OFF_W + (j + 1) * D_ + d + 1],
+                      acc[OFF_W + (j + 1) * D_ + d], acc[OFF_W + (j + 1) * D_ + d + 1]);
+            }
+            add2(acc[OFF_B + j], acc[OFF_B + j + 1], u0, u1, acc[OFF_B + j], acc[OFF_B + j + 1]);
         }
     }
 };
@@ -510,18 +608,20 @@ HODE_HD void fixed_step(PS sp, const Dose& ds, float t0, float t1, float dt, boo
         for (int d = 0; d < D; ++d) y1[d] = y0[d] + dt * k2[d];
     } else {  // 3/8 rule (tde rk4_alt_step_func), written with fused multiply-adds
         const float c13 = dt * HODE_ONE_THIRD, w1 = dt * 0.125f, w3 = dt * 0.375f;
-        float yi[D], k2[D], k3[D], k4[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) yi[d] = fmaf(c13, k1[d], y0[d]);
+        float yi[D], k2[D], k3[D], k4[D], tmp[D];
+        v_axpy<D>(yi, c13, k1, y0);
         F::eval(sp, add_rn(t0, mul_rn(dt, HODE_ONE_THIRD)), ds, yi, k2);
-#pragma unroll
-        for (int d = 0; d < D; ++d) yi[d] = fmaf(dt, k2[d], fmaf(-c13, k1[d], y0[d]));
+        v_axpy<D>(tmp, -c13, k1, y0);
+        v_axpy<D>(yi, dt, k2, tmp);
         F::eval(sp, add_rn(t0, mul_rn(dt, HODE_TWO_THIRDS)), ds, yi, k3);
-#pragma unroll
-        for (int d = 0; d < D; ++d) yi[d] = fmaf(dt, (k1[d] - k2[d]) + k3[d], y0[d]);
+        v_sub<D>(tmp, k1, k2);
+        v_add<D>(tmp, tmp, k3);
+        v_axpy<D>(yi, dt, tmp, y0);
         F::eval(sp, perturb ? t_prev(t1) : t1, ds, yi, k4);
-#pragma unroll
-        for (int d = 0; d < D; ++d) y1[d] = fmaf(w1, k1[d] + k4[d], fmaf(w3, k2[d] + k3[d], y0[d]));
+        v_add<D>(tmp, k2, k3);
+        v_axpy<D>(tmp, w3, tmp, y0);
+        v_add<D>(yi, k1, k4);
+        v_axpy<D>(y1, w1, yi, tmp);
     }
 }
 
@@ -563,46 +663,40 @@ HODE_HD void fixed_step_vjp(PS sp, const Dose& ds, float t0, float t1, float dt,
         const float tc = add_rn(t0, mul_rn(dt, HODE_TWO_THIRDS));
         const float td = perturb ? t_prev(t1) : t1;
         const float c13 = dt * HODE_ONE_THIRD, w1 = dt * 0.125f, w3 = dt * 0.375f;
-        float k1[D], k2[D], k3[D], Y[D], g4[D], g3[D];
+        float k1[D], k2[D], k3[D], Y[D], g4[D], g3[D], tmp[D];
         F::eval(sp, ta, ds, y0, k1);
-#pragma unroll
-        for (int d = 0; d < D; ++d) Y[d] = fmaf(c13, k1[d], y0[d]);
+        v_axpy<D>(Y, c13, k1, y0);
         F::eval(sp, tb, ds, Y, k2);
-#pragma unroll
-        for (int d = 0; d < D; ++d) Y[d] = fmaf(dt, k2[d], fmaf(-c13, k1[d], y0[d]));
+        v_axpy<D>(tmp, -c13, k1, y0);
+        v_axpy<D>(Y, dt, k2, tmp);
         F::eval(sp, tc, ds, Y, k3);
         // stage 4: kb4 = b4 dt lam1
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            Y[d] = fmaf(dt, (k1[d] - k2[d]) + k3[d], y0[d]);
-            kb[d] = w1 * lam1[d];
-        }
+        v_sub<D>(tmp, k1, k2);
+        v_add<D>(tmp, tmp, k3);
+        v_axpy<D>(Y, dt, tmp, y0);
+        v_scale<D>(kb, w1, lam1);
         F::template vjp<EG>(sp, td, ds, Y, nullptr, kb, g4, acc);
         // stage 3: kb3 = b3 dt lam1 + a43 dt g4
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            lam0[d] = lam1[d] + g4[d];
-            Y[d] = fmaf(dt, k2[d], fmaf(-c13, k1[d], y0[d]));
-            kb[d] = fmaf(dt, g4[d], w3 * lam1[d]);
-        }
+        v_add<D>(lam0, lam1, g4);
+        v_axpy<D>(tmp, -c13, k1, y0);
+        v_axpy<D>(Y, dt, k2, tmp);
+        v_scale<D>(tmp, w3, lam1);
+        v_axpy<D>(kb, dt, g4, tmp);
         F::template vjp<EG>(sp, tc, ds, Y, k3, kb, g3, acc);
         // stage 2: kb2 = b2 dt lam1 + a42 dt g4 + a32 dt g3 = 3/8 dt lam1 + dt (g3 - g4)
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            lam0[d] += g3[d];
-            Y[d] = fmaf(c13, k1[d], y0[d]);
-            kb[d] = fmaf(dt, g3[d] - g4[d], w3 * lam1[d]);
-        }
+        v_add<D>(lam0, lam0, g3);
+        v_axpy<D>(Y, c13, k1, y0);
+        v_sub<D>(kb, g3, g4);
+        v_axpy<D>(kb, dt, kb, tmp);  // tmp still holds w3 lam1
         F::template vjp<EG>(sp, tb, ds, Y, k2, kb, g, acc);
         // stage 1: kb1 = b1 dt lam1 + a41 dt g4 + a31 dt g3 + a21 dt g2 = 1/8 dt lam1 + dt g4 + dt/3 (g2 - g3)
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            lam0[d] += g[d];
-            kb[d] = fmaf(c13, g[d] - g3[d], fmaf(dt, g4[d], w1 * lam1[d]));
-        }
+        v_add<D>(lam0, lam0, g);
+        v_scale<D>(tmp, w1, lam1);
+        v_axpy<D>(tmp, dt, g4, tmp);
+        v_sub<D>(kb, g, g3);
+        v_axpy<D>(kb, c13, kb, tmp);
         F::template vjp<EG>(sp, ta, ds, y0, k1, kb, g, acc);
-#pragma unroll
-        for (int d = 0; d < D; ++d) lam0[d] += g[d];
+        v_add<D>(lam0, lam0, g);
     }
 }
 
@@ -669,37 +763,43 @@ HODE_HD void fixed_adjoint_step(PS sp, const Dose& ds, float s0, float s1, float
         const float td = -(perturb ? t_prev(s1) : s1);
         const float c13 = dt * HODE_ONE_THIRD, w1 = dt * 0.125f, w3 = dt * 0.375f;
         constexpr float r83 = (float)(8.0 / 3.0);
-        float Y[D], k2[D], k3[D], g2[D], g3[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) l[d] = w1 * a[d];
+        // running sums keep the live set small (D = 12 carries 117 gradient accumulators next to the state):
+        //   ys = y - ds sum_i b_i k_i,  as = a + sum_i g_i,  ks = k1 - k2 (+ k3),  ga = a + 8 g1 - 8/3 g2
+        float Y[D], ys[D], as[D], ks[D], ga[D], kk[D], g[D];
+        v_scale<D>(l, w1, a);
         F::template vjp<EG>(sp, ta, ds, y, k1, l, g1, acc);
+        v_axpy<D>(ys, -w1, k1, y);
+        v_add<D>(as, a, g1);
         // stage 2: y2 = y - ds/3 k1 ; a2 = a + ds/3 J1^T a = a + 8/3 g1
-#pragma unroll
-        for (int d = 0; d < D; ++d) { Y[d] = fmaf(-c13, k1[d], y[d]); l[d] = w3 * fmaf(r83, g1[d], a[d]); }
-        F::eval(sp, tb, ds, Y, k2);
-        F::template vjp<EG>(sp, tb, ds, Y, k2, l, g2, acc);
+        v_axpy<D>(Y, -c13, k1, y);
+        v_axpy<D>(ga, r83, g1, a);
+        v_scale<D>(l, w3, ga);
+        F::eval(sp, tb, ds, Y, kk);
+        F::template vjp<EG>(sp, tb, ds, Y, kk, l, g, acc);
+        v_axpy<D>(ys, -w3, kk, ys);
+        v_add<D>(as, as, g);
         // stage 3: y3 = y - ds (k2 - k1/3) ; a3 = a + 8/3 (g2 - g1)
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            Y[d] = fmaf(-dt, k2[d], fmaf(c13, k1[d], y[d]));
-            l[d] = w3 * fmaf(r83, g2[d] - g1[d], a[d]);
-        }
-        F::eval(sp, tc, ds, Y, k3);
-        F::template vjp<EG>(sp, tc, ds, Y, k3, l, g3, acc);
+        v_axpy<D>(Y, c13, k1, y);
+        v_axpy<D>(Y, -dt, kk, Y);
+        v_sub<D>(ks, k1, kk);
+        v_sub<D>(ga, g, g1);
+        v_axpy<D>(ga, r83, ga, a);
+        v_scale<D>(l, w3, ga);
+        v_axpy<D>(ga, 8.0f, g1, a);    // ga = a + 8 g1 - 8/3 g2
+        v_axpy<D>(ga, -r83, g, ga);
+        F::eval(sp, tc, ds, Y, kk);
+        F::template vjp<EG>(sp, tc, ds, Y, kk, l, g, acc);
+        v_axpy<D>(ys, -w3, kk, ys);
+        v_add<D>(as, as, g);
         // stage 4: y4 = y - ds (k1 - k2 + k3) ; a4 = a + 8 g1 - 8/3 g2 + 8/3 g3
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            Y[d] = fmaf(-dt, (k1[d] - k2[d]) + k3[d], y[d]);
-            l[d] = w1 * fmaf(8.0f, g1[d], fmaf(r83, g3[d] - g2[d], a[d]));
-        }
-        float k4[D], g4[D];
-        F::eval(sp, td, ds, Y, k4);
-        F::template vjp<EG>(sp, td, ds, Y, k4, l, g4, acc);
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-            y[d] = fmaf(-w1, k1[d] + k4[d], fmaf(-w3, k2[d] + k3[d], y[d]));
-            a[d] += (g1[d] + g4[d]) + (g2[d] + g3[d]);
-        }
+        v_add<D>(ks, ks, kk);
+        v_axpy<D>(Y, -dt, ks, y);
+        v_axpy<D>(ga, r83, g, ga);
+        v_scale<D>(l, w1, ga);
+        F::eval(sp, td, ds, Y, kk);
+        F::template vjp<EG>(sp, td, ds, Y, kk, l, g, acc);
+        v_axpy<D>(y, -w1, kk, ys);
+        v_add<D>(a, as, g);
     }
 }
 

@@ -59,9 +59,10 @@ struct CommCta {
 // them as c[bank][imm] operands of FFMA/FMUL: no shared-memory loads and, above all, no registers (36-117 floats that
 // ptxas otherwise keeps live across the whole solve).  Launches with several parameter sets stage into shared memory.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kConstParamMax = 128;  // >= Roche<12>::SP
-static __constant__ float c_params[kConstParamMax];
-static __device__ float g_param_stage[kConstParamMax];
+constexpr int kConstParamMax = 384;  // >= Roche<12, *, true>::SP
+static __constant__ __align__(16) float c_params[kConstParamMax];
+static __device__ __align__(16) float g_param_stage[kConstParamMax];
+static_assert(Roche<12, true, true>::SP <= kConstParamMax, "constant-bank parameter array too small");
 
 struct ParamConst {
     __device__ __forceinline__ float operator[](int i) const { return c_params[i]; }

@@ -103,3 +103,41 @@ def test_fixed_grid_points_equal_the_oracle():
     for t, h in ((torch.arange(0, 15.0), 0.0625), (torch.arange(0, 15.0), 0.3), (torch.tensor([1.0, 2.5, 7.0]), 0.05),
                  (torch.arange(0, 15.0), None)):
         assert torch.equal(solver.fixed_grid_points(t, h), OI.fixed_grid_points(t, h))
+
+
+def test_adjoint_surface_and_reversed_time_grids():
+    """odeint_adjoint: torchdiffeq's signature, fixed-grid methods only, no CPU fallback; the adjoint's per-interval grids
+    are torchdiffeq's fixed grid of the negated interval (what the oracle's reverse-time odeint constructs)."""
+    m = H.RocheODE(6, 1, 14, 1, device="cpu")
+    a = torch.zeros(15, 2, 1)
+    a[3, :, 0] = 1.0
+    m.set_action(a)
+    t = torch.arange(0, 15.0)
+    with pytest.raises(NotImplementedError, match="fixed-grid"):
+        H.odeint_adjoint(m, torch.zeros(2, 6), t)  # default method dopri5
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        H.odeint_adjoint(m, torch.zeros(2, 6), t, method="rk4", options={"step_size": 0.25})
+    with pytest.raises(ValueError, match="Invalid method"):
+        H.odeint_adjoint(m, torch.zeros(2, 6), t, method="rk45")
+    with pytest.raises(NotImplementedError, match="adjoint_params"):
+        H.odeint_adjoint(m, torch.zeros(2, 6), t, method="rk4", adjoint_params=(torch.nn.Parameter(torch.zeros(1)),))
+    for tt, h in ((t, 0.0625), (t, 0.3), (torch.tensor([1.0, 2.5, 7.0]), 0.05), (t, None)):
+        grid, counts = solver.adjoint_grid_points(tt, h)
+        assert counts.dtype == torch.int32 and counts.numel() == tt.numel() - 1 and int(counts.sum()) == grid.numel()
+        off = 0
+        for iv, i in enumerate(range(tt.numel() - 1, 0, -1)):
+            seg = grid[off:off + int(counts[iv])]
+            assert torch.equal(seg, OI.fixed_grid_points(-(tt[i - 1:i + 1].flip(0)), h))
+            assert seg[0] == -tt[i] and seg[-1] == -tt[i - 1] and bool((seg[1:] > seg[:-1]).all())
+            off += int(counts[iv])
+    import sys, types
+    saved = sys.modules.get("torchdiffeq")
+    try:
+        sys.modules.pop("torchdiffeq", None)
+        shim = H.install_as_torchdiffeq()
+        assert shim.odeint is H.odeint and shim.odeint_adjoint is H.odeint_adjoint
+    finally:
+        if saved is not None:
+            sys.modules["torchdiffeq"] = saved
+        else:
+            sys.modules.pop("torchdiffeq", None)
