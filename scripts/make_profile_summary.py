@@ -41,11 +41,16 @@ with open(os.path.join(dst, label + "_launches.txt"), "w") as f:
         f.write("{:>7} {:>12.1f} {:>12.1f} {:>6.1f}%  {}\n".format(c, t, t / c, 100 * t / tot, k[:140]))
 
 # ---- per-kernel full captures ----------------------------------------------------------------------------------------
-for name in sorted(os.listdir(src)):
-    if not name.endswith(".ncu-rep"):
+names = sorted(os.listdir(src))
+for name in names:
+    if name.endswith(".summary.txt"):  # summarised on the GPU box (scripts/profile.sh)
+        out = open(os.path.join(src, name)).read()
+        name = name[:-12] + ".ncu-rep"
+    elif name.endswith(".ncu-rep") and name[:-8] + ".summary.txt" not in names:
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), os.path.join(src, name)],
+                             capture_output=True, text=True).stdout
+    else:
         continue
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "ncu_summary.py"), os.path.join(src, name)],
-                         capture_output=True, text=True).stdout
     keep = [ln for ln in out.splitlines() if not re.search(r"occupancy_per_|fp16|_adu|_cbu|membar|sleeping|tex_throttle|misc_per|drain|syslts", ln)]
     with open(os.path.join(dst, "{}_{}.txt".format(label, name[:-8])), "w") as f:
         f.write("# ncu --set full --clock-control none --import-source on -k regex:{} (bench.py --patients 131072; one launch)\n".format(name[:-8]))
