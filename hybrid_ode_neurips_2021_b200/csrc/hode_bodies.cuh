@@ -159,11 +159,19 @@ HODE_HD void fixed_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t i
     const float* tp = a.tape_y + ((int64_t)(a.n_grid - 2) * n_traj + idx) * D;
     float t1 = a.n_grid >= 1 ? a.grid[a.n_grid - 1] : 0.0f;
     float tj = (j >= 1) ? a.t_eval_f[j] : -INFINITY;
+    // The tape entry of step s-1 is requested while step s is being reversed: with 3 warps per scheduler nothing else
+    // hides an HBM round trip per step (ncu: stall_long_scoreboard 1.3 per issue without this, 0.2 in the tape-free
+    // adjoint kernel).
+    float ynext[D];
+    if (a.n_grid >= 2) load_vec<D>(tp, ynext);
+    tp -= tape_stride;
     for (int s = a.n_grid - 2; s >= 0; --s) {
         const float t0 = a.grid[s];
         const float dt = sub_rn(t1, t0);
         float y0[D], yb0[D], lam0[D];
-        load_vec<D>(tp, y0);
+#pragma unroll
+        for (int d = 0; d < D; ++d) y0[d] = ynext[d];
+        if (s > 0) load_vec<D>(tp, ynext);
         tp -= tape_stride;
 #pragma unroll
         for (int d = 0; d < D; ++d) yb0[d] = 0.0f;
@@ -346,11 +354,17 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds
         dopri5_stages<F>(sp, ds, T, t0f, dtf, t1f, y0, ks, y1);
         // error estimate and ratio
         float ss = 0.0f, bad = 0.0f;
+        float err[D];
+#pragma unroll
+        for (int d = 0; d < D; d += 2) {
+            float e0 = 0.0f, e1 = 0.0f;
+#pragma unroll
+            for (int i = 0; i < 7; ++i) fma2s(mul_rn(dtf, T.c_err[i]), k[i][d], k[i][d + 1], e0, e1, e0, e1);
+            err[d] = e0; err[d + 1] = e1;
+        }
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            float e = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 7; ++i) e = fmaf(k[i][d], mul_rn(dtf, T.c_err[i]), e);
+            const float e = err[d];
             const float tol = atol + rtol * fmaxf(fabsf(y0[d]), fabsf(y1[d]));
             const float q = e / tol;
             ss += q * q;
@@ -437,13 +451,27 @@ HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t 
 #pragma unroll
     for (int d = 0; d < D; ++d) { lam[d] = 0.0f; phi[d] = 0.0f; }
     int j = a.n_t - 1;
+    // tape entry (state, t0, dt) of step n-1 is requested while step n is being reversed (see fixed_bwd_traj)
+    float ynext[D];
+    double t0next = 0.0, dtnext = 0.0;
+    if (nacc > 0) {
+        load_vec<D>(a.tape_y + ((int64_t)(nacc - 1) * n_traj + idx) * D, ynext);
+        t0next = a.tape_t[(ctrl * a.tape_cap + nacc - 1) * 2];
+        dtnext = a.tape_t[(ctrl * a.tape_cap + nacc - 1) * 2 + 1];
+    }
     for (int n = nacc - 1; n >= 0; --n) {
-        const double t0 = a.tape_t[(ctrl * a.tape_cap + n) * 2];
-        const double dt = a.tape_t[(ctrl * a.tape_cap + n) * 2 + 1];
+        const double t0 = t0next;
+        const double dt = dtnext;
         const double t1 = t0 + dt;
         const float t0f = (float)t0, dtf = (float)dt, t1f = (float)t1;
         float y0[D], y1[D], yb0[D], yb1[D], g[D], kr[D], lr[D];
-        load_vec<D>(a.tape_y + ((int64_t)n * n_traj + idx) * D, y0);
+#pragma unroll
+        for (int d = 0; d < D; ++d) y0[d] = ynext[d];
+        if (n > 0) {
+            load_vec<D>(a.tape_y + ((int64_t)(n - 1) * n_traj + idx) * D, ynext);
+            t0next = a.tape_t[(ctrl * a.tape_cap + n - 1) * 2];
+            dtnext = a.tape_t[(ctrl * a.tape_cap + n - 1) * 2 + 1];
+        }
         // FSAL: k1 of step n is k7 of step n-1 = f(prev(t1_{n-1}), y1_{n-1}); step 0 uses f(t[0], y0)
         F::eval(sp, n == 0 ? t0f : t_prev(t0f), ds, y0, kr);
         stage_set_row<D>(k, 0, kr);
@@ -484,10 +512,14 @@ HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t 
         for (int d = 0; d < D; ++d) yb1[d] += g[d];
         // y1 = y0 + sum_{j<6} k_j * (beta[5][j]*dt)
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            yb0[d] += yb1[d];
+        for (int d = 0; d < D; d += 2) {
+            add2(yb0[d], yb0[d + 1], yb1[d], yb1[d + 1], yb0[d], yb0[d + 1]);
 #pragma unroll
-            for (int jj = 0; jj < 6; ++jj) kb.set(jj, d, fmaf(mul_rn(T.beta[5][jj], dtf), yb1[d], kb.get(jj, d)));
+            for (int jj = 0; jj < 6; ++jj) {
+                float o0, o1;
+                fma2s(mul_rn(T.beta[5][jj], dtf), yb1[d], yb1[d + 1], kb.get(jj, d), kb.get(jj, d + 1), o0, o1);
+                kb.set(jj, d, o0); kb.set(jj, d + 1, o1);
+            }
         }
         // stages k6 .. k2  (k[i] = f(t_i, Y_i), Y_i = y0 + sum_{j<i} k_j * (beta[i-1][j]*dt))
 #pragma unroll
@@ -497,20 +529,24 @@ HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t 
             else ti = add_rn(t0f, mul_rn(T.alpha[i - 1], dtf));
             float Yi[D];
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                float s = 0.0f;
+            for (int d = 0; d < D; d += 2) {
+                float s0 = 0.0f, s1 = 0.0f;
 #pragma unroll
-                for (int jj = 0; jj < i; ++jj) s = fmaf(k.get(jj, d), mul_rn(T.beta[i - 1][jj], dtf), s);
-                Yi[d] = y0[d] + s;
+                for (int jj = 0; jj < i; ++jj) fma2s(mul_rn(T.beta[i - 1][jj], dtf), k.get(jj, d), k.get(jj, d + 1), s0, s1, s0, s1);
+                add2(y0[d], y0[d + 1], s0, s1, Yi[d], Yi[d + 1]);
             }
             stage_row<D>(k, i, kr);
             stage_row<D>(kb, i, lr);
             F::template vjp<EG>(sp, ti, ds, Yi, kr, lr, g, acc);
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                yb0[d] += g[d];
+            for (int d = 0; d < D; d += 2) {
+                add2(yb0[d], yb0[d + 1], g[d], g[d + 1], yb0[d], yb0[d + 1]);
 #pragma unroll
-                for (int jj = 0; jj < i; ++jj) kb.set(jj, d, fmaf(mul_rn(T.beta[i - 1][jj], dtf), g[d], kb.get(jj, d)));
+                for (int jj = 0; jj < i; ++jj) {
+                    float o0, o1;
+                    fma2s(mul_rn(T.beta[i - 1][jj], dtf), g[d], g[d + 1], kb.get(jj, d), kb.get(jj, d + 1), o0, o1);
+                    kb.set(jj, d, o0); kb.set(jj, d + 1, o1);
+                }
             }
         }
         if (n == 0) {

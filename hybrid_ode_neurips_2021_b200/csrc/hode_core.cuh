@@ -886,12 +886,13 @@ HODE_HD void dopri5_stages(PS sp, const Dose& ds, const Dopri5Tab& T, float t0f,
         if (T.alpha[i] == 1.0f) ti = t_prev(t1f);
         else ti = add_rn(t0f, mul_rn(T.alpha[i], dtf));
         float yi[D], kn[D];
+        static_assert(D % 2 == 0, "packed stage combination assumes even D");
 #pragma unroll
-        for (int d = 0; d < D; ++d) {
-            float a = 0.0f;
+        for (int d = 0; d < D; d += 2) {  // two state dimensions per packed FMA, same j order per element
+            float a0 = 0.0f, a1 = 0.0f;
 #pragma unroll
-            for (int j = 0; j <= i; ++j) a = fmaf(k.get(j, d), mul_rn(T.beta[i][j], dtf), a);
-            yi[d] = y0[d] + a;
+            for (int j = 0; j <= i; ++j) fma2s(mul_rn(T.beta[i][j], dtf), k.get(j, d), k.get(j, d + 1), a0, a1, a0, a1);
+            add2(y0[d], y0[d + 1], a0, a1, yi[d], yi[d + 1]);
         }
         F::eval(sp, ti, ds, yi, kn);
         stage_set_row<D>(k, i + 1, kn);

@@ -649,3 +649,46 @@ def test_continuous_adjoint_close_to_discrete_backprop_and_rejects_dopri5():
     x_hat, h = dec(z, a.to(DEV))
     x_hat.sum().backward()
     assert torch.isfinite(z.grad).all() and dec.ode.ml_net[0].weight.grad is not None
+
+
+def test_continuous_adjoint_parameter_sets_and_edge_cases():
+    """C ABI level: two parameter sets in one launch (shared-memory parameter path) equal two single-set launches
+    (constant-bank path); a single output time needs no integration; an empty cohort is a no-op."""
+    from hybrid_ode_neurips_2021_b200 import _lib as L, ops, solver
+
+    lib = L.get_lib()
+    D, B = 8, 40
+    members = [build_pair(D, seed=50 + i)[1] for i in range(2)]
+    y0, a, _, _ = make_cohort(2 * B, D, seed=21)
+    t = torch.arange(0, 15.0)
+    grid = solver.fixed_grid_points(t, 0.125).to(DEV)
+    adj_grid, adj_count = (v.to(DEV) for v in solver.adjoint_grid_points(t, 0.125))
+    tt = t.to(DEV)
+    W = torch.randn(15, 2 * B, D, generator=torch.Generator().manual_seed(9)).to(DEV)
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.RK4_38, n_dose=1, hill2=True)
+    packs, doses = [], []
+    for i, m in enumerate(members):
+        m.set_action(a[:, i * B:(i + 1) * B].to(DEV))
+        packs.append(solver.pack_params(m, L.FIELD_ROCHE).detach())
+        doses.append((m.dosage.clone(), m._dose_t_f32.clone()))
+    pset = torch.tensor([0, 1], dtype=torch.int32, device=DEV)
+    pb2 = ops.Problem(cfg, 2, B, torch.cat([d[0] for d in doses]).contiguous(), torch.cat([d[1] for d in doses]).contiguous(),
+                      torch.stack(packs).contiguous(), pset)
+    h2, _ = ops.fixed_fwd(lib, pb2, y0.to(DEV), grid, tt, False)
+    gy2, gp2 = ops.fixed_adjoint(lib, pb2, adj_grid, adj_count, h2, W)
+    for i in range(2):
+        sl = slice(i * B, (i + 1) * B)
+        pb1 = ops.Problem(cfg, 1, B, doses[i][0], doses[i][1], packs[i][None].contiguous(), None)
+        h1, _ = ops.fixed_fwd(lib, pb1, y0[sl].to(DEV), grid, tt, False)
+        gy1, gp1 = ops.fixed_adjoint(lib, pb1, adj_grid, adj_count, h1, W[:, sl].contiguous())
+        assert relerr(h2[:, sl], h1) < 1e-6 and relerr(gy2[sl], gy1) < 1e-5
+        assert relerr(gp2[i][13:], gp1[0][13:]) < 1e-5
+    # one output time: grad_y0 = grad_h[0], parameter gradients zero
+    pb1 = ops.Problem(cfg, 1, B, doses[0][0], doses[0][1], packs[0][None].contiguous(), None)
+    g1, c1 = solver.adjoint_grid_points(t[:1], 0.125)
+    gy, gp = ops.fixed_adjoint(lib, pb1, g1.to(DEV), c1.to(DEV), h2[:1, :B].contiguous(), W[:1, :B].contiguous())
+    assert torch.equal(gy, W[0, :B]) and float(gp.abs().max()) == 0.0
+    # empty cohort
+    pb0 = ops.Problem(cfg, 1, 0, doses[0][0][:0], doses[0][1][:0], packs[0][None].contiguous(), None)
+    gy, gp = ops.fixed_adjoint(lib, pb0, adj_grid, adj_count, h2[:, :0].contiguous(), W[:, :0].contiguous())
+    assert gy.shape == (0, D) and float(gp.abs().max()) == 0.0

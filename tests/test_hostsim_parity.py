@@ -353,3 +353,37 @@ def test_neural_field_continuous_adjoint(lib_adj, method, opts):
     gy0, gp = ops.fixed_adjoint(lib, pb, adj_grid.contiguous(), adj_count, h, W)
     assert relerr(gy0, z.grad) < 2e-5
     assert relerr(gp[0], grads_vec(o, True)) < 5e-5
+
+
+def test_continuous_adjoint_parameter_sets_single_time_and_empty_cohort(lib_adj):
+    from hybrid_ode_neurips_2021_b200.solver import adjoint_grid_points
+
+    lib = lib_adj
+    D, B = 6, 4
+    os_ = [oracle_roche(D, 7 + i, True) for i in range(2)]
+    y0, a, _, _ = make_cohort(2 * B, D, seed=31)
+    t = torch.arange(0, 15.0)
+    grid = OI.fixed_grid_points(t, 0.125).contiguous()
+    adj_grid, adj_count = adjoint_grid_points(t, 0.125)
+    W = torch.randn(15, 2 * B, D, generator=torch.Generator().manual_seed(5))
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.RK4_38, n_dose=1, hill2=True)
+    for i, o in enumerate(os_):
+        o.set_action(a[:, i * B:(i + 1) * B])
+    pb2 = ops.Problem(cfg, 2, B, torch.cat([o.dosage.float() for o in os_]).contiguous(),
+                      torch.cat([o.times.float() for o in os_]).contiguous(),
+                      torch.cat([pack_roche(o) for o in os_]).contiguous(), torch.tensor([0, 1], dtype=torch.int32))
+    h2, _ = ops.fixed_fwd(lib, pb2, y0, grid, t, False)
+    gy2, gp2 = ops.fixed_adjoint(lib, pb2, adj_grid, adj_count, h2, W)
+    for i, o in enumerate(os_):
+        sl = slice(i * B, (i + 1) * B)
+        pb1 = problem(o, cfg, B)
+        h1, _ = ops.fixed_fwd(lib, pb1, y0[sl], grid, t, False)
+        gy1, gp1 = ops.fixed_adjoint(lib, pb1, adj_grid, adj_count, h1, W[:, sl].contiguous())
+        assert torch.equal(h2[:, sl], h1) and torch.equal(gy2[sl], gy1) and torch.equal(gp2[i], gp1[0])
+    pb1 = problem(os_[0], cfg, B)
+    g1, c1 = adjoint_grid_points(t[:1], 0.125)
+    gy, gp = ops.fixed_adjoint(lib, pb1, g1, c1, h2[:1, :B].contiguous(), W[:1, :B].contiguous())
+    assert torch.equal(gy, W[0, :B]) and float(gp.abs().max()) == 0.0
+    pb0 = ops.Problem(cfg, 1, 0, os_[0].dosage.float()[:0], os_[0].times.float()[:0], pack_roche(os_[0]), None)
+    gy, gp = ops.fixed_adjoint(lib, pb0, adj_grid, adj_count, h2[:, :0].contiguous(), W[:, :0].contiguous())
+    assert gy.shape == (0, D) and float(gp.abs().max()) == 0.0
