@@ -1,0 +1,110 @@
+"""Caller-side integration: the reference's training iteration -- LSTM encoder run backwards in time
+over the masked observations (model.py:408-440), z = mu, decoder solve, masked SSE + Gaussian KL (model.py:1151-1195),
+``loss.backward()``, Adam on encoder + ml_net + output_function (run_simulation.py:125-129) -- with the drop-in decoder
+on the GPU against the same iteration with the oracle decoder on the CPU.  Checks that gradients reach the ENCODER through
+``dL/dy0`` of the custom autograd op, for the discrete reverse sweep (rk4, dopri5) and the continuous adjoint, and that
+a short training run reduces the loss.  The cohort comes from the GPU generator (datagen.DataGeneratorRoche)."""
+import numpy as np
+import pytest
+import torch
+from torch import nn
+
+import hybrid_ode_neurips_2021_b200 as H
+from oracle import fields as OF
+
+from _util import relerr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+class Encoder(nn.Module):
+    """Same computation as the reference's EncoderLSTM (model.py:386-440, normalize=True); written here for the test."""
+
+    def __init__(self, obs_dim, latent_dim, hidden):
+        super().__init__()
+        self.lstm = nn.LSTM(obs_dim + 1, hidden)
+        self.lin = nn.Linear(hidden, latent_dim)
+        self.log_var = nn.Linear(hidden, latent_dim)
+
+    def forward(self, x, a, mask):
+        y_in = torch.cat([x, a], dim=-1) * torch.cat([mask, torch.ones_like(a)], dim=-1)
+        out, _ = self.lstm(torch.flip(y_in, dims=[0]))  # == feeding t = T-1 .. 0 one step at a time
+        last = out[-1]
+        return torch.exp(self.lin(last)) / 10, self.log_var(last) - 5.0
+
+
+def iteration(enc, dec, data, fused):
+    x, a, mask = data["measurements"], data["actions"], data["masks"]
+    mu, log_var = enc(x, a, mask)
+    if fused:
+        h = dec.solve(mu, a)
+        lik = H.masked_sse(dec, h, x, mask)
+    else:
+        x_hat, _ = dec(mu, a)
+        lik = torch.sum((x - x_hat) ** 2 * mask) / x.shape[1]
+    kld = torch.mean(-0.5 * torch.sum(1 + log_var - mu ** 2 - log_var.exp(), dim=1), dim=0)
+    return lik + kld
+
+
+@pytest.mark.parametrize("method,opts,adjoint,tol", [
+    ("rk4", {"step_size": 0.0625}, False, 2e-4),
+    ("dopri5", None, False, 1e-3),
+    ("rk4", {"step_size": 0.0625}, True, 2e-4),
+])
+def test_training_iteration_matches_cpu_oracle_and_learns(method, opts, adjoint, tol):
+    D, obs, B = 6, 20, 50
+    torch.backends.cudnn.allow_tf32 = False  # the encoder's cuDNN LSTM must stay in fp32 for the 2e-4 comparison
+    torch.backends.cuda.matmul.allow_tf32 = False
+    np.random.seed(666)
+    torch.manual_seed(666)
+    dg = H.DataGeneratorRoche(B + 30, obs, 14, 1, H.RochConfig(kel=1), 0.1, 1, D, 0.5, p_remove=0.5, output_sparsity=0.5,
+                              device=torch.device(DEV), val_size=10, test_size=20)
+    dg.generate_data()
+    dg.split_sample()
+    batch = dg.get_split("train", B)
+    cpu_batch = {k: v.cpu() for k, v in batch.items()}
+
+    torch.manual_seed(1)
+    enc_c = Encoder(obs, D, 2 * obs)
+    o_opts = dict(opts or {})
+    if method == "dopri5":
+        o_opts["differentiable_first_step"] = False
+    dec_c = OF.OracleDecoder(obs, D, method=method, options=o_opts)
+    if adjoint:
+        from oracle import odeint as OI
+
+        class AdjointDecoder(OF.OracleDecoder):
+            def forward(self, init, a):
+                self.ode.set_action(a)
+                h = OI.odeint_adjoint(self.ode, init, self.t, method=self.method, options=dict(self.options or {}))
+                return self.output_function(h), h
+
+        dec_c.__class__ = AdjointDecoder
+    enc_g = Encoder(obs, D, 2 * obs).to(DEV)
+    enc_g.load_state_dict(enc_c.state_dict())
+    dec_g = H.RocheExpertDecoder(obs, D, 1, 14, 1, method=method, device=DEV, solver_options=opts, adjoint=adjoint)
+    dec_g.load_state_dict(dec_c.state_dict())
+
+    loss_c = iteration(enc_c, dec_c, cpu_batch, fused=False)
+    loss_c.backward()
+    loss_g = iteration(enc_g, dec_g, batch, fused=True)
+    loss_g.backward()
+    assert abs(loss_g.item() - loss_c.item()) <= tol * abs(loss_c.item())
+    # the encoder only sees the decoder through dL/dy0 of the custom autograd op
+    assert relerr(enc_g.lstm.weight_ih_l0.grad, enc_c.lstm.weight_ih_l0.grad) < 5 * tol
+    assert relerr(enc_g.lin.weight.grad, enc_c.lin.weight.grad) < 5 * tol
+    assert relerr(dec_g.ode.ml_net[0].weight.grad, dec_c.ode.ml_net[0].weight.grad) < 5 * tol
+    assert relerr(dec_g.output_function[0].weight.grad, dec_c.output_function[0].weight.grad) < 5 * tol
+
+    params = list(enc_g.parameters()) + list(dec_g.ode.ml_net.parameters()) + list(dec_g.output_function.parameters())
+    opt = torch.optim.Adam(params, lr=0.01)
+    first = last = None
+    for it in range(30):
+        opt.zero_grad()
+        loss = iteration(enc_g, dec_g, batch, fused=True)
+        loss.backward()
+        opt.step()
+        first = loss.item() if first is None else first
+        last = loss.item()
+    assert np.isfinite(last) and last < 0.9 * first, (first, last)
