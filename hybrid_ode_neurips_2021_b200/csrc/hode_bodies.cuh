@@ -45,6 +45,12 @@ struct SolveArgs {
     const int32_t* adj_cnt;
 };
 
+// Reverse sweeps request the tape entry of the NEXT step to be reversed one step ahead (D more live registers).  Only where
+// registers allow: RocheODE with <= 64 packed parameters (D <= 8).  At D = 12 (117 accumulators, kernels already spill) the
+// extra live state costs more than the hidden latency (measured: dopri5 reverse sweep 11.9 -> 13.4 ms at the C3 shape).
+template <class F> struct TapePrefetch { static constexpr bool value = false; };
+template <int D_, bool H_, bool A_> struct TapePrefetch<Roche<D_, H_, A_>> { static constexpr bool value = Roche<D_, H_, A_>::P <= 64; };
+
 // ---- vector load/store of one trajectory's D contiguous floats ------------------------------------------------
 template <int D>
 HODE_HD void load_vec(const float* __restrict__ p, float (&v)[D]) {
@@ -162,16 +168,23 @@ HODE_HD void fixed_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t i
     // The tape entry of step s-1 is requested while step s is being reversed: with 3 warps per scheduler nothing else
     // hides an HBM round trip per step (ncu: stall_long_scoreboard 1.3 per issue without this, 0.2 in the tape-free
     // adjoint kernel).
+    constexpr bool PF = TapePrefetch<F>::value;
     float ynext[D];
-    if (a.n_grid >= 2) load_vec<D>(tp, ynext);
-    tp -= tape_stride;
+    if (PF) {
+        if (a.n_grid >= 2) load_vec<D>(tp, ynext);
+        tp -= tape_stride;
+    }
     for (int s = a.n_grid - 2; s >= 0; --s) {
         const float t0 = a.grid[s];
         const float dt = sub_rn(t1, t0);
         float y0[D], yb0[D], lam0[D];
+        if (PF) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) y0[d] = ynext[d];
-        if (s > 0) load_vec<D>(tp, ynext);
+            for (int d = 0; d < D; ++d) y0[d] = ynext[d];
+            if (s > 0) load_vec<D>(tp, ynext);
+        } else {
+            load_vec<D>(tp, y0);
+        }
         tp -= tape_stride;
 #pragma unroll
         for (int d = 0; d < D; ++d) yb0[d] = 0.0f;
@@ -452,25 +465,30 @@ HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t 
     for (int d = 0; d < D; ++d) { lam[d] = 0.0f; phi[d] = 0.0f; }
     int j = a.n_t - 1;
     // tape entry (state, t0, dt) of step n-1 is requested while step n is being reversed (see fixed_bwd_traj)
+    constexpr bool PF = TapePrefetch<F>::value;
     float ynext[D];
     double t0next = 0.0, dtnext = 0.0;
-    if (nacc > 0) {
+    if (PF && nacc > 0) {
         load_vec<D>(a.tape_y + ((int64_t)(nacc - 1) * n_traj + idx) * D, ynext);
         t0next = a.tape_t[(ctrl * a.tape_cap + nacc - 1) * 2];
         dtnext = a.tape_t[(ctrl * a.tape_cap + nacc - 1) * 2 + 1];
     }
     for (int n = nacc - 1; n >= 0; --n) {
-        const double t0 = t0next;
-        const double dt = dtnext;
+        const double t0 = PF ? t0next : a.tape_t[(ctrl * a.tape_cap + n) * 2];
+        const double dt = PF ? dtnext : a.tape_t[(ctrl * a.tape_cap + n) * 2 + 1];
         const double t1 = t0 + dt;
         const float t0f = (float)t0, dtf = (float)dt, t1f = (float)t1;
         float y0[D], y1[D], yb0[D], yb1[D], g[D], kr[D], lr[D];
+        if (PF) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) y0[d] = ynext[d];
-        if (n > 0) {
-            load_vec<D>(a.tape_y + ((int64_t)(n - 1) * n_traj + idx) * D, ynext);
-            t0next = a.tape_t[(ctrl * a.tape_cap + n - 1) * 2];
-            dtnext = a.tape_t[(ctrl * a.tape_cap + n - 1) * 2 + 1];
+            for (int d = 0; d < D; ++d) y0[d] = ynext[d];
+            if (n > 0) {
+                load_vec<D>(a.tape_y + ((int64_t)(n - 1) * n_traj + idx) * D, ynext);
+                t0next = a.tape_t[(ctrl * a.tape_cap + n - 1) * 2];
+                dtnext = a.tape_t[(ctrl * a.tape_cap + n - 1) * 2 + 1];
+            }
+        } else {
+            load_vec<D>(a.tape_y + ((int64_t)n * n_traj + idx) * D, y0);
         }
         // FSAL: k1 of step n is k7 of step n-1 = f(prev(t1_{n-1}), y1_{n-1}); step 0 uses f(t[0], y0)
         F::eval(sp, n == 0 ? t0f : t_prev(t0f), ds, y0, kr);
