@@ -34,6 +34,15 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# torchrun exports OMP_NUM_THREADS=1 to every rank.  The host-side work of this file (synthetic cohorts, the CPU reference
+# arm) is sized for the host's cores, so give each rank its share BEFORE the OpenMP / MKL runtimes read the variable.
+if os.environ.get("OMP_NUM_THREADS") == "1" and "LOCAL_RANK" in os.environ:
+    _share = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))))
+    if "reference" in sys.argv:  # --impl reference: rank 0 works alone, the other ranks exit at once
+        _share = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(_share)
+    os.environ.pop("MKL_NUM_THREADS", None)
+
 import torch  # noqa: E402
 
 D, OBS, T, T_MAX = 8, 40, 15, 14
@@ -346,6 +355,16 @@ def run_ours(args):
     ms_e, wall_e = timed(e2e_step, args.steps)
     e2e_val = B_global * N_STEPS * args.steps / max(ms_e * 1e-3, wall_e)
 
+    # Every collective of the run is done.  Tear the process group down NOW on every rank: what follows is rank 0's own
+    # post-processing (kernel-level timing, CPU baseline), and a rank parked in an NCCL barrier meanwhile would hit the
+    # collective timeout (and its spinning host thread slows the CPU baseline down).
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+        if rank != 0:
+            return
+
     # ---- per-kernel device times for the roofline (CUDA events on the launching stream, same buffers) -----------------
     roof, extra = None, {}
     if rank == 0:
@@ -422,7 +441,7 @@ def run_ours(args):
                                     "peak_source": hbm_src, "algorithmic_bytes_per_launch": dec_bytes},
         }
         del h, tape, gh
-        if not args.no_extras:
+        if not args.no_extras and world == 1:  # secondary figures and CPU baselines: N = 1 only
             try:
                 extra["other_configs"] = dopri5_extras(lib, dev)
                 cpu = dopri5_cpu_baselines()
@@ -432,13 +451,13 @@ def run_ours(args):
             except Exception as e:  # secondary figures must never take the headline down
                 extra["other_configs"] = {"error": repr(e)}
 
-    if rank != 0:
-        if world > 1:
-            dist.barrier()  # matched by rank 0 after it has printed the line
-            dist.destroy_process_group()
-        return
-
-    cpu_val, cpu_s, cores = cpu_reference_rate(args.cpu_patients, 2)
+    if world == 1:
+        cpu_val, cpu_s, cores = cpu_reference_rate(args.cpu_patients, 2)
+        cpu_baseline = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "{} patients of the same workload, fwd + read-out/masked-SSE + autograd backward, "
+                                  "best of 2 ({:.1f} s each)".format(args.cpu_patients, cpu_s)}
+    else:  # the CPU baseline is a rank-0, N = 1 measurement (other ranks' host threads would share the cores)
+        cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "measured at N=1 only"}
     h2d = world * sum(t.numel() * t.element_size() for c in host_chunks for t in c)  # whole job, like `value`
     n_par = sum(p.numel() for p in train_params)
     line = {
@@ -454,16 +473,11 @@ def run_ours(args):
         "gpu_launches_per_step": {"dose_schedule_kernel": 1, "prep_params_kernel": 2, "fixed_fwd_kernel": 1,
                                   "decode_sse_fast_kernel": 1, "fixed_bwd_kernel": 1},
         "roofline": roof,
-        "cpu_baseline": {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "{} patients of the same workload, fwd + read-out/masked-SSE + autograd backward, "
-                                   "best of 2 ({:.1f} s each)".format(args.cpu_patients, cpu_s)},
+        "cpu_baseline": cpu_baseline,
         "fwd_only": {"value": B_global * N_STEPS * args.steps / (ms_f * 1e-3), "unit": UNIT, "ms_per_step": ms_f / args.steps},
     }
     line.update(extra)
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
 
 
 def ncu_traffic(kernel_file, patients):
