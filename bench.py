@@ -43,6 +43,9 @@ if os.environ.get("OMP_NUM_THREADS") == "1" and "LOCAL_RANK" in os.environ:
     os.environ["OMP_NUM_THREADS"] = str(_share)
     os.environ.pop("MKL_NUM_THREADS", None)
 
+# stdout carries exactly one JSON line: NCCL's own messages (its version banner at NCCL_DEBUG=VERSION and above) go to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 import torch  # noqa: E402
 
 D, OBS, T, T_MAX = 8, 40, 15, 14
