@@ -237,8 +237,33 @@ def workload_config(B, world, note=None):
 
 
 # -------------------------------------------------------------------------------------------------------------------
+class StdoutToStderr:
+    """stdout must carry exactly ONE JSON line, but NCCL prints its version banner to the C-level stdout when a communicator
+    is created.  File descriptor 1 is pointed at stderr for the whole run and restored (after flushing the C stdio buffers)
+    just before the line is printed."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def restore(self):
+        if self.saved is None:
+            return
+        sys.stdout.flush()
+        try:
+            ctypes.CDLL(None).fflush(None)
+        except Exception:
+            pass
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        self.saved = None
+
+
 def run_ours(args):
     import torch.distributed as dist
+
+    quiet = StdoutToStderr()
 
     import hybrid_ode_neurips_2021_b200 as H
     from hybrid_ode_neurips_2021_b200 import _lib as L
@@ -480,6 +505,7 @@ def run_ours(args):
         "fwd_only": {"value": B_global * N_STEPS * args.steps / (ms_f * 1e-3), "unit": UNIT, "ms_per_step": ms_f / args.steps},
     }
     line.update(extra)
+    quiet.restore()
     print(json.dumps(line), flush=True)
 
 
