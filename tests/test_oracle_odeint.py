@@ -211,3 +211,85 @@ def test_float32_run_keeps_time_in_float64_and_casts_per_stage():
         OI.odeint(ode, y0, t, rtol=1e-3, atol=1e-4, options={"trace": tr})
     assert set(seen) == {torch.float32}
     assert (tr.accepted, tr.rejected) == (34, 15)
+
+
+# ---- odeint_adjoint restatement (torchdiffeq adjoint.py) -------------------------------------------------------------
+class _Decay(torch.nn.Module):
+    """dy/dt = -theta * y + cos(t) * b: closed-form sensitivities for theta (b = 0) and a time-dependent forcing."""
+
+    def __init__(self, theta, b=0.0):
+        super().__init__()
+        self.theta = torch.nn.Parameter(torch.tensor(theta, dtype=torch.float64))
+        self.b = torch.nn.Parameter(torch.tensor(b, dtype=torch.float64))
+
+    def forward(self, t, y):
+        return -self.theta * y + torch.cos(t) * self.b
+
+
+@pytest.mark.parametrize("method,h,tol", [("rk4", 0.05, 1e-7), ("midpoint", 0.01, 1e-4), ("euler", 0.001, 2e-3)])
+def test_adjoint_gradients_match_closed_form(method, h, tol):
+    """L = sum_i w_i y(t_i), y = y0 exp(-theta t): dL/dy0 = sum w_i exp(-theta t_i), dL/dtheta = -sum w_i t_i y(t_i)."""
+    f = _Decay(0.7)
+    y0 = torch.tensor([[1.3], [0.4]], dtype=torch.float64, requires_grad=True)
+    t = torch.tensor([0.0, 0.5, 1.25, 2.0], dtype=torch.float64)
+    w = torch.tensor([0.3, -1.0, 2.0, 0.5], dtype=torch.float64)
+    out = OI.odeint_adjoint(f, y0, t, method=method, options={"step_size": h})
+    (out[:, :, 0] * w[:, None]).sum().backward()
+    e = torch.exp(-0.7 * t)
+    assert torch.allclose(y0.grad[:, 0], (w * e).sum().expand(2), rtol=tol, atol=0)
+    expect = -(w[:, None] * t[:, None] * e[:, None] * y0.detach()[None, :, 0]).sum()
+    assert abs(f.theta.grad.item() - expect.item()) <= tol * abs(expect.item())
+    # b enters through the forcing only: dL/db = sum_i w_i int_0^{t_i} exp(-theta (t_i - s)) cos(s) ds per trajectory
+    s = torch.linspace(0, 2, 200001, dtype=torch.float64)
+    db = 0.0
+    for wi, ti in zip(w.tolist(), t.tolist()):
+        m = s <= ti
+        db += wi * torch.trapezoid(torch.exp(-0.7 * (ti - s[m])) * torch.cos(s[m]), s[m]).item()
+    assert abs(f.b.grad.item() - 2 * db) <= max(tol, 1e-6) * abs(2 * db)
+
+
+def test_adjoint_equals_discrete_backprop_to_the_order_of_the_method():
+    """optimise-then-discretise vs discretise-then-optimise on a smooth nonlinear field: the gap must fall with the
+    method's order (rk4: ~h^4) and the forward values must be IDENTICAL (the adjoint's forward pass is plain odeint)."""
+
+    class F(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(0)
+            self.lin = torch.nn.Linear(3, 3).double()
+
+        def forward(self, t, y):
+            return torch.tanh(self.lin(y)) * torch.cos(t)
+
+    t = torch.linspace(0, 2, 5, dtype=torch.float64)
+    w = torch.randn(5, 4, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    gaps = []
+    for h in (0.25, 0.125):
+        f = F()
+        y0 = torch.randn(4, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(2)).requires_grad_(True)
+        out = OI.odeint(f, y0, t, method="rk4", options={"step_size": h})
+        (out * w).sum().backward()
+        g_d = [y0.grad.clone(), f.lin.weight.grad.clone()]
+        y0.grad = None
+        f.zero_grad()
+        out_a = OI.odeint_adjoint(f, y0, t, method="rk4", options={"step_size": h})
+        assert torch.equal(out_a, out)
+        (out_a * w).sum().backward()
+        gaps.append(max(((y0.grad - g_d[0]).norm() / g_d[0].norm()).item(),
+                        ((f.lin.weight.grad - g_d[1]).norm() / g_d[1].norm()).item()))
+    assert gaps[1] < gaps[0] / 8 and gaps[1] < 1e-6  # 4th order: halving h cuts the gap by ~16
+
+
+def test_adjoint_argument_handling():
+    f = _Decay(0.5)
+    y0 = torch.ones(1, 1, dtype=torch.float64)
+    t = torch.tensor([0.0, 1.0], dtype=torch.float64)
+    with pytest.raises(NotImplementedError):
+        OI.odeint_adjoint(f, y0, t)  # dopri5: the adaptive adjoint is not restated
+    with pytest.raises(ValueError):
+        OI.odeint_adjoint(lambda tt, yy: -yy, y0, t, method="rk4")  # not an nn.Module and no adjoint_params
+    # parameters that do not require grad are dropped from the augmented state
+    f.b.requires_grad_(False)
+    y0g = y0.clone().requires_grad_(True)
+    OI.odeint_adjoint(f, y0g, t, method="rk4", options={"step_size": 0.1}).sum().backward()
+    assert f.b.grad is None and f.theta.grad is not None
