@@ -692,3 +692,20 @@ def test_continuous_adjoint_parameter_sets_and_edge_cases():
     pb0 = ops.Problem(cfg, 1, 0, doses[0][0][:0], doses[0][1][:0], packs[0][None].contiguous(), None)
     gy, gp = ops.fixed_adjoint(lib, pb0, adj_grid, adj_count, h2[:, :0].contiguous(), W[:, :0].contiguous())
     assert gy.shape == (0, D) and float(gp.abs().max()) == 0.0
+
+
+def test_masked_sse_accepts_one_byte_masks():
+    """uint8 / bool masks (what a loader can keep on the host to cut PCIe bytes) give bit-identical results to float masks."""
+    D, obs, B = 8, 40, 300
+    dec = H.RocheExpertDecoder(obs, D, 1, 14, 1, method="rk4", device=DEV, solver_options={"step_size": 0.125})
+    _, _, x, mask = make_cohort(B, D, obs=obs, seed=3)
+    h = torch.randn(15, B, D, generator=torch.Generator().manual_seed(0)).to(DEV)
+    res = []
+    for m in (mask, mask.to(torch.uint8), mask.bool()):
+        dec.zero_grad()
+        hh = h.clone().requires_grad_(True)
+        loss = H.masked_sse(dec, hh, x.to(DEV), m.to(DEV))
+        loss.backward()
+        res.append((loss.detach().clone(), hh.grad.clone(), dec.output_function[0].weight.grad.clone()))
+    for r in res[1:]:
+        assert all(torch.equal(u, v) for u, v in zip(r, res[0]))
