@@ -90,3 +90,27 @@ def test_generator_device_rng_large_cohort_statistics():
     assert 4.5 < float(dg.dose_amount.mean()) < 5.5
     again = dg.solve_latents(dg.latents[0], torch.as_tensor(dg.dose_time)[:], torch.as_tensor(dg.dose_amount))
     assert torch.equal(again, dg.latents)
+
+
+def test_generator_device_rng_path_on_host_emulation():
+    """exact_rng=False code path (per-patient draws by torch generators on the cohort device) through the host emulation:
+    shapes, dose indexing, mask density, normalisation."""
+    subprocess.run(["make", "-C", HS_DIR], check=True, capture_output=True)
+    lib = L.HodeLib(HS, required=["hode_abi_version", "hode_last_error", "hode_dopri5_fwd"])
+    np.random.seed(3)
+    N = 1500
+    dg = DataGeneratorRoche(N, 20, 14, 1, RochConfig(kel=1), 0.1, 1, 6, 0.5, p_remove=0.5, output_sparsity=0.5,
+                            device=torch.device("cpu"), val_size=100, test_size=200, exact_rng=False, lib=lib)
+    dg.generate_data()
+    assert dg.latents.shape == (15, N, 6) and torch.isfinite(dg.latents).all()
+    assert dg.measurements.shape == (15, N, 20) and dg.masks.shape == (15, N, 20) and dg.actions.shape == (15, N, 1)
+    assert abs(float(dg.masks.mean()) - 0.5) < 0.01
+    assert torch.allclose(dg.measurements.mean(dim=(0, 1)), torch.zeros(20), atol=1e-4)
+    assert torch.allclose(dg.measurements.std(dim=(0, 1)), torch.ones(20), atol=1e-4)
+    day = torch.as_tensor(dg.dose_time)[:, 0]
+    amt = torch.as_tensor(dg.dose_amount).float()
+    assert int(day.min()) >= 0 and int(day.max()) <= 13
+    assert torch.equal(dg.actions[day, torch.arange(N), 0], amt)
+    assert float((dg.actions != 0).sum()) <= N
+    dg.split_sample()
+    assert dg.data_train["latents"].shape[1] == N - 300 and dg.data_test["masks"].shape[1] == 200
