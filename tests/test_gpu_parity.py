@@ -695,7 +695,7 @@ def test_continuous_adjoint_parameter_sets_and_edge_cases():
 
 
 def test_masked_sse_accepts_one_byte_masks():
-    """uint8 / bool masks (what a loader can keep on the host to cut PCIe bytes) give bit-identical results to float masks."""
+    """uint8 / bool masks (what a loader can keep on the host to cut PCIe bytes) give the same results as float masks."""
     D, obs, B = 8, 40, 300
     dec = H.RocheExpertDecoder(obs, D, 1, 14, 1, method="rk4", device=DEV, solver_options={"step_size": 0.125})
     _, _, x, mask = make_cohort(B, D, obs=obs, seed=3)
@@ -708,4 +708,7 @@ def test_masked_sse_accepts_one_byte_masks():
         loss.backward()
         res.append((loss.detach().clone(), hh.grad.clone(), dec.output_function[0].weight.grad.clone()))
     for r in res[1:]:
-        assert all(torch.equal(u, v) for u, v in zip(r, res[0]))
+        assert torch.equal(r[1], res[0][1])  # grad_h is computed per element: bit-identical
+        # the loss and grad_W are reduced with atomics (order varies from launch to launch): rounding-level agreement
+        assert abs(r[0].item() - res[0][0].item()) <= 1e-6 * abs(res[0][0].item())
+        assert relerr(r[2], res[0][2]) < 1e-5
