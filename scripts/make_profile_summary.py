@@ -39,6 +39,20 @@ with open(os.path.join(dst, label + "_launches.txt"), "w") as f:
     f.write("{:>7} {:>12} {:>12} {:>7}  kernel\n".format("count", "total_us", "mean_us", "share"))
     for k, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         f.write("{:>7} {:>12.1f} {:>12.1f} {:>6.1f}%  {}\n".format(c, t, t / c, 100 * t / tot, k[:140]))
+    # The list mixes full-cohort launches (the device-resident step) with the 1/8-size launches of the end-to-end phase and
+    # the extra forward launches of the forward-only timing.  Shares of ONE device-resident step: mean duration of the
+    # full-size launches of each hode kernel (a launch counts as full-size above half of that kernel's longest launch).
+    per = collections.OrderedDict()
+    for k, v in rows:
+        if "hode::" in k:
+            per.setdefault(k, []).append(v)
+    full = {k: [v for v in vs if v > 0.5 * max(vs)] for k, vs in per.items()}
+    step = {k: sum(v) / len(v) for k, v in full.items() if v and "prep_params" not in k and "ffma_probe" not in k
+            and "adj_kernel" not in k and "dopri5" not in k and "crps" not in k}
+    stot = sum(step.values())
+    f.write("\n# one device-resident step = one full-size launch of each kernel below ({:.2f} ms):\n".format(stot / 1e3))
+    for k, v in sorted(step.items(), key=lambda kv: -kv[1]):
+        f.write("{:>7} {:>12.1f} {:>12} {:>6.1f}%  {}\n".format(len(full[k]), v, "(mean us)", 100 * v / stot, k[:140]))
 
 # ---- per-kernel full captures ----------------------------------------------------------------------------------------
 names = sorted(os.listdir(src))
