@@ -17,7 +17,7 @@ here from the package's documented behaviour (module names below are the package
 * ``_impl/fixed_grid.py``  -> ``euler`` / ``midpoint`` / ``rk4`` (3/8 rule) step functions
 * ``_impl/solvers.py``     -> :class:`FixedGrid` (grid construction, linear interpolation to output times)
 * ``_impl/interp.py``      -> :func:`_quartic_fit`, :func:`_quartic_eval`
-* ``_impl/adjoint.py``     -> :func:`odeint_adjoint` (``OdeintAdjointMethod``; fixed-grid methods only)
+* ``_impl/adjoint.py``     -> :func:`odeint_adjoint` (``OdeintAdjointMethod``, default mixed adjoint norm and ``seminorm``)
 
 PARITY UNPINNED BY THE REFERENCE: the reference repository has no tests and no golden vectors at the solver boundary
 (SURVEY.md section 4).  The restatement is pinned instead by (i) closed-form ODEs and order-of-convergence checks,
@@ -579,6 +579,20 @@ class _AdjointMethod(torch.autograd.Function):
                 # vjp_t: t carries no gradient request (t_requires_grad is False at every reference call site)
                 return flatten([torch.zeros_like(t_).to(yy.dtype), func_eval.detach(), vjp_y] + vjp_params)
 
+            # adaptive adjoint solves: the package's default adjoint norm (adjoint.py handle_adjoint_norm_) is a MIXED norm
+            # over the tuple, max(|vjp_t|, rms(y), rms(adj_y), max_k rms(adj_param_k)); 'seminorm' drops the parameter part
+            adj_options = dict(adj_options)
+            if adj_method == "dopri5":
+                seminorm = adj_options.get("norm") == "seminorm"
+                if "norm" not in adj_options or seminorm:
+                    def adjoint_norm(flat):
+                        parts = unflatten(flat)
+                        terms = [parts[0].abs(), _rms_norm(parts[1]), _rms_norm(parts[2])]
+                        if not seminorm:
+                            terms += [_rms_norm(p) for p in parts[3:] if p.numel() > 0]
+                        return torch.stack([x.reshape(()) for x in terms]).max()
+
+                    adj_options["norm"] = adjoint_norm
             for i in range(len(t) - 1, 0, -1):
                 sol = odeint(augmented_dynamics, flatten(state), t[i - 1:i + 1].flip(0), rtol=adj_rtol, atol=adj_atol,
                              method=adj_method, options=adj_options)
@@ -591,9 +605,10 @@ class _AdjointMethod(torch.autograd.Function):
 
 def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=None, event_fn=None, adjoint_rtol=None,
                    adjoint_atol=None, adjoint_method=None, adjoint_options=None, adjoint_params=None):
-    """``torchdiffeq.odeint_adjoint`` (the import the reference keeps commented out at ``model.py:9``), restated for the
-    fixed-grid methods: the adaptive adjoint's mixed norm over the tuple state is not restated.  Defaults follow the
-    package: the adjoint solve uses the forward method / tolerances / options unless overridden; ``adjoint_params``
+    """``torchdiffeq.odeint_adjoint`` (the import the reference keeps commented out at ``model.py:9``).  Fixed-grid methods
+    and ``dopri5`` (the adaptive adjoint solve is controlled by the package's mixed norm over the augmented tuple, or by
+    ``adjoint_options={'norm': 'seminorm'}``; the CUDA path has kernels for the fixed-grid methods only).  Defaults follow
+    the package: the adjoint solve uses the forward method / tolerances / options unless overridden; ``adjoint_params``
     defaults to ``func.parameters()``, filtered to those that require grad."""
     if event_fn is not None:
         raise NotImplementedError("event handling is not used by the reference and not restated")
@@ -604,8 +619,6 @@ def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=No
     adjoint_rtol = rtol if adjoint_rtol is None else adjoint_rtol
     adjoint_atol = atol if adjoint_atol is None else adjoint_atol
     adjoint_method = method if adjoint_method is None else adjoint_method
-    if adjoint_method == "dopri5":
-        raise NotImplementedError("the adaptive adjoint (mixed norm over the augmented tuple state) is not restated")
     if adjoint_options is None:
         adjoint_options = {k: v for k, v in options.items() if k != "norm"} if options is not None else {}
     else:
