@@ -1,6 +1,8 @@
 """hybrid_ode_neurips_2021_b200 -- B200 (sm_100a) implementation of the hybrid-ODE hot path of
-ZhaozhiQIAN/Hybrid-ODE-NeurIPS-2021: fused fixed-step / dopri5 integration (forward + discrete backprop) of the
-expert PK/PD + latent-MLP vector field, and the fused read-out + masked-SSE reduction.
+ZhaozhiQIAN/Hybrid-ODE-NeurIPS-2021: fused fixed-step / dopri5 integration (forward + discrete backprop, and the
+tape-free continuous adjoint for the fixed-step methods) of the expert PK/PD + latent-MLP vector field, the fused
+read-out + masked-SSE reduction, one-launch Monte-Carlo evaluation with CRPS, the real-data fields, and the cohort
+generator that feeds the path.
 
 Importing this package does not load CUDA; the shared library is loaded on first solver call and its absence is a
 hard error (there is no CPU fallback).
