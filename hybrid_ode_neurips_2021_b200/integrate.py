@@ -4,8 +4,9 @@
 ``from torchdiffeq import odeint as dto`` (``/root/reference/model.py:10``) binds to it: the reference's own
 ``RocheODE`` / ``NeuralODE`` instances are recognised by structure and integrated by the sm_100a kernels
 (``odeint_adjoint``, the import the reference keeps commented out at ``model.py:9``, is provided as well).
-``patch_model(module)`` additionally swaps the hot-path classes of an imported reference ``model`` module -- and their two
-callers, ``EncoderLSTM`` and ``VariationalInference`` -- for the drop-ins (vectorised ``set_action``, fused likelihood).
+``patch_model(module)`` additionally swaps the hot-path classes of an imported reference ``model`` module for the drop-ins
+(vectorised ``set_action``, one-launch solves).  The callers either side of the path -- ``EncoderLSTM``,
+``VariationalInference``, ``training_utils`` -- stay the reference's own, unmodified code.
 """
 from __future__ import annotations
 
@@ -38,9 +39,4 @@ def patch_model(module):
     module.NeuralODEReal = _real.NeuralODEReal
     module.NeuralODEReal2nd = _real.NeuralODEReal2nd
     module.DecoderReal = _real.DecoderReal
-    from . import vi as _vi
-
-    # callers of the path: single-call LSTM encoder, fused likelihood in VariationalInference.loss (same random stream)
-    module.EncoderLSTM = _vi.EncoderLSTM
-    module.VariationalInference = _vi.VariationalInference
     return module

@@ -5,6 +5,7 @@ test-only host emulation in ``tests/`` (CPU tensors).  No arithmetic of the hot 
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 from dataclasses import dataclass
 from typing import Optional
@@ -24,6 +25,15 @@ def _stream(t: torch.Tensor):
     if t.is_cuda:
         return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
     return None
+
+
+def _on(t: torch.Tensor):
+    """Device guard for one C-ABI call: the library launches on the CURRENT device (its constant-bank lease and every kernel
+    launch use it), so a tensor living on another GPU -- the reference's default is ``cuda:1`` without ``set_device``
+    (``global_config.py:7``, ``run_simulation.py:33``) -- must make its device current for the duration of the call."""
+    if t.is_cuda:
+        return torch.cuda.device(t.device)
+    return contextlib.nullcontext()
 
 
 def _f32c(t: torch.Tensor) -> torch.Tensor:
@@ -52,8 +62,9 @@ def dose_schedule(lib, action: torch.Tensor):
     amt = torch.empty(B, dtype=torch.float32, device=dev)
     idx = torch.empty(B, T, dtype=torch.int32, device=dev)
     cnt = torch.empty(B, dtype=torch.int32, device=dev)
-    rc = lib.hode_dose_schedule(_ptr(action), action.stride(0), action.stride(1), T, B, _ptr(amt), _ptr(idx), _ptr(cnt),
-                                _stream(action))
+    with _on(action):
+        rc = lib.hode_dose_schedule(_ptr(action), action.stride(0), action.stride(1), T, B, _ptr(amt), _ptr(idx), _ptr(cnt),
+                                    _stream(action))
     lib.check(rc, "hode_dose_schedule")
     return amt, idx, cnt
 
@@ -81,9 +92,10 @@ def fixed_fwd(lib, pb: Problem, y0, grid, t_eval, want_tape):
     n_t, n_grid = t_eval.numel(), grid.numel()
     h = torch.empty(n_t, pb.n_traj, D, dtype=torch.float32, device=y0.device)
     tape = torch.empty(max(n_grid - 1, 0), pb.n_traj, D, dtype=torch.float32, device=y0.device) if want_tape else None
-    rc = lib.hode_fixed_fwd(C.byref(pb.cfg), pb.n_groups, pb.batch, _ptr(y0), _ptr(pb.dose_amt), _ptr(pb.dose_t),
-                            pb.dose_t.stride(0), _ptr(pb.params), _ptr(pb.pset), _ptr(grid), n_grid, _ptr(t_eval), n_t,
-                            _ptr(h), _ptr(tape), _stream(y0))
+    with _on(y0):
+        rc = lib.hode_fixed_fwd(C.byref(pb.cfg), pb.n_groups, pb.batch, _ptr(y0), _ptr(pb.dose_amt), _ptr(pb.dose_t),
+                                pb.dose_t.stride(0), _ptr(pb.params), _ptr(pb.pset), _ptr(grid), n_grid, _ptr(t_eval), n_t,
+                                _ptr(h), _ptr(tape), _stream(y0))
     lib.check(rc, "hode_fixed_fwd")
     return h, tape
 
@@ -94,10 +106,11 @@ def fixed_bwd(lib, pb: Problem, grid, t_eval, grad_h, tape):
     dev = grad_h.device
     gy0 = torch.empty(pb.n_traj, D, dtype=torch.float32, device=dev)
     gp = torch.empty_like(pb.params)
-    rc = lib.hode_fixed_bwd(C.byref(pb.cfg), pb.n_groups, pb.batch, _ptr(pb.dose_amt), _ptr(pb.dose_t),
-                            pb.dose_t.stride(0), _ptr(pb.params), _ptr(pb.pset), pb.params.shape[0], _ptr(grid),
-                            grid.numel(), _ptr(t_eval), t_eval.numel(), _ptr(grad_h), _ptr(tape), _ptr(gy0), _ptr(gp),
-                            _stream(grad_h))
+    with _on(grad_h):
+        rc = lib.hode_fixed_bwd(C.byref(pb.cfg), pb.n_groups, pb.batch, _ptr(pb.dose_amt), _ptr(pb.dose_t),
+                                pb.dose_t.stride(0), _ptr(pb.params), _ptr(pb.pset), pb.params.shape[0], _ptr(grid),
+                                grid.numel(), _ptr(t_eval), t_eval.numel(), _ptr(grad_h), _ptr(tape), _ptr(gy0), _ptr(gp),
+                                _stream(grad_h))
     lib.check(rc, "hode_fixed_bwd")
     return gy0, gp
 
@@ -110,10 +123,11 @@ def fixed_adjoint(lib, pb: Problem, adj_grid, adj_count, h, grad_h):
     n_t = h.shape[0]
     gy0 = torch.empty(pb.n_traj, D, dtype=torch.float32, device=dev)
     gp = torch.empty_like(pb.params)
-    rc = lib.hode_fixed_adjoint(C.byref(pb.cfg), pb.n_groups, pb.batch, _ptr(pb.dose_amt), _ptr(pb.dose_t),
-                                pb.dose_t.stride(0), _ptr(pb.params), _ptr(pb.pset), pb.params.shape[0],
-                                _ptr(adj_grid), adj_grid.numel(), _ptr(adj_count), n_t, _ptr(h), _ptr(grad_h),
-                                _ptr(gy0), _ptr(gp), _stream(grad_h))
+    with _on(grad_h):
+        rc = lib.hode_fixed_adjoint(C.byref(pb.cfg), pb.n_groups, pb.batch, _ptr(pb.dose_amt), _ptr(pb.dose_t),
+                                    pb.dose_t.stride(0), _ptr(pb.params), _ptr(pb.pset), pb.params.shape[0],
+                                    _ptr(adj_grid), adj_grid.numel(), _ptr(adj_count), n_t, _ptr(h), _ptr(grad_h),
+                                    _ptr(gy0), _ptr(gp), _stream(grad_h))
     lib.check(rc, "hode_fixed_adjoint")
     return gy0, gp
 
@@ -131,9 +145,10 @@ def dopri5_fwd(lib, pb: Problem, y0, t_eval64, tape_capacity):
     if tape_capacity:
         tape_t = torch.empty(n_ctrl, tape_capacity, 2, dtype=torch.float64, device=dev)
         tape_y = torch.empty(tape_capacity, pb.n_traj, D, dtype=torch.float32, device=dev)
-    rc = lib.hode_dopri5_fwd(C.byref(pb.cfg), pb.n_groups, pb.batch, _ptr(y0), _ptr(pb.dose_amt), _ptr(pb.dose_t),
-                             pb.dose_t.stride(0), _ptr(pb.params), _ptr(pb.pset), _ptr(t_eval64), n_t, _ptr(h),
-                             _ptr(tape_t), _ptr(tape_y), int(tape_capacity or 0), _ptr(stats), _stream(y0))
+    with _on(y0):
+        rc = lib.hode_dopri5_fwd(C.byref(pb.cfg), pb.n_groups, pb.batch, _ptr(y0), _ptr(pb.dose_amt), _ptr(pb.dose_t),
+                                 pb.dose_t.stride(0), _ptr(pb.params), _ptr(pb.pset), _ptr(t_eval64), n_t, _ptr(h),
+                                 _ptr(tape_t), _ptr(tape_y), int(tape_capacity or 0), _ptr(stats), _stream(y0))
     lib.check(rc, "hode_dopri5_fwd")
     return h, stats, (tape_t, tape_y) if tape_capacity else None
 
@@ -145,10 +160,11 @@ def dopri5_bwd(lib, pb: Problem, t_eval64, grad_h, tape, stats):
     tape_t, tape_y = tape
     gy0 = torch.empty(pb.n_traj, D, dtype=torch.float32, device=dev)
     gp = torch.empty_like(pb.params)
-    rc = lib.hode_dopri5_bwd(C.byref(pb.cfg), pb.n_groups, pb.batch, _ptr(pb.dose_amt), _ptr(pb.dose_t),
-                             pb.dose_t.stride(0), _ptr(pb.params), _ptr(pb.pset), pb.params.shape[0], _ptr(t_eval64),
-                             t_eval64.numel(), _ptr(grad_h), _ptr(tape_t), _ptr(tape_y), tape_t.shape[1], _ptr(stats),
-                             _ptr(gy0), _ptr(gp), _stream(grad_h))
+    with _on(grad_h):
+        rc = lib.hode_dopri5_bwd(C.byref(pb.cfg), pb.n_groups, pb.batch, _ptr(pb.dose_amt), _ptr(pb.dose_t),
+                                 pb.dose_t.stride(0), _ptr(pb.params), _ptr(pb.pset), pb.params.shape[0], _ptr(t_eval64),
+                                 t_eval64.numel(), _ptr(grad_h), _ptr(tape_t), _ptr(tape_y), tape_t.shape[1], _ptr(stats),
+                                 _ptr(gy0), _ptr(gp), _stream(grad_h))
     lib.check(rc, "hode_dopri5_bwd")
     return gy0, gp
 
@@ -166,8 +182,9 @@ def decode_sse(lib, h, W, b, x, mask, n_norm, want_grads=True):
         gh = torch.empty_like(h)
         gw = torch.empty(obs, D, dtype=torch.float32, device=dev)
         gb = torch.empty(obs, dtype=torch.float32, device=dev)
-    rc = lib.hode_decode_sse(D, obs, n_t, n_traj, float(n_norm), _ptr(h), _ptr(W), _ptr(b), _ptr(x), _ptr(mask),
-                             x.stride(0), x.stride(1), x.stride(2), _ptr(loss), _ptr(gh), _ptr(gw), _ptr(gb), _stream(h))
+    with _on(h):
+        rc = lib.hode_decode_sse(D, obs, n_t, n_traj, float(n_norm), _ptr(h), _ptr(W), _ptr(b), _ptr(x), _ptr(mask),
+                                 x.stride(0), x.stride(1), x.stride(2), _ptr(loss), _ptr(gh), _ptr(gw), _ptr(gb), _stream(h))
     lib.check(rc, "hode_decode_sse")
     return loss, gh, gw, gb
 
@@ -181,7 +198,8 @@ def crps_ensemble(lib, truth, forecasts):
     if f.stride(0) != n_mc * f.stride(1) and not f.is_contiguous():
         f = f.contiguous()
     out = torch.empty_like(t)
-    rc = lib.hode_crps_ensemble(_ptr(t), _ptr(f), t.numel(), n_mc, f.stride(0), f.stride(1), _ptr(out), _stream(t))
+    with _on(t):
+        rc = lib.hode_crps_ensemble(_ptr(t), _ptr(f), t.numel(), n_mc, f.stride(0), f.stride(1), _ptr(out), _stream(t))
     lib.check(rc, "hode_crps_ensemble")
     return out.reshape(truth.shape)
 
@@ -195,8 +213,9 @@ def decode_crps(lib, h, W, b, x, n_mc):
     assert x.shape == (n_t, batch, obs) and x.dtype == torch.float32
     h, W, b = _f32c(h), _f32c(W), _f32c(b)
     out = torch.empty(n_t, batch, obs, dtype=torch.float32, device=h.device)
-    rc = lib.hode_decode_crps(D, obs, n_t, batch, n_mc, _ptr(h), _ptr(W), _ptr(b), _ptr(x), x.stride(0), x.stride(1),
-                              x.stride(2), _ptr(out), _stream(h))
+    with _on(h):
+        rc = lib.hode_decode_crps(D, obs, n_t, batch, n_mc, _ptr(h), _ptr(W), _ptr(b), _ptr(x), x.stride(0), x.stride(1),
+                                  x.stride(2), _ptr(out), _stream(h))
     lib.check(rc, "hode_decode_crps")
     return out
 
@@ -207,8 +226,9 @@ def real_dose_tables(lib, field, action, params):
     assert action.dim() == 3 and action.shape[2] == 1 and action.dtype == torch.float32
     T, B = action.shape[0], action.shape[1]
     tab = torch.empty(2 if field == L.FIELD_ROCHE_REAL else 1, T + 1, B, dtype=torch.float32, device=action.device)
-    rc = lib.hode_real_dose_tables(int(field), _ptr(action), action.stride(0), action.stride(1), T, B, _ptr(params),
-                                   _ptr(tab), _stream(action))
+    with _on(action):
+        rc = lib.hode_real_dose_tables(int(field), _ptr(action), action.stride(0), action.stride(1), T, B, _ptr(params),
+                                       _ptr(tab), _stream(action))
     lib.check(rc, "hode_real_dose_tables")
     return tab
 
@@ -219,9 +239,10 @@ def real_fixed_fwd(lib, field, D, hidden, method, perturb, y0, tab, params, grid
     n_t, n_grid = t_eval.numel(), grid.numel()
     h = torch.empty(n_t, B, D, dtype=torch.float32, device=y0.device)
     tape = torch.empty(max(n_grid - 1, 0), B, D, dtype=torch.float32, device=y0.device) if want_tape else None
-    rc = lib.hode_real_fixed_fwd(int(field), D, int(hidden), int(method), int(bool(perturb)), B, _ptr(y0), _ptr(tab),
-                                 tab.shape[1] - 1, _ptr(params), _ptr(grid), n_grid, _ptr(t_eval), n_t, _ptr(h),
-                                 _ptr(tape), _stream(y0))
+    with _on(y0):
+        rc = lib.hode_real_fixed_fwd(int(field), D, int(hidden), int(method), int(bool(perturb)), B, _ptr(y0), _ptr(tab),
+                                     tab.shape[1] - 1, _ptr(params), _ptr(grid), n_grid, _ptr(t_eval), n_t, _ptr(h),
+                                     _ptr(tape), _stream(y0))
     lib.check(rc, "hode_real_fixed_fwd")
     return h, tape
 
@@ -231,8 +252,9 @@ def real_fixed_bwd(lib, field, D, hidden, method, perturb, tab, params, grid, t_
     B = grad_h.shape[1]
     gy0 = torch.empty(B, D, dtype=torch.float32, device=grad_h.device)
     gp = torch.empty_like(params)
-    rc = lib.hode_real_fixed_bwd(int(field), D, int(hidden), int(method), int(bool(perturb)), B, _ptr(tab),
-                                 tab.shape[1] - 1, _ptr(params), _ptr(grid), grid.numel(), _ptr(t_eval), t_eval.numel(),
-                                 _ptr(grad_h), _ptr(tape), _ptr(gy0), _ptr(gp), _stream(grad_h))
+    with _on(grad_h):
+        rc = lib.hode_real_fixed_bwd(int(field), D, int(hidden), int(method), int(bool(perturb)), B, _ptr(tab),
+                                     tab.shape[1] - 1, _ptr(params), _ptr(grid), grid.numel(), _ptr(t_eval), t_eval.numel(),
+                                     _ptr(grad_h), _ptr(tape), _ptr(gy0), _ptr(gp), _stream(grad_h))
     lib.check(rc, "hode_real_fixed_bwd")
     return gy0, gp

@@ -1,6 +1,7 @@
 """Import the reference's own ``model.py`` UNMODIFIED, with the two missing third-party modules injected.
 
-TEST INFRASTRUCTURE ONLY.  Works only where ``/root/reference`` exists (this container, never the GPU box).
+TEST INFRASTRUCTURE ONLY.  The tree is ``/root/reference`` where that exists (the build container) and otherwise the
+byte-identical copy ``baseline/_ref`` made by ``oracle/install_reference.py`` (git-ignored; it travels to the GPU box).
 ``model.py:10`` needs ``torchdiffeq`` and ``training_utils.py:4`` needs ``properscoring``; neither is installable
 offline, so ``oracle.odeint`` stands in for the former and a minimal ``crps_ensemble`` for the latter.
 """
@@ -11,7 +12,9 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("HODE_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = [os.environ.get("HODE_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "baseline", "_ref")]
+REFERENCE_ROOT = next((c for c in _CANDIDATES if c and os.path.isfile(os.path.join(c, "model.py"))), "/root/reference")
 
 
 def available() -> bool:
