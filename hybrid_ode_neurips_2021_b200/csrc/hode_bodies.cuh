@@ -50,6 +50,10 @@ struct SolveArgs {
 // extra live state costs more than the hidden latency (measured: dopri5 reverse sweep 11.9 -> 13.4 ms at the C3 shape).
 template <class F> struct TapePrefetch { static constexpr bool value = false; };
 template <int D_, bool H_, bool A_> struct TapePrefetch<Roche<D_, H_, A_>> { static constexpr bool value = Roche<D_, H_, A_>::P <= 64; };
+// dopri5 reverse sweep: always for the RocheODE field (at D = 12 the stage rows live in shared memory and the cooperative
+// accumulators take 14 registers, so the D + 4 registers of the prefetched entry fit)
+template <class F> struct TapePrefetchD5 { static constexpr bool value = false; };
+template <int D_, bool H_, bool A_> struct TapePrefetchD5<Roche<D_, H_, A_>> { static constexpr bool value = true; };
 
 // ---- vector load/store of one trajectory's D contiguous floats ------------------------------------------------
 template <int D>
@@ -274,22 +278,56 @@ HODE_HD void fixed_adj_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t i
 
 // ==============================================================================================================
 // dopri5 forward (tde rk_common.py RKAdaptiveStepsizeODESolver)
+//   k      storage of the 7 stage derivatives (RowsReg: registers, loops unrolled; RowsMem: shared memory, loops rolled)
 //   idx    trajectory this thread integrates (clamped to a real one for padding threads)
 //   valid  false for padding threads: they follow the group's control flow but contribute 0 and write nothing
 //   ctrl   controller index (group or trajectory); leader writes the controller-level records
 //   count  number of state elements under one controller (batch*D or D): the RMS norm is over all of them
+// Comm: sum1 / sum2 (sum over the controller group, identical in every thread of the group) and any().
 // ==============================================================================================================
-template <class F, class PS, class Dose, class Comm>
-HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds, int64_t idx,
+template <int D>
+HODE_HD bool any_nonfinite(const float (&v)[D]) {
+    // 0 * x is NaN exactly when x is inf or NaN: one FMA chain instead of D classifications
+    float z = 0.0f;
+#pragma unroll
+    for (int d = 0; d < D; ++d) z = fmaf(0.0f, v[d], z);
+    return z != z;
+}
+
+// Stage inputs of one attempt: Y_i = y0 + sum_{j <= i} k_j (beta[i][j] dt), j ascending (tde: `y0 + k[..., :i+1] @ (beta_i*dt)`).
+// Rows 0 .. i-1 come from storage, row i (`klast`) is still in registers from the evaluation that produced it.
+template <int D, bool UNROLL, class KS>
+HODE_HD void d5_stage_input(const KS& k, int i, float dtf, const float (&y0)[D], const float (&klast)[D], float (&yi)[D]) {
+    float acc[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] = 0.0f;
+    range_up<UNROLL, 6>(0, i, [&](int j) {
+        float row[D];
+        k.load(j, row);
+        v_axpy<D>(acc, mul_rn(d5_beta(i, j), dtf), row, acc);
+    });
+    v_axpy<D>(acc, mul_rn(d5_beta(i, i), dtf), klast, acc);
+    v_add<D>(yi, y0, acc);
+}
+HODE_HD float d5_stage_time(int i, float t0f, float dtf, float t1f) {
+    const float al = d5_alpha(i);
+    return (al == 1.0f) ? t_prev(t1f) : add_rn(t0f, mul_rn(al, dtf));
+}
+
+// ROLLED: stage loops rolled (needs run-time row indices: RowsMem) instead of unrolled
+template <class F, bool ROLLED, class PS, class Dose, class Comm, class KS>
+HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds, KS& k, int64_t idx,
                              bool valid, int64_t ctrl, bool leader, float count) {
     constexpr int D = F::D;
+    constexpr bool UNROLL = !ROLLED;
+    static_assert(UNROLL || KS::kDynamic, "rolled stage loops need rows that can be indexed at run time");
+    static_assert(D % 2 == 0, "packed stage combination assumes even D");
     const int64_t n_traj = a.n_groups * a.batch;
-    const Dopri5Tab T = dopri5_tab();
     const float rtol = a.rtol_f, atol = a.atol_f;
+    const float inv_count = 1.0f / count;
+    const float safety = (float)a.safety, ifactor = (float)a.ifactor, dfactor = (float)a.dfactor;
 
-    float y0[D], y1[D];
-    StageRegs<D> ks;
-    float (&k)[7][D] = ks.v;
+    float y0[D], y1[D], klast[D];
     load_vec<D>(a.y0 + idx * D, y0);
     if (valid) store_vec<D>(a.h_out + idx * D, y0);
     const bool poisoned = !F::params_ok(sp);  // kernel variant and parameters disagree: HODE_SOLVE_NONFINITE
@@ -300,7 +338,8 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds
 
     double t0 = a.t_eval_d[0];
     const float t0f_init = (float)t0;
-    F::eval(sp, t0f_init, ds, y0, k[0]);  // f0 = func(t[0], y0)
+    F::eval(sp, t0f_init, ds, y0, klast);  // f0 = func(t[0], y0)
+    k.store(0, klast);
 
     // ---- _select_initial_step (all float32) ----------------------------------------------------------------
     double dt;
@@ -312,7 +351,7 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds
 #pragma unroll
         for (int d = 0; d < D; ++d) {
             scale[d] = atol + fabsf(y0[d]) * rtol;
-            const float q0 = y0[d] / scale[d], q1 = k[0][d] / scale[d];
+            const float q0 = y0[d] / scale[d], q1 = klast[d] / scale[d];
             s0 += q0 * q0;
             s1 += q1 * q1;
         }
@@ -324,16 +363,16 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds
         else h0 = (0.01f * d0) / d1;
         float f1[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) y1[d] = y0[d] + h0 * k[0][d];
+        for (int d = 0; d < D; ++d) y1[d] = y0[d] + h0 * klast[d];
         F::eval(sp, add_rn(t0f_init, h0), ds, y1, f1);
-        float s2 = 0.0f, dummy = 0.0f;
+        float s2 = 0.0f;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            const float q = (f1[d] - k[0][d]) / scale[d];
+            const float q = (f1[d] - klast[d]) / scale[d];
             s2 += q * q;
         }
         if (!valid) s2 = 0.0f;
-        cm.sum2(s2, dummy);
+        cm.sum1(s2);
         const float d2 = sqrtf(s2 / count) / h0;
         float h1;
         if (d1 <= 1e-15f && d2 <= 1e-15f) {
@@ -342,52 +381,58 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds
             const float dm = (d2 > d1) ? d2 : d1;  // python max(d1, d2)
             h1 = powf(0.01f / dm, 0.2f);
         }
-        const float hh = 100.0f * h0;
-        // torch.min propagates NaN
-        dt = (double)((hh != hh || h1 != h1) ? (hh + h1) : (hh < h1 ? hh : h1));
+        dt = (double)nan_minf(100.0f * h0, h1);  // torch.min propagates NaN
     }
 
     int j = 1, nacc = 0, nrej = 0, status = HODE_SOLVE_OK;
-    int64_t n_steps = 0, attempts = 0;
-    float bad0 = 0.0f, dummy0 = 0.0f;
-#pragma unroll
-    for (int d = 0; d < D; ++d) bad0 += isfinite(y0[d]) ? 0.0f : 1.0f;
-    if (!valid) bad0 = 0.0f;
-    cm.sum2(bad0, dummy0);
-    bool y0_bad = bad0 > 0.0f;
+    // int32 counters (the caps are clamped: torchdiffeq's default max_num_steps is 2**31 - 1)
+    const int max_steps = (int)(a.max_num_steps < 0x7fffffffLL ? a.max_num_steps : 0x7fffffffLL);
+    const int attempt_cap = (int)(a.attempt_cap < 0x7fffffffLL ? a.attempt_cap : 0x7fffffffLL);
+    int n_steps = 0, attempts = 0;
+    bool y0_bad = cm.any(valid && any_nonfinite<D>(y0));
 
     while (j < a.n_t) {
         // _advance(t[j]): while next_t > rk_state.t1 -> _adaptive_step
         if (poisoned) { status = HODE_SOLVE_NONFINITE; break; }
-        if (n_steps >= a.max_num_steps || attempts >= a.attempt_cap) { status = HODE_SOLVE_MAX_STEPS; break; }
+        if (n_steps >= max_steps || attempts >= attempt_cap) { status = HODE_SOLVE_MAX_STEPS; break; }
         if (!(t0 + dt > t0)) { status = HODE_SOLVE_DT_UNDERFLOW; break; }
         if (y0_bad) { status = HODE_SOLVE_NONFINITE; break; }
         const double t1 = t0 + dt;
         const float t0f = (float)t0, dtf = (float)dt, t1f = (float)t1;
-        dopri5_stages<F>(sp, ds, T, t0f, dtf, t1f, y0, ks, y1);
-        // error estimate and ratio
-        float ss = 0.0f, bad = 0.0f;
+        // ---- the 6 new stages (row 0 holds f0: FSAL); the error estimate k @ (dt c_error) is accumulated on the fly,
+        //      in stage order, while each k_i is still in registers --------------------------------------------------
         float err[D];
 #pragma unroll
-        for (int d = 0; d < D; d += 2) {
-            float e0 = 0.0f, e1 = 0.0f;
-#pragma unroll
-            for (int i = 0; i < 7; ++i) fma2s(mul_rn(dtf, T.c_err[i]), k[i][d], k[i][d + 1], e0, e1, e0, e1);
-            err[d] = e0; err[d + 1] = e1;
-        }
+        for (int d = 0; d < D; ++d) err[d] = 0.0f;
+        k.load(0, klast);
+        stage_up<UNROLL, 0, 6>([&](auto il) {
+            float ti;
+            stage_switch<ROLLED, 6>(il, [&](auto ic) {  // ic: compile-time stage index in both variants
+                const int i = ic;
+                d5_stage_input<D, true>(k, i, dtf, y0, klast, y1);
+                v_axpy<D>(err, mul_rn(dtf, d5_cerr(i)), klast, err);
+                ti = d5_stage_time(i, t0f, dtf, t1f);
+            });
+            F::eval(sp, ti, ds, y1, klast);
+            k.store((int)il + 1, klast);
+        });
+        v_axpy<D>(err, mul_rn(dtf, d5_cerr(6)), klast, err);  // y1 = last stage input, klast = k7 = f1
+        // ---- error ratio: rms(err / (atol + rtol max(|y0|, |y1|))) over the controller group.  torch.max propagates
+        //      NaN: a NaN in y1 poisons the tolerance, hence the ratio, hence the step is rejected like in tde and dt
+        //      becomes NaN ('underflow in dt nan').  tde additionally asserts isfinite(y0) at the start of every attempt;
+        //      after the first attempt that can only trigger for a state that overflowed to +-inf WITHOUT producing a NaN
+        //      in the error estimate (|y| ~ 1e38), which here ends as 'underflow in dt' a few attempts later -- the
+        //      group-wide test per accepted step was ~100 instructions of warp votes for that one message -------------
+        float ss = 0.0f;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-            const float e = err[d];
-            const float tol = atol + rtol * fmaxf(fabsf(y0[d]), fabsf(y1[d]));
-            const float q = e / tol;
-            ss += q * q;
-            bad += isfinite(y1[d]) ? 0.0f : 1.0f;
+            const float tol = fmaf(rtol, nan_maxf(fabsf(y0[d]), fabsf(y1[d])), atol);
+            const float q = div_tol(err[d], tol);
+            ss = fmaf(q, q, ss);
         }
-        // fmaxf drops NaN; torch.max propagates it.  A NaN in y1 must poison the ratio like it does in the reference.
-        if (bad > 0.0f) ss = nanf("");
-        if (!valid) { ss = 0.0f; bad = 0.0f; }
-        cm.sum2(ss, bad);
-        const float ratio = fabsf(sqrtf(ss / count));
+        if (!valid) ss = 0.0f;
+        cm.sum1(ss);
+        const float ratio = fast_sqrt(ss * inv_count);
         const bool accept = ratio <= 1.0f;
         ++attempts; ++n_steps;
         if (accept) {
@@ -401,19 +446,29 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds
             }
             ++nacc;
             if (a.t_eval_d[j] <= t1) {
-                // _interp_fit
-                float ca[D], cb[D], cc[D], cd[D];
+                // _interp_fit: y_mid = y0 + k @ (dt c_mid)
+                float ca[D], cb[D], cc[D], cd[D], f0[D];
+                {
+                    float m[D];
 #pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    float m = 0.0f;
+                    for (int d = 0; d < D; ++d) m[d] = 0.0f;
+                    range_up<UNROLL, 7>(0, 7, [&](int i) {
+                        float row[D];
+                        k.load(i, row);
+                        const float c = mul_rn(dtf, d5_cmid(i));
 #pragma unroll
-                    for (int i = 0; i < 7; ++i) m = fmaf(k[i][d], mul_rn(dtf, T.c_mid[i]), m);
-                    const float ymid = y0[d] + m;
-                    const float f0 = k[0][d], f1 = k[6][d];
-                    ca[d] = 2.0f * dtf * (f1 - f0) - 8.0f * (y1[d] + y0[d]) + 16.0f * ymid;
-                    cb[d] = dtf * (5.0f * f0 - 3.0f * f1) + 18.0f * y0[d] + 14.0f * y1[d] - 32.0f * ymid;
-                    cc[d] = dtf * (f1 - 4.0f * f0) - 11.0f * y0[d] - 5.0f * y1[d] + 16.0f * ymid;
-                    cd[d] = dtf * f0;
+                        for (int d = 0; d < D; ++d) m[d] = fmaf(row[d], c, m[d]);
+                    });
+                    k.load(0, f0);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        const float ymid = y0[d] + m[d];
+                        const float f1 = klast[d];
+                        ca[d] = 2.0f * dtf * (f1 - f0[d]) - 8.0f * (y1[d] + y0[d]) + 16.0f * ymid;
+                        cb[d] = dtf * (5.0f * f0[d] - 3.0f * f1) + 18.0f * y0[d] + 14.0f * y1[d] - 32.0f * ymid;
+                        cc[d] = dtf * (f1 - 4.0f * f0[d]) - 11.0f * y0[d] - 5.0f * y1[d] + 16.0f * ymid;
+                        cd[d] = dtf * f0[d];
+                    }
                 }
                 while (j < a.n_t && a.t_eval_d[j] <= t1) {
                     // _interp_evaluate
@@ -433,14 +488,14 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds
                     n_steps = 0;
                 }
             }
+            k.store(0, klast);  // FSAL: f0 of the next step is f1 of this one
 #pragma unroll
-            for (int d = 0; d < D; ++d) { y0[d] = y1[d]; k[0][d] = k[6][d]; }
+            for (int d = 0; d < D; ++d) y0[d] = y1[d];
             t0 = t1;
-            y0_bad = bad > 0.0f;
         } else {
             ++nrej;
         }
-        dt = optimal_step(dt, ratio, a.safety, a.ifactor, a.dfactor);
+        dt = optimal_step(dt, ratio, safety, ifactor, dfactor);
     }
     if (leader) {
         hode_stats st;
@@ -451,137 +506,190 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds
 
 // ==============================================================================================================
 // dopri5 reverse sweep over the tape (discrete adjoint of the accepted-step map with constant step sizes, through
-// FSAL and the quartic dense output).  SURVEY.md Appendix D.4.
+// FSAL and the quartic dense output).  SURVEY.md Appendix D.4, reorganised so that a step needs 9 rows of D floats
+// instead of 7 stage derivatives + 7 stage adjoints:
+//   rows 0..5  k_1..k_6 of the step (recomputed from the tape entry); row i is OVERWRITTEN by G_i = J(Y_i)^T kbar_i once
+//              stage i has been reversed -- the stage adjoints kbar_i are never stored, they are rebuilt when needed as
+//              kbar_i = dt c_mid[i] YM + dt sum_{m > i} beta[m-1][i] G_m  (m descending = the order in which the literal
+//              recurrence adds them), with G_6 = adjoint of y1;
+//   row 6      lambda (adjoint of y_{n+1}) on entry, G_6 after the last stage has been reversed;
+//   row 7      YM = adjoint of y_mid (dense outputs emitted by this step; zero otherwise);
+//   row 8      phi = adjoint of the next step's k_1, which IS this step's k_7 (FSAL).
+// `nloop` >= the number of accepted steps of this trajectory's controller: the loop is END-aligned (a thread with fewer steps
+// idles first with zero adjoints), so that n == 0 -- the one step with an eighth VJP -- is reached by all threads of a warp
+// together and every VJP call site is warp-converged (required by the cooperative accumulators).
 // ==============================================================================================================
-template <class F, bool EG, class PS, class Dose, class KS, class ACC>
-HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t idx, int64_t ctrl, ACC acc, KS& k,
-                             KS& kb, bool valid = true) {
+template <class F, bool EG, bool ROLLED, class PS, class Dose, class KS, class ACC>
+HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, KS& R, int64_t idx, int64_t ctrl, ACC acc,
+                             bool valid, int nloop) {
     constexpr int D = F::D;
+    constexpr bool UNROLL = !ROLLED;
+    static_assert(UNROLL || KS::kDynamic, "rolled stage loops need rows that can be indexed at run time");
     const int64_t n_traj = a.n_groups * a.batch;
-    const Dopri5Tab T = dopri5_tab();
-    const int nacc = a.stats[ctrl].accepted;
-    float lam[D], phi[D];
+    const int nacc = valid ? a.stats[ctrl].accepted : 0;
+    float zero[D];
 #pragma unroll
-    for (int d = 0; d < D; ++d) { lam[d] = 0.0f; phi[d] = 0.0f; }
+    for (int d = 0; d < D; ++d) zero[d] = 0.0f;
+    R.store(6, zero);
+    R.store(8, zero);
     int j = a.n_t - 1;
-    // tape entry (state, t0, dt) of step n-1 is requested while step n is being reversed (see fixed_bwd_traj)
-    constexpr bool PF = TapePrefetch<F>::value;
+    // The tape entry (state, t0, dt) of step n-1 is requested while step n is being reversed: with 2-3 warps per scheduler
+    // nothing else hides one HBM round trip per step (ncu: stall_long_scoreboard 1.0 per issue without it).
+    constexpr bool PF = TapePrefetchD5<F>::value;
     float ynext[D];
-    double t0next = 0.0, dtnext = 0.0;
-    if (PF && nacc > 0) {
-        load_vec<D>(a.tape_y + ((int64_t)(nacc - 1) * n_traj + idx) * D, ynext);
-        t0next = a.tape_t[(ctrl * a.tape_cap + nacc - 1) * 2];
-        dtnext = a.tape_t[(ctrl * a.tape_cap + nacc - 1) * 2 + 1];
-    }
-    for (int n = nacc - 1; n >= 0; --n) {
-        const double t0 = PF ? t0next : a.tape_t[(ctrl * a.tape_cap + n) * 2];
-        const double dt = PF ? dtnext : a.tape_t[(ctrl * a.tape_cap + n) * 2 + 1];
-        const double t1 = t0 + dt;
-        const float t0f = (float)t0, dtf = (float)dt, t1f = (float)t1;
-        float y0[D], y1[D], yb0[D], yb1[D], g[D], kr[D], lr[D];
+    double t0next = 0.0, dtnext = 1.0;
+    auto fetch = [&](int n, float (&y)[D], double& t0v, double& dtv) {
+        if (n >= 0 && n < nacc) {
+            t0v = a.tape_t[(ctrl * a.tape_cap + n) * 2];
+            dtv = a.tape_t[(ctrl * a.tape_cap + n) * 2 + 1];
+            load_vec<D>(a.tape_y + ((int64_t)n * n_traj + idx) * D, y);
+        } else {  // idle thread: any finite state will do (its adjoints are zero); 1 keeps pow / log of the Hill terms finite
+            t0v = 0.0; dtv = 1.0;
+#pragma unroll
+            for (int d = 0; d < D; ++d) y[d] = 1.0f;
+        }
+    };
+    if (PF) fetch(nloop - 1, ynext, t0next, dtnext);
+    for (int n = nloop - 1; n >= 0; --n) {
+        const bool act = n < nacc;
+        double t0, dt;
+        float y0[D], klast[D], Yi[D];
         if (PF) {
+            t0 = t0next; dt = dtnext;
 #pragma unroll
             for (int d = 0; d < D; ++d) y0[d] = ynext[d];
-            if (n > 0) {
-                load_vec<D>(a.tape_y + ((int64_t)(n - 1) * n_traj + idx) * D, ynext);
-                t0next = a.tape_t[(ctrl * a.tape_cap + n - 1) * 2];
-                dtnext = a.tape_t[(ctrl * a.tape_cap + n - 1) * 2 + 1];
-            }
+            fetch(n - 1, ynext, t0next, dtnext);
         } else {
-            load_vec<D>(a.tape_y + ((int64_t)n * n_traj + idx) * D, y0);
+            fetch(n, y0, t0, dt);
         }
+        const double t1 = t0 + dt;
+        const float t0f = (float)t0, dtf = (float)dt, t1f = (float)t1;
         // FSAL: k1 of step n is k7 of step n-1 = f(prev(t1_{n-1}), y1_{n-1}); step 0 uses f(t[0], y0)
-        F::eval(sp, n == 0 ? t0f : t_prev(t0f), ds, y0, kr);
-        stage_set_row<D>(k, 0, kr);
-        dopri5_stages<F>(sp, ds, T, t0f, dtf, t1f, y0, k, y1);
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-            for (int d = 0; d < D; ++d) kb.set(i, d, 0.0f);
-#pragma unroll
-        for (int d = 0; d < D; ++d) { yb1[d] = lam[d]; yb0[d] = 0.0f; kb.set(6, d, phi[d]); }
-        // dense outputs emitted by this step: t0 < t_eval[j] <= t1
-        while (j >= 1 && a.t_eval_d[j] > t0) {
-            const float x = (float)((a.t_eval_d[j] - t0) / (t1 - t0));
-            const float x2 = x * x, x3 = x2 * x, x4 = x3 * x;
-            load_vec<D>(a.grad_h + ((int64_t)j * n_traj + idx) * D, g);
-            if (!valid) {  // padding lane of a warp-cooperative accumulator: follows the control flow, contributes 0
-#pragma unroll
-                for (int d = 0; d < D; ++d) g[d] = 0.0f;
-            }
-#pragma unroll
-            for (int d = 0; d < D; ++d) {
-                const float eb = g[d], db = x * g[d], cb = x2 * g[d], bb = x3 * g[d], ab = x4 * g[d];
-                const float ymb = 16.0f * ab - 32.0f * bb + 16.0f * cb;
-                yb0[d] += eb - 8.0f * ab + 18.0f * bb - 11.0f * cb + ymb;
-                yb1[d] += -8.0f * ab + 14.0f * bb - 5.0f * cb;
-                kb.set(0, d, kb.get(0, d) + dtf * (-2.0f * ab + 5.0f * bb - 4.0f * cb + db));
-                kb.set(6, d, kb.get(6, d) + dtf * (2.0f * ab - 3.0f * bb + cb));
-#pragma unroll
-                for (int i = 0; i < 7; ++i) kb.set(i, d, fmaf(mul_rn(dtf, T.c_mid[i]), ymb, kb.get(i, d)));
-            }
-            --j;
-        }
-        // k7 = f(prev(t1), y1)
-        stage_row<D>(k, 6, kr);
-        stage_row<D>(kb, 6, lr);
-        F::template vjp<EG>(sp, t_prev(t1f), ds, y1, kr, lr, g, acc);
-#pragma unroll
-        for (int d = 0; d < D; ++d) yb1[d] += g[d];
-        // y1 = y0 + sum_{j<6} k_j * (beta[5][j]*dt)
-#pragma unroll
-        for (int d = 0; d < D; d += 2) {
-            add2(yb0[d], yb0[d + 1], yb1[d], yb1[d + 1], yb0[d], yb0[d + 1]);
-#pragma unroll
-            for (int jj = 0; jj < 6; ++jj) {
-                float o0, o1;
-                fma2s(mul_rn(T.beta[5][jj], dtf), yb1[d], yb1[d + 1], kb.get(jj, d), kb.get(jj, d + 1), o0, o1);
-                kb.set(jj, d, o0); kb.set(jj, d + 1, o1);
-            }
-        }
-        // stages k6 .. k2  (k[i] = f(t_i, Y_i), Y_i = y0 + sum_{j<i} k_j * (beta[i-1][j]*dt))
-#pragma unroll
-        for (int i = 5; i >= 1; --i) {
+        F::eval(sp, n == 0 ? t0f : t_prev(t0f), ds, y0, klast);
+        R.store(0, klast);
+        stage_up<UNROLL, 0, 5>([&](auto il) {  // k_2 .. k_6 (k_7 is only needed inside its own VJP, which recomputes it)
             float ti;
-            if (T.alpha[i - 1] == 1.0f) ti = t_prev(t1f);
-            else ti = add_rn(t0f, mul_rn(T.alpha[i - 1], dtf));
-            float Yi[D];
+            stage_switch<ROLLED, 5>(il, [&](auto ic) {
+                const int i = ic;
+                d5_stage_input<D, true>(R, i, dtf, y0, klast, Yi);
+                ti = d5_stage_time(i, t0f, dtf, t1f);
+            });
+            F::eval(sp, ti, ds, Yi, klast);
+            R.store((int)il + 1, klast);
+        });
+        // ---- dense outputs emitted by this step (t0 < t_eval[j] <= t1): adjoints of y_mid, y1 and k_7 now; those of y0
+        //      and k_1 are recomputed from grad_h at the end of the step (rare, and it keeps 2 D registers free) ---------
+        const int j_hi = j;
+        {
+            float ym[D];
 #pragma unroll
-            for (int d = 0; d < D; d += 2) {
-                float s0 = 0.0f, s1 = 0.0f;
+            for (int d = 0; d < D; ++d) ym[d] = 0.0f;
+            if (act && j >= 1 && a.t_eval_d[j] > t0) {
+                float e1[D], e6[D], g[D];
 #pragma unroll
-                for (int jj = 0; jj < i; ++jj) fma2s(mul_rn(T.beta[i - 1][jj], dtf), k.get(jj, d), k.get(jj, d + 1), s0, s1, s0, s1);
-                add2(y0[d], y0[d + 1], s0, s1, Yi[d], Yi[d + 1]);
+                for (int d = 0; d < D; ++d) { e1[d] = 0.0f; e6[d] = 0.0f; }
+                while (j >= 1 && a.t_eval_d[j] > t0) {
+                    const float x = (float)((a.t_eval_d[j] - t0) / (t1 - t0));
+                    const float x2 = x * x, x3 = x2 * x, x4 = x3 * x;
+                    load_vec<D>(a.grad_h + ((int64_t)j * n_traj + idx) * D, g);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        const float cb = x2 * g[d], bb = x3 * g[d], ab = x4 * g[d];
+                        ym[d] += 16.0f * ab - 32.0f * bb + 16.0f * cb;
+                        e1[d] += -8.0f * ab + 14.0f * bb - 5.0f * cb;
+                        e6[d] += dtf * (2.0f * ab - 3.0f * bb + cb);
+                    }
+                    --j;
+                }
+                float r[D];
+                R.load(6, r);
+                v_add<D>(r, r, e1);
+                R.store(6, r);
+                R.load(8, r);
+                v_add<D>(r, r, e6);
+                R.store(8, r);
             }
-            stage_row<D>(k, i, kr);
-            stage_row<D>(kb, i, lr);
-            F::template vjp<EG>(sp, ti, ds, Yi, kr, lr, g, acc);
+            R.store(7, ym);
+        }
+        // ---- stages k_7 .. k_2 in reverse: i = 6 is k_7 = f(prev(t1), y1), evaluated at y1 = Y_6 ----------------------
+        stage_down<UNROLL, 6, 1>([&](auto il) {
+            float cot[D], row[D], g[D], ti;
+            stage_switch<ROLLED, 7>(il, [&](auto ic) {
+                const int i = ic;
+                if (i >= 1) {
+                    {
+                        float acc_y[D];
 #pragma unroll
-            for (int d = 0; d < D; d += 2) {
-                add2(yb0[d], yb0[d + 1], g[d], g[d + 1], yb0[d], yb0[d + 1]);
+                        for (int d = 0; d < D; ++d) acc_y[d] = 0.0f;
+                        range_up<true, 6>(0, i, [&](int jj) {
+                            R.load(jj, row);
+                            v_axpy<D>(acc_y, mul_rn(d5_beta(i - 1, jj), dtf), row, acc_y);
+                        });
+                        v_add<D>(Yi, y0, acc_y);
+                    }
+                    R.load(7, row);
+                    v_scale<D>(cot, mul_rn(dtf, d5_cmid(i)), row);
+                    range_down<true, 7>(i + 1, 7, [&](int m) {
+                        R.load(m, row);
+                        v_axpy<D>(cot, mul_rn(d5_beta(m - 1, i), dtf), row, cot);
+                    });
+                    if (i == 6) {
+                        R.load(8, row);
+                        v_add<D>(cot, cot, row);
+                    }
+                    ti = d5_stage_time(i - 1, t0f, dtf, t1f);
+                }
+            });
+            const int i = il;
+            R.load(i, row);  // k_{i+1} for i < 6; lambda (+ dense-output terms) for i = 6
+            F::template vjp<EG>(sp, ti, ds, Yi, i == 6 ? nullptr : (const float*)row, cot, g, acc);
+            if (i == 6) v_add<D>(g, g, row);
+            R.store(i, g);
+        });
+        // ---- adjoint of k_1 and of y0 ---------------------------------------------------------------------------------
+        float kb0[D], yb0[D];
+        {
+            float row[D];
+            R.load(7, row);
+            v_scale<D>(kb0, mul_rn(dtf, d5_cmid(0)), row);
 #pragma unroll
-                for (int jj = 0; jj < i; ++jj) {
-                    float o0, o1;
-                    fma2s(mul_rn(T.beta[i - 1][jj], dtf), g[d], g[d + 1], kb.get(jj, d), kb.get(jj, d + 1), o0, o1);
-                    kb.set(jj, d, o0); kb.set(jj, d + 1, o1);
+            for (int d = 0; d < D; ++d) yb0[d] = 0.0f;
+            range_down<UNROLL, 7>(1, 7, [&](int m) {
+                R.load(m, row);
+                v_axpy<D>(kb0, mul_rn(d5_beta(m - 1, 0), dtf), row, kb0);
+                v_add<D>(yb0, yb0, row);
+            });
+        }
+        if (j != j_hi) {  // dense-output terms of y0 and k_1 (e = y0, d = dt f0 and their share of c, b, a)
+            float g[D];
+            for (int jo = j_hi; jo > j; --jo) {
+                const float x = (float)((a.t_eval_d[jo] - t0) / (t1 - t0));
+                const float x2 = x * x, x3 = x2 * x, x4 = x3 * x;
+                load_vec<D>(a.grad_h + ((int64_t)jo * n_traj + idx) * D, g);
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const float db = x * g[d], cb = x2 * g[d], bb = x3 * g[d], ab = x4 * g[d];
+                    yb0[d] += g[d] - 8.0f * ab + 18.0f * bb - 11.0f * cb + (16.0f * ab - 32.0f * bb + 16.0f * cb);
+                    kb0[d] += dtf * (-2.0f * ab + 5.0f * bb - 4.0f * cb + db);
                 }
             }
         }
         if (n == 0) {
-            stage_row<D>(k, 0, kr);
-            stage_row<D>(kb, 0, lr);
-            F::template vjp<EG>(sp, t0f, ds, y0, kr, lr, g, acc);
-#pragma unroll
-            for (int d = 0; d < D; ++d) yb0[d] += g[d];
-        } else {
-#pragma unroll
-            for (int d = 0; d < D; ++d) phi[d] = kb.get(0, d);
+            float row[D], g[D];
+            R.load(0, row);
+            F::template vjp<EG>(sp, t0f, ds, y0, (const float*)row, kb0, g, acc);
+            v_add<D>(yb0, yb0, g);
         }
+        if (!act) {
 #pragma unroll
-        for (int d = 0; d < D; ++d) lam[d] = yb0[d];
+            for (int d = 0; d < D; ++d) { yb0[d] = 0.0f; kb0[d] = 0.0f; }
+        }
+        R.store(6, yb0);  // lambda of the previous step
+        R.store(8, kb0);  // phi of the previous step
     }
     if (!valid) return;
-    float g0[D];
+    float lam[D], g0[D];
+    R.load(6, lam);
     load_vec<D>(a.grad_h + idx * D, g0);
 #pragma unroll
     for (int d = 0; d < D; ++d) lam[d] += g0[d];
@@ -590,14 +698,6 @@ HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t 
         for (int d = 0; d < D; ++d) lam[d] = nanf("");
     }
     store_vec<D>(a.grad_y0 + idx * D, lam);
-}
-
-// register-resident stage storage (the default)
-template <class F, bool EG, class PS, class Dose, class ACC>
-HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t idx, int64_t ctrl, ACC acc,
-                             bool valid = true) {
-    StageRegs<F::D> k, kb;
-    dopri5_bwd_traj<F, EG>(a, sp, ds, idx, ctrl, acc, k, kb, valid);
 }
 
 }  // namespace hode

@@ -228,6 +228,30 @@ enum RocheIdx {
     R_NSCALAR
 };
 
+// Warp-cooperative accumulation of the ml_net weight gradients for the wide hybrid field (D = 12: 96 + 8 = 104
+// accumulators; kept per thread they push the reverse sweeps to 255 registers plus 1.5 - 1.9 KB of local-memory spills).
+// Every lane still owns one trajectory.  Per vjp call each lane publishes u = l (1 - s^2) [ML] and the stage input
+// y [D] to a warp-private staging area; after a __syncwarp lane L accumulates, for ITS block of the gradient -- hidden-unit
+// pair jb = (L & 7) >> 1, input columns 6 db .. 6 db + 5 with db = L & 1 -- the contributions of 8 of the warp's 32
+// trajectories (tg = L >> 3 selects which): 16 LDS.128 + 48 packed FMAs for 14 accumulator registers.  The four partial
+// sums per entry meet in shared memory when the kernel flushes.  Call sites must be warp-converged.
+template <int D_>
+struct RocheCoop {
+    static constexpr int ML = D_ - 4;
+    static constexpr int NJB = ML / 2;                 // hidden-unit pairs
+    static constexpr int SU = 68;                      // floats per unit-pair row: [32 trajectories][2] + pad (bank spread)
+    static constexpr int SY = 36;                      // floats per input row: [32 trajectories] + pad
+    static constexpr int kStageFloats = NJB * SU + D_ * SY;  // per warp
+    static constexpr int NE = 16;                      // expert-scalar accumulators (13 + theta_1, theta_2 of the ablation)
+    static_assert(D_ == 12, "lane -> block mapping below is written for D = 12 (4 unit pairs x 2 column halves x 4 groups)");
+    float* stage;  // warp-private: U [NJB][32][2] (row stride SU), Y [D][32] (row stride SY)
+    int lane;
+    float w[6][2];  // dW[2 jb + {0, 1}][6 db + c]
+    float b[2];     // db[2 jb + {0, 1}] (identical in the two db lanes; flushed by db == 0)
+    float e[NE];    // expert scalars (only touched when EG)
+    bool mute;      // true: the call only needs J^T l (zero-weight stage of the continuous adjoint)
+};
+
 // ABLATE_: the ablation study's expert part (model.py:545-549): dx = (R, -D theta_1, Q, -I theta_2); theta_1, theta_2 are
 // appended to the packed parameters.
 template <int D_, bool HILL2_ = false, bool ABLATE_ = false>
@@ -306,11 +330,11 @@ struct Roche {
         }
     }
 
-    // gy = J^T l ; acc += d<l, f>/dtheta.  `k` (may be null) is f(t, y) if the caller already has it: its ML part is
-    // tanh(W y + b), which is all the MLP backward needs.  EG: also accumulate the 13 expert scalars.
-    template <bool EG, class PS, class Dose>
-    HODE_HD static void vjp(PS sp, float t, const Dose& ds, const float (&y)[D_], const float* k,
-                            const float (&l)[D_], float (&gy)[D_], float* acc) {
+    // expert part of gy = J^T l and of the expert-scalar gradients (EG); ML columns of gy are zeroed
+    // TH: index of theta_1 in `acc` (OFF_TH in a packed-parameter accumulator, R_NSCALAR in a compact expert-only one)
+    template <bool EG, int TH, class PS, class Dose>
+    HODE_HD static void vjp_expert(PS sp, float t, const Dose& ds, const float (&y)[D_], const float (&l)[D_],
+                                   float (&gy)[D_], float* acc) {
         if (ABLATE) {
             gy[0] = -l[1] * sp[OFF_TH];
             gy[1] = l[0];
@@ -319,8 +343,8 @@ struct Roche {
 #pragma unroll
             for (int d = 4; d < D_; ++d) gy[d] = 0.0f;
             if (EG) {
-                acc[OFF_TH] -= l[1] * y[0];
-                acc[OFF_TH + 1] -= l[3] * y[2];
+                acc[TH] -= l[1] * y[0];
+                acc[TH + 1] -= l[3] * y[2];
             }
         } else {
             const float dis = y[0], react = y[1], imm = y[2], dose2 = y[3];
@@ -337,7 +361,7 @@ struct Roche {
             gy[1] = fmaf(-l0d, kdcir, fmaf(l1, fmaf(dis, kfb, hill_d) - fmaf(dose2, kdexa, sp[R_KOFF]), l2 * sp[R_KIM]));
             gy[2] = -l0d * kdci * hdpow(imm, hc);
             gy[3] = fmaf(-l1 * react, kdexa, -l3 * kel);
-    #pragma unroll
+#pragma unroll
             for (int d = 4; d < D_; ++d) gy[d] = 0.0f;
             if (EG) {
                 const float ec50 = sp[R_EC50];
@@ -359,38 +383,98 @@ struct Roche {
                 acc[R_KEL] += l3 * (dose - dose2 + kel * roche_dose_dkel(ds, t, kel, sp[OFF_KL2]));
             }
         }
+    }
+    // hidden-unit pair (j, j+1): s = tanh(W y + b) (from k when the caller has f(t, y)), u = l (1 - s^2), gy += W^T u
+    template <class PS>
+    HODE_HD static void vjp_unit_pair(PS sp, int j, const float (&y)[D_], const float* k, const float (&l)[D_],
+                                      float (&gy)[D_], float& u0, float& u1) {
+        float s0, s1;
+        if (k != nullptr) {
+            s0 = k[4 + j]; s1 = k[4 + j + 1];
+        } else {
+            float a0 = sp[OFF_BT + j], a1 = sp[OFF_BT + j + 1];
+#pragma unroll
+            for (int d = 0; d < D_; ++d)
+                fma2s(y[d], sp[OFF_WT + ((j >> 1) * D_ + d) * 2], sp[OFF_WT + ((j >> 1) * D_ + d) * 2 + 1], a0, a1, a0, a1);
+            tanh_pre2(a0, a1, s0, s1);
+        }
+        // u = l (1 - s^2);  uw = u / kTanhPre (the staged weights carry the factor kTanhPre)
+        float q0, q1, uw0, uw1;
+        fma2(-s0, -s1, s0, s1, 1.0f, 1.0f, q0, q1);
+        mul2(l[4 + j], l[4 + j + 1], q0, q1, u0, u1);
+        mul2(u0, u1, kTanhPreInv, kTanhPreInv, uw0, uw1);
+#pragma unroll
+        for (int d = 0; d < D_; d += 2)
+            fma2s(uw0, sp[OFF_WR + j * D_ + d], sp[OFF_WR + j * D_ + d + 1], gy[d], gy[d + 1], gy[d], gy[d + 1]);
+#pragma unroll
+        for (int d = 0; d < D_; d += 2)
+            fma2s(uw1, sp[OFF_WR + (j + 1) * D_ + d], sp[OFF_WR + (j + 1) * D_ + d + 1], gy[d], gy[d + 1], gy[d], gy[d + 1]);
+    }
+
+    // gy = J^T l ; acc += d<l, f>/dtheta.  `k` (may be null) is f(t, y) if the caller already has it: its ML part is
+    // tanh(W y + b), which is all the MLP backward needs.  EG: also accumulate the 13 expert scalars.
+    template <bool EG, class PS, class Dose>
+    HODE_HD static void vjp(PS sp, float t, const Dose& ds, const float (&y)[D_], const float* k,
+                            const float (&l)[D_], float (&gy)[D_], float* acc) {
+        vjp_expert<EG, OFF_TH>(sp, t, ds, y, l, gy, acc);
 #pragma unroll
         for (int j = 0; j < ML; j += 2) {
-            float s0, s1;
-            if (k != nullptr) {
-                s0 = k[4 + j]; s1 = k[4 + j + 1];
-            } else {
-                float a0 = sp[OFF_BT + j], a1 = sp[OFF_BT + j + 1];
-#pragma unroll
-                for (int d = 0; d < D_; ++d)
-                    fma2s(y[d], sp[OFF_WT + ((j >> 1) * D_ + d) * 2], sp[OFF_WT + ((j >> 1) * D_ + d) * 2 + 1], a0, a1, a0, a1);
-                tanh_pre2(a0, a1, s0, s1);
-            }
-            // u = l (1 - s^2);  uw = u / kTanhPre (the staged weights carry the factor kTanhPre)
-            float q0, q1, u0, u1, uw0, uw1;
-            fma2(-s0, -s1, s0, s1, 1.0f, 1.0f, q0, q1);
-            mul2(l[4 + j], l[4 + j + 1], q0, q1, u0, u1);
-            mul2(u0, u1, kTanhPreInv, kTanhPreInv, uw0, uw1);
+            float u0, u1;
+            vjp_unit_pair(sp, j, y, k, l, gy, u0, u1);
 #pragma unroll
             for (int d = 0; d < D_; d += 2) {
-                fma2s(uw0, sp[OFF_WR + j * D_ + d], sp[OFF_WR + j * D_ + d + 1], gy[d], gy[d + 1], gy[d], gy[d + 1]);
                 fma2s(u0, y[d], y[d + 1], acc[OFF_W + j * D_ + d], acc[OFF_W + j * D_ + d + 1],
                       acc[OFF_W + j * D_ + d], acc[OFF_W + j * D_ + d + 1]);
-            }
-#pragma unroll
-            for (int d = 0; d < D_; d += 2) {
-                fma2s(uw1, sp[OFF_WR + (j + 1) * D_ + d], sp[OFF_WR + (j + 1) * D_ + d + 1], gy[d], gy[d + 1], gy[d], gy[d + 1]);
                 fma2s(u1, y[d], y[d + 1], acc[OFF_W + (j + 1) * D_ + d], acc[OFF_W + (j + 1) * D_ + d + 1],
                       acc[OFF_W + (j + 1) * D_ + d], acc[OFF_W + (j + 1) * D_ + d + 1]);
             }
             add2(acc[OFF_B + j], acc[OFF_B + j + 1], u0, u1, acc[OFF_B + j], acc[OFF_B + j + 1]);
         }
     }
+
+#if HODE_DEVICE_BUILD && defined(__CUDA_ARCH__)
+    // same VJP, ml_net gradients accumulated warp-cooperatively (RocheCoop above); all 32 lanes must call together
+    template <bool EG, class PS, class Dose>
+    HODE_D static void vjp(PS sp, float t, const Dose& ds, const float (&y)[D_], const float* k, const float (&l)[D_],
+                           float (&gy)[D_], RocheCoop<D_>* cp) {
+        using C = RocheCoop<D_>;
+        vjp_expert<EG, R_NSCALAR>(sp, t, ds, y, l, gy, cp->e);
+        float u[ML];
+#pragma unroll
+        for (int j = 0; j < ML; j += 2) vjp_unit_pair(sp, j, y, k, l, gy, u[j], u[j + 1]);
+        if (cp->mute) return;  // warp-uniform
+        float* SUp = cp->stage;
+        float* SYp = SUp + C::NJB * C::SU;
+        const int lane = cp->lane;
+        __syncwarp();  // the previous call's owner phase has finished reading the staging area
+#pragma unroll
+        for (int j = 0; j < ML; j += 2) *reinterpret_cast<float2*>(SUp + (j >> 1) * C::SU + 2 * lane) = make_float2(u[j], u[j + 1]);
+#pragma unroll
+        for (int d = 0; d < D_; ++d) SYp[d * C::SY + lane] = y[d];
+        __syncwarp();
+        // owner phase: unit pair jb, columns 6 db .. 6 db + 5, trajectories 4 tg + 16 h + {0..3}
+        const int tg = lane >> 3, jb = (lane & 7) >> 1, db = lane & 1;
+        const float* up = SUp + jb * C::SU + 8 * tg;
+        const float* yp = SYp + (6 * db) * C::SY + 4 * tg;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float4 ua = *reinterpret_cast<const float4*>(up + 32 * h);      // (u_j0, u_j1) of trajectories tt, tt+1
+            const float4 ub = *reinterpret_cast<const float4*>(up + 32 * h + 4);  // ... tt+2, tt+3
+#pragma unroll
+            for (int c = 0; c < 6; ++c) {
+                const float4 yv = *reinterpret_cast<const float4*>(yp + c * C::SY + 16 * h);
+                fma2s(yv.x, ua.x, ua.y, cp->w[c][0], cp->w[c][1], cp->w[c][0], cp->w[c][1]);
+                fma2s(yv.y, ua.z, ua.w, cp->w[c][0], cp->w[c][1], cp->w[c][0], cp->w[c][1]);
+                fma2s(yv.z, ub.x, ub.y, cp->w[c][0], cp->w[c][1], cp->w[c][0], cp->w[c][1]);
+                fma2s(yv.w, ub.z, ub.w, cp->w[c][0], cp->w[c][1], cp->w[c][0], cp->w[c][1]);
+            }
+            add2(cp->b[0], cp->b[1], ua.x, ua.y, cp->b[0], cp->b[1]);
+            add2(cp->b[0], cp->b[1], ua.z, ua.w, cp->b[0], cp->b[1]);
+            add2(cp->b[0], cp->b[1], ub.x, ub.y, cp->b[0], cp->b[1]);
+            add2(cp->b[0], cp->b[1], ub.z, ub.w, cp->b[0], cp->b[1]);
+        }
+    }
+#endif
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -723,6 +807,13 @@ HODE_D void vjp_state_only(PS sp, float t, const Dose& ds, const float (&y)[F::D
     F::template vjp<false>(sp, t, ds, y, k, l, gy, cp);
     cp->mute = false;
 }
+template <class F, class PS, class Dose, int DD>
+HODE_D void vjp_state_only(PS sp, float t, const Dose& ds, const float (&y)[F::D], const float* k,
+                           const float (&l)[F::D], float (&gy)[F::D], RocheCoop<DD>* cp) {
+    cp->mute = true;
+    F::template vjp<false>(sp, t, ds, y, k, l, gy, cp);
+    cp->mute = false;
+}
 #endif
 
 // One step s0 -> s1 (ds = s1 - s0 > 0) of the augmented system in negated time; y and a are updated in place and
@@ -804,102 +895,246 @@ HODE_HD void fixed_adjoint_step(PS sp, const Dose& ds, float s0, float s1, float
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// dopri5 (tde dopri5.py tableau, cast to float32 like `tableau.to(y0.dtype)`)
+// dopri5 (tde dopri5.py tableau, cast to float32 like `tableau.to(y0.dtype)`).  The coefficients live in tables that can
+// be indexed at run time: the D = 12 kernels keep their stage derivatives in shared memory and run the stage loops
+// ROLLED (one inlined copy of the vector field instead of seven: the unrolled reverse sweep was 118 KB of code, far
+// beyond the 32 KB instruction cache -- ncu: stall_no_instruction 2.1 per issue), the small-D kernels unroll them and
+// the compiler folds the constants.
 // ------------------------------------------------------------------------------------------------------------
-struct Dopri5Tab {
-    float alpha[6];
-    float beta[6][6];
-    float c_err[7];
-    float c_mid[7];
+#define HODE_D5_ALPHA {(float)(1.0 / 5), (float)(3.0 / 10), (float)(4.0 / 5), (float)(8.0 / 9), 1.0f, 1.0f}
+#define HODE_D5_BETA                                                                                                        \
+    {{(float)(1.0 / 5), 0, 0, 0, 0, 0},                                                                                     \
+     {(float)(3.0 / 40), (float)(9.0 / 40), 0, 0, 0, 0},                                                                    \
+     {(float)(44.0 / 45), (float)(-56.0 / 15), (float)(32.0 / 9), 0, 0, 0},                                                 \
+     {(float)(19372.0 / 6561), (float)(-25360.0 / 2187), (float)(64448.0 / 6561), (float)(-212.0 / 729), 0, 0},             \
+     {(float)(9017.0 / 3168), (float)(-355.0 / 33), (float)(46732.0 / 5247), (float)(49.0 / 176), (float)(-5103.0 / 18656), 0}, \
+     {(float)(35.0 / 384), 0.0f, (float)(500.0 / 1113), (float)(125.0 / 192), (float)(-2187.0 / 6784), (float)(11.0 / 84)}}
+#define HODE_D5_CERR                                                                                                     \
+    {(float)(35.0 / 384 - 1951.0 / 21600), 0.0f, (float)(500.0 / 1113 - 22642.0 / 50085), (float)(125.0 / 192 - 451.0 / 720), \
+     (float)(-2187.0 / 6784 - -12231.0 / 42400), (float)(11.0 / 84 - 649.0 / 6300), (float)(-1.0 / 60.0)}
+#define HODE_D5_CMID                                                                                                      \
+    {(float)(6025192743.0 / 30085553152.0 / 2), 0.0f, (float)(51252292925.0 / 65400821598.0 / 2),                         \
+     (float)(-2691868925.0 / 45128329728.0 / 2), (float)(187940372067.0 / 1594534317056.0 / 2),                           \
+     (float)(-1776094331.0 / 19743644256.0 / 2), (float)(11237099.0 / 235043384.0 / 2)}
+// host copies (the plain-C++ build, and the never-executed host pass of the __host__ __device__ bodies under nvcc)
+static const float kD5AlphaH[6] = HODE_D5_ALPHA;
+static const float kD5BetaH[6][6] = HODE_D5_BETA;
+static const float kD5CErrH[7] = HODE_D5_CERR;
+static const float kD5CMidH[7] = HODE_D5_CMID;
+#if HODE_DEVICE_BUILD
+static __constant__ float kD5Alpha[6] = HODE_D5_ALPHA;
+static __constant__ float kD5Beta[6][6] = HODE_D5_BETA;
+static __constant__ float kD5CErr[7] = HODE_D5_CERR;
+static __constant__ float kD5CMid[7] = HODE_D5_CMID;
+#endif
+#if HODE_DEVICE_BUILD && defined(__CUDA_ARCH__)
+HODE_D float d5_alpha(int i) { return kD5Alpha[i]; }
+HODE_D float d5_beta(int i, int j) { return kD5Beta[i][j]; }
+HODE_D float d5_cerr(int i) { return kD5CErr[i]; }
+HODE_D float d5_cmid(int i) { return kD5CMid[i]; }
+#else
+HODE_HD float d5_alpha(int i) { return kD5AlphaH[i]; }
+HODE_HD float d5_beta(int i, int j) { return kD5BetaH[i][j]; }
+HODE_HD float d5_cerr(int i) { return kD5CErrH[i]; }
+HODE_HD float d5_cmid(int i) { return kD5CMidH[i]; }
+#endif
+
+// torch.max / torch.min propagate NaN (fmaxf / fminf drop it)
+#if HODE_DEVICE_BUILD && defined(__CUDA_ARCH__)
+HODE_D float nan_maxf(float a, float b) { float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+HODE_D float nan_minf(float a, float b) { float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+#else
+HODE_HD float nan_maxf(float a, float b) { return (a != a || b != b) ? (a + b) : (a > b ? a : b); }
+HODE_HD float nan_minf(float a, float b) { return (a != a || b != b) ? (a + b) : (a < b ? a : b); }
+#endif
+
+// tde misc.py _optimal_step_size (order = 5): dt * min(ifactor, max(safety / ratio**(1/5), dfactor or 1)).  The ratio is a
+// float32 quantity (tde computes it in y.dtype); the factor is evaluated in float32 as 2^(-log2(ratio) / 5) with the MUFU
+// lg2 / ex2 units (relative error ~3e-7, the effect of a few ulps of the ratio itself) and only the product with dt is
+// float64 -- the float64 pow + divide of the literal formula were ~250 instructions per attempt.  ratio == 0 gives
+// 2^(+inf) = inf -> min(ifactor, inf) = ifactor like tde's special case; NaN propagates like torch.min / torch.max.
+#if HODE_FAST_MATH && HODE_DEVICE_BUILD && defined(__CUDA_ARCH__)
+HODE_D float lg2_approx(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+HODE_D float sqrt_approx(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+HODE_D float inv_fifth_root(float r) { return ex2_approx(-0.2f * lg2_approx(r)); }
+HODE_D float fast_sqrt(float x) { return sqrt_approx(x); }
+// e / tol for tol >= atol > 0 (one MUFU.RCP + one multiply instead of the ~12-instruction IEEE division)
+HODE_D float div_tol(float e, float tol) { return e * rcp_approx(tol); }
+#else
+HODE_HD float inv_fifth_root(float r) { return 1.0f / powf(r, 0.2f); }
+HODE_HD float fast_sqrt(float x) { return sqrtf(x); }
+HODE_HD float div_tol(float e, float tol) { return e / tol; }
+#endif
+HODE_HD double optimal_step(double last, float ratio, float safety, float ifactor, float dfactor) {
+    if (ratio < 1.0f) dfactor = 1.0f;
+    const float factor = nan_minf(ifactor, nan_maxf(safety * inv_fifth_root(ratio), dfactor));
+    return last * (double)factor;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Per-thread rows of D floats (stage derivatives, stage adjoints).  RowsReg keeps them in registers: every index must
+// be a compile-time constant after unrolling (kDynamic = false).  RowsMem keeps them in the thread's slots of a
+// shared-memory array, interleaved by thread so that a warp's vector access touches consecutive 16 / 8-byte chunks
+// (conflict-free): chunk c of row i of this thread is at p[(i * NC + c) * stride]; rows may be indexed at run time.
+// ------------------------------------------------------------------------------------------------------------
+template <int D, int NR>
+struct RowsReg {
+    static constexpr bool kDynamic = false;
+    float v[NR][D];
+    HODE_HD void load(int i, float (&o)[D]) const {
+#pragma unroll
+        for (int d = 0; d < D; ++d) o[d] = v[i][d];
+    }
+    HODE_HD void store(int i, const float (&x)[D]) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) v[i][d] = x[d];
+    }
 };
-HODE_HD Dopri5Tab dopri5_tab() {
-    Dopri5Tab T = {
-        {(float)(1.0 / 5), (float)(3.0 / 10), (float)(4.0 / 5), (float)(8.0 / 9), 1.0f, 1.0f},
-        {{(float)(1.0 / 5), 0, 0, 0, 0, 0},
-         {(float)(3.0 / 40), (float)(9.0 / 40), 0, 0, 0, 0},
-         {(float)(44.0 / 45), (float)(-56.0 / 15), (float)(32.0 / 9), 0, 0, 0},
-         {(float)(19372.0 / 6561), (float)(-25360.0 / 2187), (float)(64448.0 / 6561), (float)(-212.0 / 729), 0, 0},
-         {(float)(9017.0 / 3168), (float)(-355.0 / 33), (float)(46732.0 / 5247), (float)(49.0 / 176),
-          (float)(-5103.0 / 18656), 0},
-         {(float)(35.0 / 384), 0.0f, (float)(500.0 / 1113), (float)(125.0 / 192), (float)(-2187.0 / 6784),
-          (float)(11.0 / 84)}},
-        {(float)(35.0 / 384 - 1951.0 / 21600), 0.0f, (float)(500.0 / 1113 - 22642.0 / 50085),
-         (float)(125.0 / 192 - 451.0 / 720), (float)(-2187.0 / 6784 - -12231.0 / 42400),
-         (float)(11.0 / 84 - 649.0 / 6300), (float)(-1.0 / 60.0)},
-        {(float)(6025192743.0 / 30085553152.0 / 2), 0.0f, (float)(51252292925.0 / 65400821598.0 / 2),
-         (float)(-2691868925.0 / 45128329728.0 / 2), (float)(187940372067.0 / 1594534317056.0 / 2),
-         (float)(-1776094331.0 / 19743644256.0 / 2), (float)(11237099.0 / 235043384.0 / 2)}};
-    return T;
+#if HODE_DEVICE_BUILD && defined(__CUDA_ARCH__)
+HODE_D float4 ld_row4(const float* p) {
+    float4 v;
+    asm volatile("ld.volatile.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
 }
-
-// torch.max / torch.min propagate NaN
-HODE_HD double nan_max(double a, double b) { return (a != a || b != b) ? (a + b) : (a > b ? a : b); }
-HODE_HD double nan_min(double a, double b) { return (a != a || b != b) ? (a + b) : (a < b ? a : b); }
-
-// tde misc.py _optimal_step_size (order = 5): float64 arithmetic on a float32 error ratio
-HODE_HD double optimal_step(double last, float ratio, double safety, double ifactor, double dfactor) {
-    if (ratio == 0.0f) return last * ifactor;
-    if (ratio < 1.0f) dfactor = 1.0;
-    // ratio ** (1/5): the ratio is a float32 quantity (tde computes it in y.dtype), so a float32 power (relative error
-    // ~1e-7, i.e. the same perturbation of dt as one ulp of the ratio itself) replaces the ~200-instruction float64 pow
-    const double factor = nan_min(ifactor, nan_max(safety / (double)powf(ratio, 0.2f), dfactor));
-    return last * factor;
+HODE_D float2 ld_row2(const float* p) {
+    float2 v;
+    asm volatile("ld.volatile.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"((unsigned)__cvta_generic_to_shared(p)));
+    return v;
 }
-
-// Storage of the 7 stage derivatives (and of their adjoints in the reverse sweep).  StageRegs keeps them in registers;
-// StageSmem keeps them in the thread's column of a shared-memory array (element (i, d) at p[(i * D + d) * stride],
-// stride = threads per CTA: conflict-free) -- used where 2 x 7 x D floats on top of the parameter-gradient
-// accumulators do not fit the register file (dopri5 reverse sweep, D >= 12).
-template <int D>
-struct StageRegs {
-    float v[7][D];
-    HODE_HD float get(int i, int d) const { return v[i][d]; }
-    HODE_HD void set(int i, int d, float x) { v[i][d] = x; }
-};
-template <int D>
-struct StageSmem {
-    float* p;
-    int stride;
-    HODE_HD float get(int i, int d) const { return p[(i * D + d) * stride]; }
-    HODE_HD void set(int i, int d, float x) { p[(i * D + d) * stride] = x; }
-};
-template <int D, class KS>
-HODE_HD void stage_row(const KS& k, int i, float (&out)[D]) {
-#pragma unroll
-    for (int d = 0; d < D; ++d) out[d] = k.get(i, d);
+HODE_D void st_row4(float* p, float a, float b, float c, float d) {
+    asm volatile("st.volatile.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"((unsigned)__cvta_generic_to_shared(p)), "f"(a), "f"(b), "f"(c), "f"(d));
 }
-template <int D, class KS>
-HODE_HD void stage_set_row(KS& k, int i, const float (&in)[D]) {
-#pragma unroll
-    for (int d = 0; d < D; ++d) k.set(i, d, in[d]);
+HODE_D void st_row2(float* p, float a, float b) {
+    asm volatile("st.volatile.shared.v2.f32 [%0], {%1, %2};" ::"r"((unsigned)__cvta_generic_to_shared(p)), "f"(a), "f"(b));
 }
-
-// The 7 stages of one attempt.  Stage 0 of `k` must hold f0 on entry.  On exit stages 1..6 are filled and y1 is the last
-// stage input.
-template <class F, class PS, class Dose, class KS>
-HODE_HD void dopri5_stages(PS sp, const Dose& ds, const Dopri5Tab& T, float t0f, float dtf, float t1f,
-                           const float (&y0)[F::D], KS& k, float (&y1)[F::D]) {
-    constexpr int D = F::D;
+#elif HODE_DEVICE_BUILD
+HODE_HD float4 ld_row4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+HODE_HD float2 ld_row2(const float* p) { return *reinterpret_cast<const float2*>(p); }
+HODE_HD void st_row4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
+HODE_HD void st_row2(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+#endif
+template <int D, int NR, int STRIDE = 0>
+struct RowsMem {
+    static constexpr bool kDynamic = true;
+    static constexpr int VEC = (D % 4 == 0) ? 4 : ((D % 2 == 0) ? 2 : 1);
+    static constexpr int NC = D / VEC;
+    static constexpr int kFloatsPerThread = NR * D;
+    float* p;     // this thread's first chunk
+    int stride_;  // floats between consecutive chunks of one thread = threads * VEC (used when STRIDE == 0)
+    // STRIDE > 0: the stride is a compile-time constant (fixed CTA size): chunk offsets become immediates
+    HODE_HD int stride() const { return STRIDE > 0 ? STRIDE : stride_; }
+    // The accesses are volatile: with unrolled stage loops the compiler otherwise forwards every stored row to its later
+    // loads, i.e. keeps all rows in registers after all (measured: 250 registers or 0.5 KB of spills at D = 12).
+    HODE_HD void load(int i, float (&o)[D]) const {
+        const float* q = p + (size_t)(i * NC) * stride();
 #pragma unroll
-    for (int i = 0; i < 6; ++i) {
-        float ti;
-        if (T.alpha[i] == 1.0f) ti = t_prev(t1f);
-        else ti = add_rn(t0f, mul_rn(T.alpha[i], dtf));
-        float yi[D], kn[D];
-        static_assert(D % 2 == 0, "packed stage combination assumes even D");
+        for (int c = 0; c < NC; ++c) {
+#if HODE_DEVICE_BUILD
+            if (VEC == 4) {
+                const float4 t = ld_row4(q + (size_t)c * stride());
+                o[4 * c] = t.x; o[4 * c + 1] = t.y; o[4 * c + 2] = t.z; o[4 * c + 3] = t.w;
+                continue;
+            } else if (VEC == 2) {
+                const float2 t = ld_row2(q + (size_t)c * stride());
+                o[2 * c] = t.x; o[2 * c + 1] = t.y;
+                continue;
+            }
+#endif
 #pragma unroll
-        for (int d = 0; d < D; d += 2) {  // two state dimensions per packed FMA, same j order per element
-            float a0 = 0.0f, a1 = 0.0f;
-#pragma unroll
-            for (int j = 0; j <= i; ++j) fma2s(mul_rn(T.beta[i][j], dtf), k.get(j, d), k.get(j, d + 1), a0, a1, a0, a1);
-            add2(y0[d], y0[d + 1], a0, a1, yi[d], yi[d + 1]);
+            for (int e = 0; e < VEC; ++e) o[c * VEC + e] = q[(size_t)c * stride() + e];
         }
-        F::eval(sp, ti, ds, yi, kn);
-        stage_set_row<D>(k, i + 1, kn);
-        if (i == 5) {
+    }
+    HODE_HD void store(int i, const float (&x)[D]) {
+        float* q = p + (size_t)(i * NC) * stride();
 #pragma unroll
-            for (int d = 0; d < D; ++d) y1[d] = yi[d];
+        for (int c = 0; c < NC; ++c) {
+#if HODE_DEVICE_BUILD
+            if (VEC == 4) {
+                st_row4(q + (size_t)c * stride(), x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+                continue;
+            } else if (VEC == 2) {
+                st_row2(q + (size_t)c * stride(), x[2 * c], x[2 * c + 1]);
+                continue;
+            }
+#endif
+#pragma unroll
+            for (int e = 0; e < VEC; ++e) q[(size_t)c * stride() + e] = x[c * VEC + e];
         }
+    }
+};
+
+// Stage loops: fully unrolled with compile-time indices (UNROLL: register rows) or rolled.  `fn` receives either a
+// std::integral_constant<int, I> or an int; both convert to int.
+template <int I>
+struct IdxC {
+    constexpr operator int() const { return I; }
+};
+template <bool UNROLL, int LO, int HI, class Fn>  // i = LO .. HI-1 ascending
+HODE_HD void stage_up(Fn&& fn) {
+    if constexpr (UNROLL) {
+        if constexpr (LO < HI) {
+            fn(IdxC<LO>{});
+            stage_up<true, LO + 1, HI>(fn);
+        }
+    } else {
+#pragma unroll 1
+        for (int i = LO; i < HI; ++i) fn(i);
+    }
+}
+template <bool UNROLL, int HI, int LO, class Fn>  // i = HI .. LO descending (inclusive)
+HODE_HD void stage_down(Fn&& fn) {
+    if constexpr (UNROLL) {
+        if constexpr (HI >= LO) {
+            fn(IdxC<HI>{});
+            stage_down<true, HI - 1, LO>(fn);
+        }
+    } else {
+#pragma unroll 1
+        for (int i = HI; i >= LO; --i) fn(i);
+    }
+}
+// Rolled stage loops run the vector field ONCE per trip (one inlined copy), but the stage algebra around it -- which rows
+// enter with which tableau coefficients -- is different for every stage: dispatching on the run-time stage index to a
+// compile-time one gives each stage its own straight-line code (immediate row offsets, coefficients folded into FMUL
+// immediates, no inner loop control).  With run-time inner loops those three were ~35 % of the executed instructions.
+template <bool SWITCH, int N, class Fn>
+HODE_HD void stage_switch(int i, Fn&& fn) {
+    if constexpr (!SWITCH) {
+        fn(i);
+    } else {
+        switch (i) {
+            case 0: fn(IdxC<0>{}); break;
+            case 1: if constexpr (N > 1) fn(IdxC<1>{}); break;
+            case 2: if constexpr (N > 2) fn(IdxC<2>{}); break;
+            case 3: if constexpr (N > 3) fn(IdxC<3>{}); break;
+            case 4: if constexpr (N > 4) fn(IdxC<4>{}); break;
+            case 5: if constexpr (N > 5) fn(IdxC<5>{}); break;
+            case 6: if constexpr (N > 6) fn(IdxC<6>{}); break;
+            default: break;
+        }
+    }
+}
+// j = lo .. hi-1 ascending with run-time bounds inside [0, MAXN): unrolled (bounds fold after inlining) or rolled
+template <bool UNROLL, int MAXN, class Fn>
+HODE_HD void range_up(int lo, int hi, Fn&& fn) {
+    if constexpr (UNROLL) {
+#pragma unroll
+        for (int j = 0; j < MAXN; ++j)
+            if (j >= lo && j < hi) fn(j);
+    } else {
+#pragma unroll 1
+        for (int j = lo; j < hi; ++j) fn(j);
+    }
+}
+template <bool UNROLL, int MAXN, class Fn>  // j = hi-1 .. lo descending
+HODE_HD void range_down(int lo, int hi, Fn&& fn) {
+    if constexpr (UNROLL) {
+#pragma unroll
+        for (int j = MAXN - 1; j >= 0; --j)
+            if (j >= lo && j < hi) fn(j);
+    } else {
+#pragma unroll 1
+        for (int j = hi - 1; j >= lo; --j) fn(j);
     }
 }
 

@@ -18,15 +18,21 @@
 #ifndef HODE_BWD_MINBLOCKS
 #define HODE_BWD_MINBLOCKS 1
 #endif
+#ifndef HODE_D5_FWD_MINBLOCKS
+#define HODE_D5_FWD_MINBLOCKS 4
+#endif
 #ifndef HODE_DOPRI5_MAX_THREADS
 #define HODE_DOPRI5_MAX_THREADS 512
 #endif
 
 namespace hode {
 
-// ---- group sum across the CTA (batch-coupled controller) or nothing (per-trajectory) -------------------------
+// ---- group operations of the dopri5 controller: a sum over the controller group (batch-coupled: the CTA or a lane
+//      segment; per-trajectory: nothing) that is bit-identical in every thread of the group, and any() -------------------
 struct CommNone {
+    __device__ __forceinline__ void sum1(float&) {}
     __device__ __forceinline__ void sum2(float&, float&) {}
+    __device__ __forceinline__ bool any(bool p) { return p; }
 };
 struct CommCta {
     float* red;  // 2 buffers x (2 * 32) floats of shared memory, used alternately: ONE barrier per reduction
@@ -50,6 +56,24 @@ struct CommCta {
             phase ^= 1;
             a = sa; b = sb;
         }
+    }
+    __device__ __forceinline__ void sum1(float& a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (nwarps > 1) {
+            const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+            float* r = red + phase * 64;
+            if (lane == 0) r[wid] = a;
+            __syncthreads();
+            float sa = 0.0f;
+            for (int i = 0; i < nwarps; ++i) sa += r[i];
+            phase ^= 1;
+            a = sa;
+        }
+    }
+    __device__ __forceinline__ bool any(bool p) {
+        if (nwarps > 1) return __syncthreads_or(p ? 1 : 0) != 0;
+        return __any_sync(0xffffffffu, p) != 0;
     }
 };
 
@@ -126,22 +150,34 @@ inline bool const_params_enabled() {
 template <class F>
 inline bool use_const_params(const SolveArgs& a) { return F::kConstBank && a.pset == nullptr && const_params_enabled(); }
 
-// several small groups share one warp: a group is a segment of `size` consecutive lanes; only the lanes of a segment
-// take part in its shuffles (independent thread scheduling lets segments follow different accept/reject sequences)
+// several small groups share one warp: a group is a segment of `size` consecutive lanes with its own accept / reject
+// sequence (independent thread scheduling lets the segments of a warp diverge).  The group sum goes through a warp-private
+// shared-memory buffer -- one store, one __syncwarp over the segment's lanes, round_up4(size) / 4 vector loads: every lane
+// adds the segment's values in the same order, so the sum (and the accept decision) is bit-identical across the group.
+// (Per-lane __shfl_sync with a run-time mask cost a MATCH + REDUX + VOTE + WARPSYNC sequence per shuffle: ~120
+// instructions per reduction of a 10-lane group.)  Two buffers are used alternately, so one __syncwarp per reduction.
 struct CommSeg {
     unsigned mask;  // lanes of this segment
-    int base, size, rel;
-    // every lane adds the segment's values in the same order (lane base, base+1, ...): the sums are bit-identical
-    // across the group, which the group-uniform accept/reject decision relies on
-    __device__ __forceinline__ void sum2(float& a, float& b) {
-        const float a0 = a, b0 = b;
-        float sa = 0.0f, sb = 0.0f;
-        for (int i = 0; i < size; ++i) {
-            sa += __shfl_sync(mask, a0, base + i);
-            sb += __shfl_sync(mask, b0, base + i);
-        }
-        a = sa; b = sb;
+    int rel;        // lane index inside the segment
+    int nvec;       // round_up4(size) / 4
+    float* buf;     // this segment's slots: [2 phases][16] floats, padding slots stay zero
+    int phase = 0;
+    static constexpr int kFloatsPerWarp = 2 * 8 * 16;  // up to 8 segments (size >= 4 ... the launcher uses size <= 16)
+    __device__ __forceinline__ void sum1(float& a) {
+        float* b = buf + phase * 16;
+        b[rel] = a;
+        __syncwarp(mask);
+        const float4* b4 = reinterpret_cast<const float4*>(b);
+        float4 q = b4[0];
+        float s = ((q.x + q.y) + q.z) + q.w;
+        if (nvec > 1) { q = b4[1]; s = (((s + q.x) + q.y) + q.z) + q.w; }
+        if (nvec > 2) { q = b4[2]; s = (((s + q.x) + q.y) + q.z) + q.w; }
+        if (nvec > 3) { q = b4[3]; s = (((s + q.x) + q.y) + q.z) + q.w; }
+        phase ^= 1;
+        a = s;
     }
+    __device__ __forceinline__ void sum2(float& a, float& b) { sum1(a); sum1(b); }
+    __device__ __forceinline__ bool any(bool p) { return (__ballot_sync(mask, p) & mask) != 0u; }
 };
 
 template <class F>
@@ -248,9 +284,13 @@ __global__ void __launch_bounds__(128, HODE_FWD_MINBLOCKS) fixed_fwd_kernel(cons
     else { HODE_WITH_DOSE(ND, a, idx, (fixed_fwd_traj<F, METHOD>(a, (const float*)smem, ds, idx))); }
 }
 
-// does the field accumulate its parameter gradients warp-cooperatively (NeuralCoop) in the fixed-grid reverse sweep?
-template <class F> struct CoopOf { static constexpr bool value = false; };
-template <int D> struct CoopOf<Neural<D>> { static constexpr bool value = true; };
+// Does the field accumulate its parameter gradients warp-cooperatively?  NeuralODE (846 - 3 132 parameters) always;
+// RocheODE at D = 12 (104 ml_net accumulators) in the dopri5 reverse sweep and the continuous adjoint, where the
+// per-thread accumulators spill (the fixed-grid reverse sweep keeps them: 3 recomputed stages fit next to them).
+template <class F> struct CoopOf { static constexpr bool value = false; using type = void; };
+template <int D> struct CoopOf<Neural<D>> { static constexpr bool value = true; using type = NeuralCoop<D>; };
+template <class F> struct CoopD5 : CoopOf<F> {};
+template <bool H, bool A> struct CoopD5<Roche<12, H, A>> { static constexpr bool value = true; using type = RocheCoop<12>; };
 
 template <int D>
 __device__ __forceinline__ void coop_init(NeuralCoop<D>& cp, float* stage_base) {
@@ -290,6 +330,51 @@ __device__ __forceinline__ void coop_flush(const SolveArgs& a, int64_t group, Ne
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (cp.lane == 0) atomicAdd(&sred[F::OFF_B2 + d], v);
+    }
+    __syncthreads();
+    const int set = a.pset ? a.pset[group] : 0;
+    float* dst = a.grad_params + (int64_t)set * F::P;
+    for (int i = threadIdx.x; i < F::P; i += blockDim.x) atomicAdd(&dst[i], sred[i]);
+}
+
+template <int D>
+__device__ __forceinline__ void coop_init(RocheCoop<D>& cp, float* stage_base) {
+    cp.lane = threadIdx.x & 31;
+    cp.stage = stage_base + (threadIdx.x >> 5) * RocheCoop<D>::kStageFloats;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) { cp.w[c][0] = 0.0f; cp.w[c][1] = 0.0f; }
+    cp.b[0] = 0.0f; cp.b[1] = 0.0f;
+#pragma unroll
+    for (int i = 0; i < RocheCoop<D>::NE; ++i) cp.e[i] = 0.0f;
+    cp.mute = false;
+}
+// owned blocks (4 partial sums per entry, one per trajectory group of the warp) + per-thread expert scalars -> shared
+// accumulator -> one global atomic per parameter per CTA
+template <class F, bool EG, int D>
+__device__ __forceinline__ void coop_flush(const SolveArgs& a, int64_t group, RocheCoop<D>& cp, float* sred) {
+    for (int i = threadIdx.x; i < F::P; i += blockDim.x) sred[i] = 0.0f;
+    __syncthreads();
+    const int jb = (cp.lane & 7) >> 1, db = cp.lane & 1;
+#pragma unroll
+    for (int c = 0; c < 6; ++c) {
+        atomicAdd(&sred[F::OFF_W + (2 * jb) * D + 6 * db + c], cp.w[c][0]);
+        atomicAdd(&sred[F::OFF_W + (2 * jb + 1) * D + 6 * db + c], cp.w[c][1]);
+    }
+    if (db == 0) {
+        atomicAdd(&sred[F::OFF_B + 2 * jb], cp.b[0]);
+        atomicAdd(&sred[F::OFF_B + 2 * jb + 1], cp.b[1]);
+    }
+    if (EG) {
+#pragma unroll
+        for (int i = 0; i < RocheCoop<D>::NE; ++i) {
+            const int pi = i < R_NSCALAR ? i : F::OFF_TH + (i - R_NSCALAR);  // 13 expert scalars, then theta_1 / theta_2
+            if (pi < F::P && (i < R_NSCALAR || F::ABLATE) && i < R_NSCALAR + 2) {
+                float v = cp.e[i];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (cp.lane == 0) atomicAdd(&sred[pi], v);
+            }
+        }
     }
     __syncthreads();
     const int set = a.pset ? a.pset[group] : 0;
@@ -352,13 +437,51 @@ __global__ void __launch_bounds__(128, HODE_BWD_MINBLOCKS) fixed_adj_kernel(cons
     }
 }
 
-// MAXT: launch bound.  128 for per-trajectory control and small groups (up to 255 registers per thread);
-// HODE_DOPRI5_MAX_THREADS for a batch-coupled group that needs a whole large CTA (128 registers per thread).
+// ---------------------------------------------------------------------------------------------------------------
+// dopri5 kernels.  Where do the stage rows live?  In registers for D <= 8 (stage loops unrolled); in shared memory for
+// D = 12 (RowsMem, stage loops rolled): 7 x 12 stage floats on top of state + stage input + error estimate put the
+// register-resident forward kernel at 240 registers (2 warps per scheduler, ncu: issue-active 42 %, `wait` 1.7 per issue)
+// and the reverse sweep at 255 registers + 1.9 KB of spills with 118 KB of unrolled code (stall_no_instruction 2.1).
+// ---------------------------------------------------------------------------------------------------------------
+template <class F>
+struct D5Store {
+    static constexpr bool kSmem = F::D >= 12;
+    // Rolled stage loops wherever the rows are in shared memory: one inlined copy of the vector field (and of its VJP)
+    // per loop, stage algebra dispatched to per-stage straight-line code (stage_switch).  Unrolling the forward loop with
+    // shared-memory rows was tried: ptxas hoists the 34 tableau x dt products and the row loads across stages and needs
+    // ~250 registers again (or spills at the 128 / 168 caps).
+    static constexpr bool kFwdRolled = kSmem, kBwdRolled = kSmem;
+    static constexpr int kFwdRows = 7, kBwdRows = 9;
+    static constexpr int kFwdMinBlocks = kSmem ? HODE_D5_FWD_MINBLOCKS : 1;  // 128-thread CTAs per SM the register budget must allow
+    static constexpr int kBwdMinBlocks = kSmem ? 3 : 1;
+    __host__ __device__ static constexpr size_t fwd_floats(int threads) { return kSmem ? (size_t)kFwdRows * F::D * threads : 0; }
+    __host__ __device__ static constexpr size_t bwd_floats(int threads) { return kSmem ? (size_t)kBwdRows * F::D * threads : 0; }
+};
+__host__ __device__ constexpr int round4(int n) { return (n + 3) / 4 * 4; }
+
+// runs `fn(rows)` with the storage D5Store selects; `base` = the CTA's row area in shared memory (16-byte aligned)
+// THREADS > 0: the CTA size is known at compile time (row strides become immediates)
+template <class F, int NR, int THREADS, class Fn>
+__device__ __forceinline__ void with_rows(float* base, Fn&& fn) {
+    if constexpr (D5Store<F>::kSmem) {
+        using RM = RowsMem<F::D, NR, THREADS * RowsMem<F::D, NR>::VEC>;
+        RM rows{base + threadIdx.x * RM::VEC, (int)blockDim.x * RM::VEC};
+        fn(rows);
+    } else {
+        RowsReg<F::D, NR> rows;
+        fn(rows);
+    }
+}
+
+// MAXT: launch bound.  128 for per-trajectory control and small groups; HODE_DOPRI5_MAX_THREADS for a batch-coupled group
+// that needs a whole large CTA (128 registers per thread).
 template <class F, bool PER_TRAJ, int ND, int MAXT, bool CP>
-__global__ void __launch_bounds__(MAXT) dopri5_fwd_kernel(const SolveArgs a, int tiles_per_group) {
-    extern __shared__ float smem[];
+__global__ void __launch_bounds__(MAXT, MAXT <= 128 ? D5Store<F>::kFwdMinBlocks : 1)
+dopri5_fwd_kernel(const SolveArgs a, int tiles_per_group) {
+    extern __shared__ __align__(16) float smem[];
     float* sp = smem;
-    float* red = smem + (CP ? 0 : F::SP);
+    float* red = smem + (CP ? 0 : round4(F::SP));
+    float* rows = red + 128;
     const Tile tl = tile_of(a, tiles_per_group);
     if constexpr (!CP) stage_params<F>(a, tl.group, sp);
     const bool valid = tl.b < a.batch;
@@ -368,24 +491,30 @@ __global__ void __launch_bounds__(MAXT) dopri5_fwd_kernel(const SolveArgs a, int
     const int64_t ctrl = PER_TRAJ ? idx : tl.group;
     const bool leader = PER_TRAJ ? true : (threadIdx.x == 0);
     const float count = PER_TRAJ ? (float)F::D : (float)(a.batch * F::D);
-    if (PER_TRAJ) {
-        CommNone cm;
-        if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F>(a, cm, ParamConst(), ds, idx, valid, ctrl, leader, count))); }
-        else { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F>(a, cm, (const float*)sp, ds, idx, valid, ctrl, leader, count))); }
-    } else {
-        CommCta cm{red, (int)(blockDim.x >> 5), 0};
-        if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F>(a, cm, ParamConst(), ds, idx, valid, ctrl, leader, count))); }
-        else { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F>(a, cm, (const float*)sp, ds, idx, valid, ctrl, leader, count))); }
-    }
+    with_rows<F, 7, (MAXT <= 128 ? 128 : 0)>(rows, [&](auto& k) {
+        if (PER_TRAJ) {
+            CommNone cm;
+            if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F, D5Store<F>::kFwdRolled>(a, cm, ParamConst(), ds, k, idx, valid, ctrl, leader, count))); }
+            else { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F, D5Store<F>::kFwdRolled>(a, cm, (const float*)sp, ds, k, idx, valid, ctrl, leader, count))); }
+        } else {
+            CommCta cm{red, (int)(blockDim.x >> 5), 0};
+            if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F, D5Store<F>::kFwdRolled>(a, cm, ParamConst(), ds, k, idx, valid, ctrl, leader, count))); }
+            else { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F, D5Store<F>::kFwdRolled>(a, cm, (const float*)sp, ds, k, idx, valid, ctrl, leader, count))); }
+        }
+    });
 }
 
 // Batch-coupled controller for SMALL groups (batch <= 16, one parameter set): floor(32 / batch) groups per warp, each a
 // lane segment with its own step-size sequence.  (One group per CTA leaves 22 of 32 lanes idle at the reference's
 // batch of 10, run_dim.sh:41.)
 template <class F, int ND, bool CP>
-__global__ void __launch_bounds__(128) dopri5_fwd_seg_kernel(const SolveArgs a) {
-    extern __shared__ float smem[];
+__global__ void __launch_bounds__(128, D5Store<F>::kFwdMinBlocks) dopri5_fwd_seg_kernel(const SolveArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float* segbuf = smem + (CP ? 0 : round4(F::SP));
+    float* rows = segbuf + 4 * CommSeg::kFloatsPerWarp;
     if constexpr (!CP) stage_params<F>(a, 0, smem);
+    for (int i = threadIdx.x; i < 4 * CommSeg::kFloatsPerWarp; i += blockDim.x) segbuf[i] = 0.0f;
+    __syncthreads();
     const int lane = threadIdx.x & 31;
     const int size = (int)a.batch, gpw = 32 / size, seg = lane / size;
     if (seg >= gpw) return;
@@ -393,59 +522,56 @@ __global__ void __launch_bounds__(128) dopri5_fwd_seg_kernel(const SolveArgs a) 
     const int64_t group = warp * gpw + seg;
     if (group >= a.n_groups) return;
     CommSeg cm;
-    cm.base = seg * size; cm.size = size; cm.rel = lane - cm.base;
-    cm.mask = (size == 32 ? 0xffffffffu : ((1u << size) - 1u)) << cm.base;
+    const int base = seg * size;
+    cm.rel = lane - base;
+    cm.nvec = (size + 3) >> 2;
+    cm.mask = (size == 32 ? 0xffffffffu : ((1u << size) - 1u)) << base;
+    cm.buf = segbuf + (threadIdx.x >> 5) * CommSeg::kFloatsPerWarp + seg * 32;
     const int64_t idx = group * a.batch + cm.rel;
     const float count = (float)(a.batch * F::D);
-    if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F>(a, cm, ParamConst(), ds, idx, true, group, cm.rel == 0, count))); }
-    else { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F>(a, cm, (const float*)smem, ds, idx, true, group, cm.rel == 0, count))); }
+    with_rows<F, 7, 128>(rows, [&](auto& k) {
+        if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F, D5Store<F>::kFwdRolled>(a, cm, ParamConst(), ds, k, idx, true, group, cm.rel == 0, count))); }
+        else { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F, D5Store<F>::kFwdRolled>(a, cm, (const float*)smem, ds, k, idx, true, group, cm.rel == 0, count))); }
+    });
 }
 
-// Where do the 7 stage derivatives and their 7 adjoints live in the reverse sweep?  In registers.  At D = 12 (2 x 84
-// floats on top of 104 parameter-gradient accumulators) ptxas spills ~1.5 KB per thread; moving the stages to shared
-// memory (StageSmem, kSmem = true) was measured 2.4x SLOWER on B200 (C3 shape: 30.0 vs 12.6 ms) because the spills do
-// not go away (the accumulators are what overflows) and every stage access becomes an LDS.  Kept as a switch.
-template <class F>
-struct Dopri5BwdStore {
-    static constexpr bool kSmem = false;
-    static constexpr int floats_per_thread = kSmem ? 2 * 7 * F::D : 0;
-};
-
 template <class F, bool EG, int ND, bool CP>
-__global__ void __launch_bounds__(128) dopri5_bwd_kernel(const SolveArgs a, int tiles_per_group) {
-    extern __shared__ float smem[];
+__global__ void __launch_bounds__(128, D5Store<F>::kBwdMinBlocks) dopri5_bwd_kernel(const SolveArgs a, int tiles_per_group) {
+    extern __shared__ __align__(16) float smem[];
     float* sp = smem;
-    float* sred = smem + (CP ? 0 : F::SP);
+    float* sred = smem + (CP ? 0 : round4(F::SP));
+    float* rows = sred + round4(F::P);
+    float* coop_stage = rows + D5Store<F>::bwd_floats(128);
     const Tile tl = tile_of(a, tiles_per_group);
     if constexpr (!CP) stage_params<F>(a, tl.group, sp);
-    if constexpr (CoopOf<F>::value) {
-        if (!a.per_traj) {
-            // batch-coupled groups (one group per CTA, never flattened for this field): every lane of the CTA reverses
-            // the same number of accepted steps, so the warp-cooperative accumulation applies
-            NeuralCoop<F::D> cp;
-            coop_init(cp, sred + F::P);
-            const bool valid = tl.b < a.batch;
-            const int64_t idx = tl.group * a.batch + (valid ? tl.b : a.batch - 1);
-            HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, (const float*)sp, ds, idx, tl.group, &cp, valid)));
-            coop_flush(a, tl.group, cp, sred);
+    const bool valid = tl.b < a.batch;
+    const int64_t idx = tl.group * a.batch + (valid ? tl.b : a.batch - 1);
+    const int64_t ctrl = a.per_traj ? idx : (a.ctrl_batch > 0 ? idx / a.ctrl_batch : tl.group);
+    const int my_steps = valid ? a.stats[ctrl].accepted : 0;
+    if constexpr (CoopD5<F>::value) {
+        // Cooperative accumulators: every lane of every warp walks the warp's longest tape (padding lanes and lanes with
+        // fewer accepted steps idle with zero adjoints).  Neural: batch-coupled groups only (one group per CTA).
+        constexpr bool kRoche = !CoopOf<F>::value;
+        if (kRoche || !a.per_traj) {
+            typename CoopD5<F>::type cp;
+            coop_init(cp, coop_stage);
+            const int nloop = __reduce_max_sync(0xffffffffu, my_steps);
+            with_rows<F, 9, 128>(rows, [&](auto& R) {
+                if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG, D5Store<F>::kBwdRolled>(a, ParamConst(), ds, R, idx, ctrl, &cp, valid, nloop))); }
+                else { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG, D5Store<F>::kBwdRolled>(a, (const float*)sp, ds, R, idx, ctrl, &cp, valid, nloop))); }
+            });
+            if constexpr (kRoche) coop_flush<F, EG>(a, tl.group, cp, sred);
+            else coop_flush(a, tl.group, cp, sred);
             return;
         }
     }
     float acc[F::P];
     zero_acc<F>(acc);
-    if (tl.b < a.batch) {
-        const int64_t idx = tl.group * a.batch + tl.b;
-        const int64_t ctrl = a.per_traj ? idx : (a.ctrl_batch > 0 ? idx / a.ctrl_batch : tl.group);
-        if constexpr (Dopri5BwdStore<F>::kSmem) {
-            float* base = sred + F::P + threadIdx.x;
-            StageSmem<F::D> k{base, (int)blockDim.x};
-            StageSmem<F::D> kb{base + 7 * F::D * blockDim.x, (int)blockDim.x};
-            if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, ParamConst(), ds, idx, ctrl, (float*)acc, k, kb))); }
-            else { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, (const float*)sp, ds, idx, ctrl, (float*)acc, k, kb))); }
-        } else {
-            if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, ParamConst(), ds, idx, ctrl, (float*)acc))); }
-            else { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG>(a, (const float*)sp, ds, idx, ctrl, (float*)acc))); }
-        }
+    if (valid) {
+        with_rows<F, 9, 128>(rows, [&](auto& R) {
+            if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG, D5Store<F>::kBwdRolled>(a, ParamConst(), ds, R, idx, ctrl, (float*)acc, true, my_steps))); }
+            else { HODE_WITH_DOSE(ND, a, idx, (dopri5_bwd_traj<F, EG, D5Store<F>::kBwdRolled>(a, (const float*)sp, ds, R, idx, ctrl, (float*)acc, true, my_steps))); }
+        });
     }
     reduce_param_grads<F>(a, tl.group, acc, sred);
 }
@@ -586,24 +712,34 @@ int launch_fixed_adj(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st
     return 0;
 }
 
+template <class K>
+inline int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return 0;
+}
+
 template <class F>
 int launch_dopri5_fwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st) {
     const bool nd1 = cfg.n_dose == 1;
     if (!a_in.per_traj && a_in.batch > HODE_DOPRI5_MAX_THREADS) return -2;
-    if (!a_in.per_traj && a_in.pset == nullptr && a_in.batch <= 16) {
+    if (!a_in.per_traj && a_in.pset == nullptr && a_in.batch <= 16 && a_in.batch >= 4) {
         // small batch-coupled groups: several groups per warp
         const SolveArgs& a = a_in;
         const int gpw = 32 / (int)a.batch;
         const int64_t warps = (a.n_groups + gpw - 1) / gpw;
         const int threads = warps >= 4 ? 128 : (int)warps * 32;
         const int64_t nblk = (warps * 32 + threads - 1) / threads;
-#define HODE_DS_CP(CP)                                                                                                     \
-    do {                                                                                                                   \
-        if (nd1) dopri5_fwd_seg_kernel<F, 1, CP><<<(unsigned)nblk, threads, (CP ? 0 : F::SP) * sizeof(float), st>>>(a);    \
-        else dopri5_fwd_seg_kernel<F, 0, CP><<<(unsigned)nblk, threads, (CP ? 0 : F::SP) * sizeof(float), st>>>(a);        \
+#define HODE_DS(ND, CP)                                                                                                          \
+    do {                                                                                                                         \
+        const size_t sh_ = ((CP ? 0 : round4(F::SP)) + 4 * CommSeg::kFloatsPerWarp + D5Store<F>::fwd_floats(128)) * sizeof(float); \
+        int e_ = set_smem(dopri5_fwd_seg_kernel<F, ND, CP>, sh_);                                                                \
+        if (e_ != 0) return e_;                                                                                                  \
+        dopri5_fwd_seg_kernel<F, ND, CP><<<(unsigned)nblk, threads, sh_, st>>>(a);                                               \
     } while (0)
+#define HODE_DS_CP(CP) do { if (nd1) HODE_DS(1, CP); else HODE_DS(0, CP); } while (0)
         HODE_DISPATCH_CP(F, a, st, HODE_DS_CP);
 #undef HODE_DS_CP
+#undef HODE_DS
         HODE_LAUNCH_CHECK();
         return 0;
     }
@@ -611,8 +747,13 @@ int launch_dopri5_fwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t s
     const int threads = a.per_traj ? (a.batch >= 128 ? 128 : round_up32(a.batch)) : round_up32(a.batch);
     const int tiles = a.per_traj ? (int)((a.batch + threads - 1) / threads) : 1;
     const int64_t nblk = a.n_groups * tiles;
-#define HODE_DF(PT, ND, MAXT, CP) \
-    dopri5_fwd_kernel<F, PT, ND, MAXT, CP><<<(unsigned)nblk, threads, ((CP ? 0 : F::SP) + 128) * sizeof(float), st>>>(a, tiles)
+#define HODE_DF(PT, ND, MAXT, CP)                                                                                             \
+    do {                                                                                                                      \
+        const size_t sh_ = ((CP ? 0 : round4(F::SP)) + 128 + D5Store<F>::fwd_floats(MAXT <= 128 ? 128 : threads)) * sizeof(float); \
+        int e_ = set_smem(dopri5_fwd_kernel<F, PT, ND, MAXT, CP>, sh_);                                                       \
+        if (e_ != 0) return e_;                                                                                               \
+        dopri5_fwd_kernel<F, PT, ND, MAXT, CP><<<(unsigned)nblk, threads, sh_, st>>>(a, tiles);                               \
+    } while (0)
 #define HODE_DF_CP(CP)                                                                                       \
     do {                                                                                                     \
         if (a.per_traj) { if (nd1) HODE_DF(true, 1, 128, CP); else HODE_DF(true, 0, 128, CP); }              \
@@ -634,12 +775,13 @@ int launch_dopri5_bwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t s
     const int64_t nblk = a.n_groups * tiles;
     const bool nd1 = cfg.n_dose == 1;
     const bool eg = cfg.expert_grads != 0;
+    size_t coop_floats = 0;
+    if constexpr (CoopD5<F>::value) coop_floats = (size_t)CoopD5<F>::type::kStageFloats * 4;
 #define HODE_DB(EG, ND, CP)                                                                                              \
     do {                                                                                                                 \
-        const size_t sh_ = ((CP ? 0 : F::SP) + F::P + (size_t)Dopri5BwdStore<F>::floats_per_thread * threads +           \
-                            coop_stage_floats<F>() * (size_t)(threads / 32)) * sizeof(float);                            \
-        if (sh_ > 48 * 1024)                                                                                             \
-            cudaFuncSetAttribute(dopri5_bwd_kernel<F, EG, ND, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_); \
+        const size_t sh_ = ((CP ? 0 : round4(F::SP)) + round4(F::P) + D5Store<F>::bwd_floats(128) + coop_floats) * sizeof(float); \
+        int e_ = set_smem(dopri5_bwd_kernel<F, EG, ND, CP>, sh_);                                                        \
+        if (e_ != 0) return e_;                                                                                          \
         dopri5_bwd_kernel<F, EG, ND, CP><<<(unsigned)nblk, threads, sh_, st>>>(a, tiles);                                \
     } while (0)
 #define HODE_DB_CP(CP)                                                         \

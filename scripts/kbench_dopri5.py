@@ -22,9 +22,11 @@ ap.add_argument("--cap", type=int, default=768)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--hill2", type=int, default=1)
 ap.add_argument("--eg", type=int, default=0)
+ap.add_argument("--lib", default=None)
+ap.add_argument("--peak", type=float, default=72.1, help="FP32 FMA peak in TFLOP/s for the printed roofline fractions")
 args = ap.parse_args()
 dev = "cuda:0"
-lib = L.get_lib()
+lib = L.get_lib() if args.lib is None else L.HodeLib(args.lib)
 G, Bg, D = args.groups, args.batch, args.D
 B = G * Bg
 torch.manual_seed(0)
@@ -58,7 +60,11 @@ gh = torch.randn_like(h)
 t_b, _ = ev(lambda: ops.dopri5_bwd(lib, pb, tt, gh, tape, stats))
 per = Bg if ctrl == L.CTRL_BATCH else 1
 acc, rej = int(st[:, 0].sum()) * per, int(st[:, 1].sum()) * per
-print(json.dumps({"groups": G, "batch": Bg, "D": D, "ctrl": args.ctrl, "rtol": args.rtol, "fwd_notape_ms": t_f0, "fwd_ms": t_f, "bwd_ms": t_b,
+Ff = 29 + 2 * D * (D - 4) + (D - 4) + 3 + (D - 4)
+fl_att, fl_acc = 6 * Ff + 64 * D, 44 * D
+fwd_flops = (acc + rej) * fl_att + acc * fl_acc
+bwd_flops = 3 * acc * (fl_att + fl_acc)
+print(json.dumps({"roof_fwd": fwd_flops / t_f / 1e9 / args.peak, "roof_bwd": bwd_flops / t_b / 1e9 / args.peak, "groups": G, "batch": Bg, "D": D, "ctrl": args.ctrl, "rtol": args.rtol, "fwd_notape_ms": t_f0, "fwd_ms": t_f, "bwd_ms": t_b,
                   "acc_per_ctrl": float(st[:, 0].float().mean()), "rej_per_ctrl": float(st[:, 1].float().mean()),
                   "max_acc": int(st[:, 0].max()), "traj_attempts": acc + rej,
                   "fwd_Gattempts_s": (acc + rej) / t_f / 1e6, "fwdbwd_Gattempts_s": (acc + rej) / (t_f + t_b) / 1e6,

@@ -6,9 +6,12 @@
 // oracle without a GPU.  It exports the solver subset of the include/hode.h ABI, taking HOST pointers.
 #define HODE_HOSTSIM 1
 #define HODE_HAVE_NEURAL 1
+#include <algorithm>
 #include <barrier>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "../../hybrid_ode_neurips_2021_b200/csrc/hode_bodies.cuh"
@@ -18,7 +21,9 @@ using namespace hode;
 
 namespace {
 struct CommNone {
+    void sum1(float&) {}
     void sum2(float&, float&) {}
+    bool any(bool p) { return p; }
 };
 struct CommThreads {
     std::barrier<>* bar;
@@ -33,7 +38,30 @@ struct CommThreads {
         bar->arrive_and_wait();
         a = sa; b = sb;
     }
+    void sum1(float& a) { float z = 0.f; sum2(a, z); }
+    bool any(bool p) { float v = p ? 1.f : 0.f, z = 0.f; sum2(v, z); return v > 0.f; }
 };
+// Row storage of the dopri5 bodies: the device keeps the rows of the D = 12 kernels in shared memory with ROLLED stage
+// loops (RowsMem) and in registers with unrolled loops otherwise (RowsReg).  The emulation follows the same policy;
+// HODE_HOSTSIM_ROWS=mem / reg forces one of the two code paths for every D (both are tested).
+bool rows_in_memory(int D) {
+    const char* e = getenv("HODE_HOSTSIM_ROWS");
+    if (e && !strcmp(e, "mem")) return true;
+    if (e && !strcmp(e, "reg")) return false;
+    return D >= 12;
+}
+template <class F, int NR, class Fn>
+void with_rows(Fn&& fn) {
+    if (rows_in_memory(F::D)) {
+        using RM = RowsMem<F::D, NR>;
+        std::vector<float> buf(RM::kFloatsPerThread);
+        RM rows{buf.data(), RM::VEC};
+        fn(rows, std::true_type{});  // rolled stage loops, like the device's shared-memory variant
+    } else {
+        RowsReg<F::D, NR> rows;
+        fn(rows, std::false_type{});
+    }
+}
 
 void fill(SolveArgs& a, const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,
           const float* dose_t, int64_t stride, const float* params, const int32_t* pset) {
@@ -100,7 +128,7 @@ void dopri5_fwd(const SolveArgs& a) {
             for (int64_t b = 0; b < a.batch; ++b) {
                 const int64_t idx = g * a.batch + b;
                 CommNone cm;
-                dopri5_fwd_traj<F>(a, cm, sp.data(), dose(a, idx), idx, true, idx, true, (float)F::D);
+                with_rows<F, 7>([&](auto& k, auto rolled) { dopri5_fwd_traj<F, decltype(rolled)::value>(a, cm, sp.data(), dose(a, idx), k, idx, true, idx, true, (float)F::D); });
             }
         } else {
             const int n = (int)a.batch;
@@ -111,7 +139,7 @@ void dopri5_fwd(const SolveArgs& a) {
                 th.emplace_back([&, b]() {
                     const int64_t idx = g * a.batch + b;
                     CommThreads cm{&bar, buf.data(), n, b};
-                    dopri5_fwd_traj<F>(a, cm, sp.data(), dose(a, idx), idx, true, g, b == 0, (float)(a.batch * F::D));
+                    with_rows<F, 7>([&](auto& k, auto rolled) { dopri5_fwd_traj<F, decltype(rolled)::value>(a, cm, sp.data(), dose(a, idx), k, idx, true, g, b == 0, (float)(a.batch * F::D)); });
                 });
             for (auto& t : th) t.join();
         }
@@ -125,8 +153,16 @@ void dopri5_bwd(const SolveArgs& a, bool eg) {
         for (int64_t b = 0; b < a.batch; ++b) {
             const int64_t idx = g * a.batch + b;
             const int64_t ctrl = a.per_traj ? idx : g;
-            if (eg) dopri5_bwd_traj<F, true>(a, sp.data(), dose(a, idx), idx, ctrl, acc.data());
-            else dopri5_bwd_traj<F, false>(a, sp.data(), dose(a, idx), idx, ctrl, acc.data());
+            // nloop = the longest tape of the launch: exercises the idle (end-aligned) iterations of the device's
+            // warp-cooperative path as well
+            int nloop = 0;
+            const int64_t n_ctrl = a.per_traj ? a.n_groups * a.batch : a.n_groups;
+            for (int64_t c = 0; c < n_ctrl; ++c) nloop = std::max(nloop, (int)a.stats[c].accepted);
+            with_rows<F, 9>([&](auto& R, auto rolled) {
+                constexpr bool RL = decltype(rolled)::value;
+                if (eg) dopri5_bwd_traj<F, true, RL>(a, sp.data(), dose(a, idx), R, idx, ctrl, acc.data(), true, nloop);
+                else dopri5_bwd_traj<F, false, RL>(a, sp.data(), dose(a, idx), R, idx, ctrl, acc.data(), true, nloop);
+            });
         }
         const int set = a.pset ? a.pset[g] : 0;
         for (int i = 0; i < F::P; ++i) a.grad_params[(int64_t)set * F::P + i] += acc[i];
