@@ -391,12 +391,13 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds
     int n_steps = 0, attempts = 0;
     bool y0_bad = cm.any(valid && any_nonfinite<D>(y0));
 
-    while (j < a.n_t) {
-        // _advance(t[j]): while next_t > rk_state.t1 -> _adaptive_step
-        if (poisoned) { status = HODE_SOLVE_NONFINITE; break; }
-        if (n_steps >= max_steps || attempts >= attempt_cap) { status = HODE_SOLVE_MAX_STEPS; break; }
-        if (!(t0 + dt > t0)) { status = HODE_SOLVE_DT_UNDERFLOW; break; }
-        if (y0_bad) { status = HODE_SOLVE_NONFINITE; break; }
+    // One trip = one attempt of _adaptive_step inside _advance(t[j]).  Returns false when this controller has finished
+    // (all outputs emitted, or a failure status).
+    auto attempt = [&]() -> bool {
+        if (poisoned) { status = HODE_SOLVE_NONFINITE; return false; }
+        if (n_steps >= max_steps || attempts >= attempt_cap) { status = HODE_SOLVE_MAX_STEPS; return false; }
+        if (!(t0 + dt > t0)) { status = HODE_SOLVE_DT_UNDERFLOW; return false; }
+        if (y0_bad) { status = HODE_SOLVE_NONFINITE; return false; }
         const double t1 = t0 + dt;
         const float t0f = (float)t0, dtf = (float)dt, t1f = (float)t1;
         // ---- the 6 new stages (row 0 holds f0: FSAL); the error estimate k @ (dt c_error) is accumulated on the fly,
@@ -437,7 +438,7 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds
         ++attempts; ++n_steps;
         if (accept) {
             if (a.tape_y != nullptr) {
-                if (nacc >= a.tape_cap) { status = HODE_SOLVE_TAPE_FULL; break; }
+                if (nacc >= a.tape_cap) { status = HODE_SOLVE_TAPE_FULL; return false; }
                 if (valid) store_vec<D>(a.tape_y + ((int64_t)nacc * n_traj + idx) * D, y0);
                 if (leader) {
                     a.tape_t[(ctrl * a.tape_cap + nacc) * 2] = t0;
@@ -496,6 +497,13 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds
             ++nrej;
         }
         dt = optimal_step(dt, ratio, safety, ifactor, dfactor);
+        return j < a.n_t;
+    };
+    // Controllers that share a warp (lane segments) are re-converged before every attempt, so that they walk the stage loop
+    // in lock-step and share its instruction issue; a finished controller idles until the last one of its warp is done.
+    bool done = !(j < a.n_t);
+    while (!cm.all_done(done)) {
+        if (!done) done = !attempt();
     }
     if (leader) {
         hode_stats st;

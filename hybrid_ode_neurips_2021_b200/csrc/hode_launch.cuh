@@ -21,6 +21,9 @@
 #ifndef HODE_D5_FWD_MINBLOCKS
 #define HODE_D5_FWD_MINBLOCKS 4
 #endif
+#ifndef HODE_D5_FWD_MINBLOCKS_REG
+#define HODE_D5_FWD_MINBLOCKS_REG 4
+#endif
 #ifndef HODE_DOPRI5_MAX_THREADS
 #define HODE_DOPRI5_MAX_THREADS 512
 #endif
@@ -33,6 +36,7 @@ struct CommNone {
     __device__ __forceinline__ void sum1(float&) {}
     __device__ __forceinline__ void sum2(float&, float&) {}
     __device__ __forceinline__ bool any(bool p) { return p; }
+    __device__ __forceinline__ bool all_done(bool done) { return done; }
 };
 struct CommCta {
     float* red;  // 2 buffers x (2 * 32) floats of shared memory, used alternately: ONE barrier per reduction
@@ -75,6 +79,7 @@ struct CommCta {
         if (nwarps > 1) return __syncthreads_or(p ? 1 : 0) != 0;
         return __any_sync(0xffffffffu, p) != 0;
     }
+    __device__ __forceinline__ bool all_done(bool done) { return done; }  // CTA-uniform by construction
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -178,6 +183,9 @@ struct CommSeg {
     }
     __device__ __forceinline__ void sum2(float& a, float& b) { sum1(a); sum1(b); }
     __device__ __forceinline__ bool any(bool p) { return (__ballot_sync(mask, p) & mask) != 0u; }
+    // re-converges every controller of the warp (`part` = the warp's participating lanes) and tells whether all are done
+    unsigned part;
+    __device__ __forceinline__ bool all_done(bool done) { return __all_sync(part, done) != 0; }
 };
 
 template <class F>
@@ -452,7 +460,7 @@ struct D5Store {
     // ~250 registers again (or spills at the 128 / 168 caps).
     static constexpr bool kFwdRolled = kSmem, kBwdRolled = kSmem;
     static constexpr int kFwdRows = 7, kBwdRows = 9;
-    static constexpr int kFwdMinBlocks = kSmem ? HODE_D5_FWD_MINBLOCKS : 1;  // 128-thread CTAs per SM the register budget must allow
+    static constexpr int kFwdMinBlocks = kSmem ? HODE_D5_FWD_MINBLOCKS : (F::D <= 6 ? HODE_D5_FWD_MINBLOCKS_REG : 1);  // 128-thread CTAs per SM the register budget must allow
     static constexpr int kBwdMinBlocks = kSmem ? 3 : 1;
     __host__ __device__ static constexpr size_t fwd_floats(int threads) { return kSmem ? (size_t)kFwdRows * F::D * threads : 0; }
     __host__ __device__ static constexpr size_t bwd_floats(int threads) { return kSmem ? (size_t)kBwdRows * F::D * threads : 0; }
@@ -522,6 +530,7 @@ __global__ void __launch_bounds__(128, D5Store<F>::kFwdMinBlocks) dopri5_fwd_seg
     const int64_t group = warp * gpw + seg;
     if (group >= a.n_groups) return;
     CommSeg cm;
+    cm.part = __activemask();  // lanes left after the early returns above (converged here)
     const int base = seg * size;
     cm.rel = lane - base;
     cm.nvec = (size + 3) >> 2;

@@ -24,6 +24,7 @@ struct CommNone {
     void sum1(float&) {}
     void sum2(float&, float&) {}
     bool any(bool p) { return p; }
+    bool all_done(bool done) { return done; }
 };
 struct CommThreads {
     std::barrier<>* bar;
@@ -40,6 +41,7 @@ struct CommThreads {
     }
     void sum1(float& a) { float z = 0.f; sum2(a, z); }
     bool any(bool p) { float v = p ? 1.f : 0.f, z = 0.f; sum2(v, z); return v > 0.f; }
+    bool all_done(bool done) { return done; }
 };
 // Row storage of the dopri5 bodies: the device keeps the rows of the D = 12 kernels in shared memory with ROLLED stage
 // loops (RowsMem) and in registers with unrolled loops otherwise (RowsReg).  The emulation follows the same policy;
