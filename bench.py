@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- the contract benchmark of the hybrid-ODE hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--patients B]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--patients B] [--scaling weak|strong]
 
 Workload (BASELINE.json configs[1] shape, metric "patient-trajectory solver steps/sec fwd+bwd"):
   2**20 synthetic patients per GPU, dim-8 hybrid RocheODE (generate_data_dim8.py shape: D=8, obs=40, T=15), fixed-step
@@ -16,8 +16,18 @@ Data: synthetic, drawn from the reference generator's distributions (dataloader.
 one dose per patient on a uniform day 0..13 with amount U(0, 10), x ~ N(0,1), mask ~ Bernoulli(0.5); weights: default
 nn.Linear init under torch.manual_seed(666), expert scalars at RochConfig defaults.
 
---impl reference: the reference's CPU path (oracle port of model.py + restated torchdiffeq; /root/reference and the
-torchdiffeq package do not exist on the GPU box) on all host cores, each step a bounded sample of the same workload.
+End to end (`e2e`): the same step through the public API from pinned HOST buffers -- float32 y0 / actions / measurements and
+the 0/1 masks as ONE BYTE per entry (the reference's masks are float32 0/1 tensors, dataloader.py:264-266; masked_sse takes
+uint8 / bool masks and the results are identical) -- H2D copies on a copy stream inside the timed region, loss + packed
+gradients read back.  `e2e_float_masks` is the same with 4-byte masks, `e2e_resident` the reference's actual usage
+(dg.set_device(device), run_simulation.py:65: the cohort is moved to the device once per run, not once per step).
+
+--scaling strong: `--patients` is the TOTAL cohort, split over the ranks (default weak: `--patients` per GPU).
+
+--impl reference: the reference's CPU path on all host cores, each step a bounded sample of the same workload: the
+reference's own model.py classes (RocheODE vector field + set_action + output_function, from the byte-identical copy in
+baseline/_ref made by oracle/install_reference.py) driven by the restated torchdiffeq 0.2.2 (oracle/odeint.py; the package
+is not installable offline) -- kind "reference"; the oracle port of model.py if baseline/_ref is absent -- kind "port".
 """
 from __future__ import annotations
 
@@ -157,25 +167,48 @@ def dist_setup(n_gpus):
 
 
 # -------------------------------------------------------------------------------------------------------------------
-def cpu_reference_rate(sample_patients, repeats, threads=None):
-    """Oracle port of the reference path on the host cores: fwd + read-out + masked SSE + backward (autograd)."""
-    from oracle import fields as OF
+def reference_decoder():
+    """The reference's CPU implementation of the path for the C2 workload.  Returns (kind, decoder-like callable, loss).
 
-    torch.set_num_threads(threads or os.cpu_count() or 1)
+    kind "reference": model.RocheODE / output_function of the reference's own model.py (baseline/_ref or /root/reference),
+    integrated by the restated torchdiffeq with options={'step_size': 1/16}.  (RocheExpertDecoder.forward itself never
+    forwards a step size -- model.py:1116-1118 -- and the default grid h = 1 diverges to NaN, SURVEY.md fact 6, so the
+    decoder's three statements are issued here with the option added.)  kind "port": the oracle's restatement of model.py."""
+    from oracle import fields as OF
+    from oracle import odeint as OI
+    from oracle import refload
+
     torch.manual_seed(666)
+    if refload.available():
+        M = refload.load("model")
+        dec = M.RocheExpertDecoder(OBS, D, 1, T_MAX, 1, roche=True, method="rk4", device=torch.device("cpu"))
+
+        def run(z, a):
+            dec.ode.set_action(a)  # the reference's O(B) Python loop, model.py:495-507
+            h = OI.odeint(dec.ode, z, dec.t, rtol=1e-7, atol=1e-8, method="rk4", options={"step_size": STEP})
+            return dec.output_function(h), h
+
+        return "reference", dec, run, (lambda x, xh, m: torch.sum((x - xh) ** 2 * m) / x.shape[1])
     dec = OF.OracleDecoder(OBS, D, method="rk4", options={"step_size": STEP})
+    return "port", dec, (lambda z, a: dec(z, a)), OF.masked_sse
+
+
+def cpu_reference_rate(sample_patients, repeats, threads=None):
+    """The reference path on the host cores: set_action + fwd + read-out + masked SSE + backward (autograd)."""
+    torch.set_num_threads(threads or os.cpu_count() or 1)
+    kind, dec, run, lossf = reference_decoder()
     y0, a, x, mask = synth_cohort(sample_patients, seed=1)
     times = []
     for _ in range(repeats):
         dec.zero_grad()
         z = y0.clone().requires_grad_(True)
         t0 = time.perf_counter()
-        xh, _ = dec(z, a)
-        loss = OF.masked_sse(x, xh, mask)
+        xh, _ = run(z, a)
+        loss = lossf(x, xh, mask)
         loss.backward()
         times.append(time.perf_counter() - t0)
     best = min(times)
-    return sample_patients * N_STEPS / best, best, torch.get_num_threads()
+    return sample_patients * N_STEPS / best, best, torch.get_num_threads(), kind
 
 
 def run_reference(args):
@@ -183,20 +216,17 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import fields as OF
-
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    torch.manual_seed(666)
     B = args.ref_patients
-    dec = OF.OracleDecoder(OBS, D, method="rk4", options={"step_size": STEP})
+    kind, dec, run, lossf = reference_decoder()
     y0, a, x, mask = synth_cohort(B, seed=1)
 
     def step():
         dec.zero_grad()
         z = y0.clone().requires_grad_(True)
-        xh, _ = dec(z, a)
-        loss = OF.masked_sse(x, xh, mask)
+        xh, _ = run(z, a)
+        loss = lossf(x, xh, mask)
         loss.backward()
         return loss.item()
 
@@ -207,14 +237,15 @@ def run_reference(args):
         step()
     el = time.perf_counter() - t0
     val = B * N_STEPS * args.steps / el
-    sample = "{} patients per step (of the 2^20-patient workload), fwd + read-out/masked-SSE + autograd backward".format(B)
+    what = ("reference model.py classes (baseline/_ref) + restated torchdiffeq 0.2.2" if kind == "reference"
+            else "oracle port of model.py + restated torchdiffeq 0.2.2 (baseline/_ref absent)")
+    sample = "{} patients per step (of the 2^20-patient workload), set_action + fwd + read-out/masked-SSE + autograd backward".format(B)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(B, world=1, note="reference CPU path: oracle port of model.py + restated torchdiffeq 0.2.2 "
-                                                   "(neither /root/reference nor torchdiffeq exists on the GPU box)"),
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+        "config": workload_config(B, world=1, note="reference CPU path: " + what),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -260,6 +291,28 @@ class StdoutToStderr:
         self.saved = None
 
 
+def numa_local_affinity(dev_index):
+    """Pin this process to the cores of the GPU's NUMA node BEFORE any host buffer is allocated or pinned (first-touch page
+    placement): with all ranks on one node, 8 GPUs' worth of pinned H2D traffic crosses one socket's memory controllers
+    (round 1: 182 GB/s aggregate at N = 8).  Returns a description for the JSON line."""
+    try:
+        pr = torch.cuda.get_device_properties(dev_index)
+        bus = "{:04x}:{:02x}:{:02x}.0".format(pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/{}/numa_node".format(bus)).read().strip())
+        if node < 0:
+            return {"pci": bus, "numa_node": node, "pinned": False}
+        cpus = set()
+        for part in open("/sys/devices/system/node/node{}/cpulist".format(node)).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0) or cpus
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"pci": bus, "numa_node": node, "pinned": bool(cpus), "cores": len(cpus)}
+    except Exception as e:  # best effort: containers may hide sysfs
+        return {"error": repr(e), "pinned": False}
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -270,47 +323,79 @@ def run_ours(args):
     from hybrid_ode_neurips_2021_b200 import dist as hd
 
     world, rank, local = dist_setup(args.gpus)
-    # torchrun pins OMP_NUM_THREADS=1: give every rank its share of the host cores for the synthetic-cohort generation
-    torch.set_num_threads(max(1, (os.cpu_count() or 1) // max(world, 1)))
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
+    numa = numa_local_affinity(local)
+    # torchrun pins OMP_NUM_THREADS=1: give every rank its share of the host cores for the synthetic-cohort generation
+    torch.set_num_threads(max(1, min(len(os.sched_getaffinity(0)), (os.cpu_count() or 1) // max(world, 1))))
     lib = L.get_lib()  # raises if the CUDA extension is missing: no fallback
-    B = args.patients
+    strong = args.scaling == "strong"
+    B = args.patients // world if strong else args.patients  # patients per GPU
+    B_global = B * world
     torch.manual_seed(666)
     dec = H.RocheExpertDecoder(OBS, D, 1, T_MAX, 1, method="rk4", device=dev,
                                solver_options={"step_size": STEP, "expert_grads": False})
+    for n_, p_ in dec.ode.named_parameters():  # the optimizer of the reference never receives the 13 expert scalars
+        if not n_.startswith("ml_net"):        # (run_simulation.py:125-129): trained are ml_net + output_function
+            p_.requires_grad_(False)
+    train_params = list(dec.output_function.parameters()) + list(dec.ode.ml_net.parameters())
+    fg = hd.FlatGrads(train_params, extra=1)  # gradients live in ONE flat buffer: no pack / unpack kernels, one collective
+
+    # ---- multi-GPU correctness: the all-reduced gradient of a cohort split N ways == the 1-GPU gradient of the cohort ------
+    grad_check = None
+    if world > 1:
+        Bc = 1 << 16
+        y0c, ac, xc, mc = [t.to(dev) for t in synth_cohort(Bc, seed=4242)]
+
+        def cohort_grad(lo, hi):
+            fg.zero_()
+            z = y0c[lo:hi].detach().requires_grad_(True)
+            h = dec.solve(z, ac[:, lo:hi])
+            loss = H.masked_sse(dec, h, xc[:, lo:hi], mc[:, lo:hi], n_norm=Bc)
+            loss.backward()
+            fg.extra.copy_(loss.detach().reshape(1))
+
+        cohort_grad(0, Bc)
+        full = fg.flat.clone()
+        lo, hi = hd.shard_range(Bc, rank, world)
+        cohort_grad(lo, hi)
+        fg.allreduce()
+        err = float((fg.grads - full[:-1]).abs().max() / full[:-1].abs().max())
+        lerr = float((fg.extra - full[-1:]).abs().max() / full[-1:].abs().max())
+        grad_check = {"patients": Bc, "ranks": world, "grad_relerr_inf": err, "loss_relerr": lerr, "tol": 5e-4,
+                      "ok": bool(err <= 5e-4 and lerr <= 1e-5)}
+        if not grad_check["ok"]:
+            raise AssertionError("all-reduced sharded gradient differs from the single-GPU gradient: {}".format(grad_check))
+        del y0c, ac, xc, mc, full
+
     # host cohort = E2E_CHUNKS mini-batches in pinned memory (what a data loader hands to the training loop, cf.
     # dataloader.py:322 get_split); the device-resident cohort of the kernel-level measurement is their concatenation
     n_chunks = max(1, min(args.e2e_chunks, B // 1024)) if B >= 1024 else 1
     bounds = [(B * i) // n_chunks for i in range(n_chunks + 1)]
-    host_chunks = [synth_cohort(bounds[i + 1] - bounds[i], seed=1000 + 97 * rank + i, pin=True) for i in range(n_chunks)]
-    y0 = torch.cat([c[0].to(dev) for c in host_chunks], dim=0)
-    a, x, mask = (torch.cat([c[k].to(dev) for c in host_chunks], dim=1).contiguous() for k in (1, 2, 3))
-    train_params = list(dec.output_function.parameters()) + list(dec.ode.ml_net.parameters())
-    B_global = B * world
+    host_f32 = [synth_cohort(bounds[i + 1] - bounds[i], seed=1000 + 97 * rank + i, pin=True) for i in range(n_chunks)]
+    host_u8 = [(c[0], c[1], c[2], c[3].to(torch.uint8).pin_memory()) for c in host_f32]  # contract path: 1-byte masks
+    y0 = torch.cat([c[0].to(dev) for c in host_f32], dim=0)
+    a, x, mask = (torch.cat([c[k].to(dev) for c in host_f32], dim=1).contiguous() for k in (1, 2, 3))
 
     def device_step():
-        for p in dec.parameters():
-            p.grad = None
+        fg.zero_()
         z = y0.detach().requires_grad_(True)
         h = dec.solve(z, a)
         loss = H.masked_sse(dec, h, x, mask, n_norm=B_global)
         loss.backward()
-        total = hd.allreduce_grads(train_params, extra=loss.detach().reshape(1))
-        return loss if total is None else total
+        fg.extra.copy_(loss.detach().reshape(1))
+        return fg.allreduce()
 
     copy_stream = torch.cuda.Stream(device=dev)
 
-    def e2e_step(chunks=None):
+    def e2e_step(chunks):
         """Public API from HOST buffers: every mini-batch is copied host->device on a copy stream while the previous one
-        is solved (forward + loss + backward, gradients accumulate in .grad); one gradient all-reduce; the loss and the
-        packed gradients are read back."""
-        for p in dec.parameters():
-            p.grad = None
+        is solved (forward + loss + backward, gradients accumulate in the flat buffer); one gradient all-reduce; the loss
+        and the packed gradients are read back."""
+        fg.zero_()
         main = torch.cuda.current_stream(dev)
-        loss_sum = torch.zeros((), device=dev)
         keep = []
-        for (y0_c, a_c, x_c, m_c) in (host_chunks if chunks is None else chunks):
+        for (y0_c, a_c, x_c, m_c) in chunks:
             with torch.cuda.stream(copy_stream):
                 dev_c = [t.to(dev, non_blocking=True) for t in (y0_c, a_c, x_c, m_c)]
                 ready = torch.cuda.Event()
@@ -323,11 +408,15 @@ def run_ours(args):
             h = dec.solve(z, dev_c[1])
             loss = H.masked_sse(dec, h, dev_c[2], dev_c[3], n_norm=B_global)
             loss.backward()
-            loss_sum += loss.detach()
-        total = hd.allreduce_grads(train_params, extra=loss_sum.reshape(1))
-        out = loss_sum if total is None else total
-        flat, _ = hd.pack_grads(train_params)
-        return float(out.item()), flat.cpu()
+            fg.extra.add_(loss.detach().reshape(1))
+        fg.allreduce()
+        return fg.flat.cpu()  # loss + packed gradients: the device->host read of the step's result
+
+    def resident_step():
+        """The reference's actual usage: the cohort lives on the device (dg.set_device, run_simulation.py:65); per step only
+        the loss and the gradients come back."""
+        device_step()
+        return fg.flat.cpu()
 
     def fwd_only_step():
         with torch.no_grad():
@@ -355,6 +444,8 @@ def run_ours(args):
             ms, wall = float(tt[0]), float(tt[1]) / 1e3
         return ms, wall
 
+    rate = lambda ms, wall=0.0: B_global * N_STEPS * args.steps / max(ms * 1e-3, wall)  # noqa: E731
+
     # every rank runs the SAME sequence of steps (device_step contains a collective when N > 1); only rank 0 samples clocks
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler is not None:
@@ -373,27 +464,44 @@ def run_ours(args):
         torch.cuda.synchronize()
     if sampler is not None:
         sampler.__exit__()
-    value = B_global * N_STEPS * args.steps / (ms * 1e-3)
+    value = rate(ms)
 
     for _ in range(2):
         fwd_only_step()
     ms_f, _ = timed(fwd_only_step, args.steps)
     for _ in range(2):
-        e2e_step()
-    ms_e, wall_e = timed(e2e_step, args.steps)
-    e2e_val = B_global * N_STEPS * args.steps / max(ms_e * 1e-3, wall_e)
-    # Secondary: the same end-to-end step when the data loader keeps the 0/1 masks as one byte per entry on the host
-    # (masked_sse accepts uint8 / bool masks and widens them on the device; the values, and so the results, are identical).
-    # The contract `e2e` above uses the reference's own float32 masks.
-    chunks_u8 = [(c[0], c[1], c[2], c[3].to(torch.uint8).pin_memory()) for c in host_chunks]
+        e2e_step(host_u8)
+    ms_e, wall_e = timed(lambda: e2e_step(host_u8), args.steps)
     for _ in range(2):
-        e2e_step(chunks_u8)
-    ms_c, wall_c = timed(lambda: e2e_step(chunks_u8), args.steps)
-    e2e_compact = {"value": B_global * N_STEPS * args.steps / max(ms_c * 1e-3, wall_c), "unit": UNIT,
-                   "ms_per_step": max(ms_c, wall_c * 1e3) / args.steps,
-                   "h2d_bytes_per_step": world * sum(t.numel() * t.element_size() for c in chunks_u8 for t in c),
-                   "note": "same step with uint8 masks in the pinned host buffers (1 byte instead of 4 per mask entry)"}
-    del chunks_u8
+        e2e_step(host_f32)
+    ms_c, wall_c = timed(lambda: e2e_step(host_f32), args.steps)
+    for _ in range(2):
+        resident_step()
+    ms_r, wall_r = timed(resident_step, args.steps)
+    bytes_of = lambda chunks: world * sum(t.numel() * t.element_size() for c in chunks for t in c)  # noqa: E731
+    n_par = fg.n_params
+    e2e = {"value": rate(ms_e, wall_e), "unit": UNIT, "h2d_bytes_per_step": bytes_of(host_u8),
+           "d2h_bytes_per_step": world * 4 * (n_par + 1), "ms_per_step": max(ms_e, wall_e * 1e3) / args.steps,
+           "api": "RocheExpertDecoder.solve + masked_sse + backward over {} pinned host mini-batches per GPU (float32 y0 / "
+                  "actions / measurements, uint8 masks), H2D on a copy stream overlapped with the previous mini-batch's "
+                  "kernels; loss + packed gradients read back".format(n_chunks)}
+    e2e_float = {"value": rate(ms_c, wall_c), "unit": UNIT, "ms_per_step": max(ms_c, wall_c * 1e3) / args.steps,
+                 "h2d_bytes_per_step": bytes_of(host_f32), "note": "same step with the reference's float32 0/1 masks on the host"}
+    e2e_resident = {"value": rate(ms_r, wall_r), "unit": UNIT, "ms_per_step": max(ms_r, wall_r * 1e3) / args.steps,
+                    "h2d_bytes_per_step": 0, "d2h_bytes_per_step": world * 4 * (n_par + 1),
+                    "note": "cohort resident on the device (the reference's dg.set_device usage, run_simulation.py:65); per "
+                            "step only the loss + packed gradients are read back"}
+
+    # ---- host -> device ceiling of this box: every rank copies its own pinned 1 GiB buffer, all ranks at once ---------------
+    probe = torch.empty(1 << 30, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(1 << 30, dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        dst.copy_(probe, non_blocking=True)
+    ms_p, _ = timed(lambda: dst.copy_(probe, non_blocking=True), 5)
+    h2d_probe = {"gbs_per_gpu_all_ranks_concurrently": 5 * (1 << 30) / (ms_p * 1e-3) / 1e9, "ranks": world,
+                 "aggregate_gbs": world * 5 * (1 << 30) / (ms_p * 1e-3) / 1e9, "numa": numa,
+                 "note": "cudaMemcpyAsync of one pinned 1 GiB buffer per rank, max over ranks of the time"}
+    del probe, dst
 
     # Every collective of the run is done.  Tear the process group down NOW on every rank: what follows is rank 0's own
     # post-processing (kernel-level timing, CPU baseline), and a rank parked in an NCCL barrier meanwhile would hit the
@@ -404,6 +512,7 @@ def run_ours(args):
         dist.destroy_process_group()
         if rank != 0:
             return
+    del host_u8
 
     # ---- per-kernel device times for the roofline (CUDA events on the launching stream, same buffers) -----------------
     roof, extra = None, {}
@@ -439,13 +548,7 @@ def run_ours(args):
         adj_grid, adj_count = adj_grid.to(dev), adj_count.to(dev)
         t_fwd_nt, _ = ev_time(lambda: ops.fixed_fwd(lib, pb, y0, grid, tt, False))
         t_adj, _ = ev_time(lambda: ops.fixed_adjoint(lib, pb, adj_grid, adj_count, h, gh))
-        # FP32 FMA peak, measured in this run (MEASURED_PEAKS.json carries HBM and bf16 only)
-        sms = torch.cuda.get_device_properties(dev).multi_processor_count
-        out = torch.zeros(1, device=dev)
-        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        probe = lambda: lib.hode_bench_ffma(sms * 8, 1 << 14, ctypes.c_void_p(out.data_ptr()), stream)  # noqa: E731
-        t_probe, flops_probe = ev_time(probe)
-        fma_peak = flops_probe / (t_probe * 1e-3) / 1e12
+        fma_peak, peak_src = ffma_peak(lib, dev, ev_time)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -461,7 +564,7 @@ def run_ours(args):
             "achieved": bwd_flops / (t_bwd * 1e-3) / 1e12, "peak": fma_peak, "unit": "TFLOP/s",
             "frac": bwd_flops / (t_bwd * 1e-3) / 1e12 / fma_peak, "traffic": traffic, "traffic_source": traffic_src,
             "algorithmic_bytes_per_launch": B * 4 * D * (N_STEPS + T + 1),  # tape + grad_h read, grad_y0 written
-            "peak_source": "FFMA probe kernel timed in this run ({} SMs; nominal 148 x 128 lanes x 2 x 1.965 GHz = 74.5)".format(sms),
+            "peak_source": peak_src,
             "algorithmic_flops_per_traj_step": FLOPS_BWD_STEP, "launch_ms": t_bwd,
         }
         dec_bytes = T * B * (2 * OBS + 2 * D) * 4
@@ -482,44 +585,60 @@ def run_ours(args):
         }
         del h, tape, gh
         if not args.no_extras and world == 1:  # secondary figures and CPU baselines: N = 1 only
+            del y0, a, x, mask
+            torch.cuda.empty_cache()
             try:
-                extra["other_configs"] = dopri5_extras(lib, dev)
+                oc = dopri5_extras(lib, dev, fma_peak)
                 cpu = dopri5_cpu_baselines()
                 for k, v in cpu.items():
-                    if k in extra["other_configs"] and "error" not in extra["other_configs"][k]:
-                        extra["other_configs"][k]["cpu_baseline"] = v
+                    if k in oc and "error" not in oc[k]:
+                        oc[k]["cpu_baseline"] = v
+                extra["other_configs"] = oc
+                for key, name in (("roofline_c3", "C3_dim12_dopri5_groups_of_10"), ("roofline_c1", "C1_dim6_dopri5_groups_of_50")):
+                    if name in oc and "roofline" in oc[name]:
+                        extra[key] = oc[name]["roofline"]
+                extra["other_configs"]["C4_ensemble_members"] = ensemble_extra(dev)
             except Exception as e:  # secondary figures must never take the headline down
-                extra["other_configs"] = {"error": repr(e)}
+                extra.setdefault("other_configs", {})["error"] = repr(e)
 
     if world == 1:
-        cpu_val, cpu_s, cores = cpu_reference_rate(args.cpu_patients, 2)
-        cpu_baseline = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": "{} patients of the same workload, fwd + read-out/masked-SSE + autograd backward, "
+        cpu_val, cpu_s, cores, kind = cpu_reference_rate(args.cpu_patients, 2)
+        cpu_baseline = {"value": cpu_val, "unit": UNIT, "cores": cores, "kind": kind,
+                        "sample": "{} patients of the same workload, set_action + fwd + read-out/masked-SSE + autograd backward, "
                                   "best of 2 ({:.1f} s each)".format(args.cpu_patients, cpu_s)}
     else:  # the CPU baseline is a rank-0, N = 1 measurement (other ranks' host threads would share the cores)
-        cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "measured at N=1 only"}
-    h2d = world * sum(t.numel() * t.element_size() for c in host_chunks for t in c)  # whole job, like `value`
-    n_par = sum(p.numel() for p in train_params)
+        cpu_baseline = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "measured at N=1 only"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(B, world),
         "clocks": sampler.summary() if sampler else None,
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": world * (4 + 4 * n_par),
-                "ms_per_step": max(ms_e, wall_e * 1e3) / args.steps,
-                "api": "RocheExpertDecoder.solve + masked_sse + backward over {} pinned host mini-batches, H2D on a copy "
-                       "stream overlapped with the previous mini-batch's kernels".format(n_chunks)},
+        "e2e": e2e,
         "gpu_launches": 6 * args.steps,
         "gpu_launches_per_step": {"dose_schedule_kernel": 1, "prep_params_kernel": 2, "fixed_fwd_kernel": 1,
                                   "decode_sse_fast_kernel": 1, "fixed_bwd_kernel": 1},
         "roofline": roof,
         "cpu_baseline": cpu_baseline,
-        "fwd_only": {"value": B_global * N_STEPS * args.steps / (ms_f * 1e-3), "unit": UNIT, "ms_per_step": ms_f / args.steps},
-        "e2e_uint8_masks": e2e_compact,
+        "fwd_only": {"value": rate(ms_f), "unit": UNIT, "ms_per_step": ms_f / args.steps},
+        "e2e_float_masks": e2e_float,
+        "e2e_resident": e2e_resident,
+        "h2d_probe": h2d_probe,
+        "grad_check": grad_check,
     }
     line.update(extra)
     quiet.restore()
     print(json.dumps(line), flush=True)
+
+
+def ffma_peak(lib, dev, ev_time):
+    """FP32 FMA peak measured in this run (MEASURED_PEAKS.json carries HBM and bf16 only)."""
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    out = torch.zeros(1, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    probe = lambda: lib.hode_bench_ffma(sms * 8, 1 << 14, ctypes.c_void_p(out.data_ptr()), stream)  # noqa: E731
+    t_probe, flops_probe = ev_time(probe)
+    return flops_probe / (t_probe * 1e-3) / 1e12, ("FFMA probe kernel timed in this run ({} SMs; nominal 148 x 128 lanes x 2 x "
+                                                   "1.965 GHz = 74.5)".format(sms))
 
 
 def ncu_traffic(kernel_file, patients):
@@ -539,17 +658,18 @@ def ncu_traffic(kernel_file, patients):
         return None, None
 
 
-def dopri5_extras(lib, dev):
-    """Secondary figures (not the headline): adaptive dopri5 at the reference tolerances (rtol 1e-7 / atol 1e-8,
+def dopri5_extras(lib, dev, fma_peak):
+    """Secondary configurations (not the headline): adaptive dopri5 at the reference tolerances (rtol 1e-7 / atol 1e-8,
     model.py:1079-1080), forward + tape + reverse sweep, batch-coupled controller = one controller per odeint call.
-    C3 shape (run_dim.sh:41): D = 12, groups of 10 patients; C1 shape (sim_config.py:52): D = 6, groups of 50.
-    1 trajectory-step = one attempt (accepted or rejected) of one trajectory."""
+    C3 shape (BASELINE configs[2], run_dim.sh:41): D = 12, odeint calls of 10 patients; C1 shape (sim_config.py:52): D = 6,
+    calls of 50.  1 trajectory-step = one attempt (accepted or rejected) of one trajectory.
+    Roofline flops: attempt 6 F_f + 64 D, + 44 D per accepted step; reverse sweep 3 x the accepted-step flops."""
     import hybrid_ode_neurips_2021_b200 as H
     from hybrid_ode_neurips_2021_b200 import _lib as L
     from hybrid_ode_neurips_2021_b200 import ops, solver
 
     out = {}
-    for name, Dd, groups, batch in (("C3_dim12_dopri5_groups_of_10", 12, 8192, 10), ("C1_dim6_dopri5_groups_of_50", 6, 2048, 50)):
+    for name, Dd, groups, batch in (("C3_dim12_dopri5_groups_of_10", 12, 65536, 10), ("C1_dim6_dopri5_groups_of_50", 6, 8192, 50)):
         Bt = groups * batch
         torch.manual_seed(666)
         m = H.RocheODE(Dd, 1, T_MAX, 1, device=dev)
@@ -573,19 +693,70 @@ def dopri5_extras(lib, dev):
                 ts.append(s_.elapsed_time(e_))
             return statistics.median(ts), r
 
-        t_f, (h, stats, tape) = ev(lambda: ops.dopri5_fwd(lib, pb, y0, tt, 768))
+        t_f, (h, stats, tape) = ev(lambda: ops.dopri5_fwd(lib, pb, y0, tt, 448))
         st = stats.cpu()
         if int(st[:, 3].max()) != 0:
             out[name] = {"error": "solver status {}".format(st[:, 3].unique().tolist())}
             continue
         gh = torch.randn_like(h)
         t_b, _ = ev(lambda: ops.dopri5_bwd(lib, pb, tt, gh, tape, stats))
-        attempts = int((st[:, 0] + st[:, 1]).sum()) * batch
-        out[name] = {"value": attempts / ((t_f + t_b) * 1e-3), "unit": UNIT, "fwd_ms": t_f, "bwd_ms": t_b, "patients": Bt,
-                     "accepted_per_call": float(st[:, 0].float().mean()), "rejected_per_call": float(st[:, 1].float().mean()),
-                     "latent_dim": Dd, "batch_per_odeint_call": batch}
-        del h, tape, gh
+        acc, rej = int(st[:, 0].sum()) * batch, int(st[:, 1].sum()) * batch
+        Ff = 29 + 2 * Dd * (Dd - 4) + (Dd - 4) + 3 + (Dd - 4)
+        fl_att, fl_acc = 6 * Ff + 64 * Dd, 44 * Dd
+        fwd_tf = ((acc + rej) * fl_att + acc * fl_acc) / (t_f * 1e-3) / 1e12
+        bwd_tf = 3 * acc * (fl_att + fl_acc) / (t_b * 1e-3) / 1e12
+        out[name] = {"value": (acc + rej) / ((t_f + t_b) * 1e-3), "unit": UNIT, "fwd_ms": t_f, "bwd_ms": t_b, "patients": Bt,
+                     "odeint_calls": groups, "accepted_per_call": float(st[:, 0].float().mean()),
+                     "rejected_per_call": float(st[:, 1].float().mean()), "latent_dim": Dd, "batch_per_odeint_call": batch,
+                     "roofline": {"bound": "fp32_fma", "peak": fma_peak, "unit": "TFLOP/s",
+                                  "fwd": {"kernel": "dopri5_fwd_seg_kernel" if batch <= 16 else "dopri5_fwd_kernel",
+                                          "achieved": fwd_tf, "frac": fwd_tf / fma_peak, "launch_ms": t_f,
+                                          "flops_per_attempt": fl_att, "flops_per_accepted_step_extra": fl_acc},
+                                  "bwd": {"kernel": "dopri5_bwd_kernel", "achieved": bwd_tf, "frac": bwd_tf / fma_peak,
+                                          "launch_ms": t_b, "flops_per_accepted_step": 3 * (fl_att + fl_acc)},
+                                  "frac": min(fwd_tf, bwd_tf) / fma_peak}}
+        del h, tape, gh, y0, a
+        torch.cuda.empty_cache()
     return out
+
+
+def ensemble_extra(dev):
+    """C4 (BASELINE configs[3]): M ensemble members / restarts with their OWN ml_net + expert parameters integrated and
+    differentiated in ONE launch each way (odeint_ensemble); members shard over GPUs with no cross-member reduction."""
+    import hybrid_ode_neurips_2021_b200 as H
+
+    M, Bm, Dd = 64, 4096, 6
+    torch.manual_seed(666)
+    fs = [H.RocheODE(Dd, 1, T_MAX, 1, device=dev) for _ in range(M)]
+    g = torch.Generator(device=dev).manual_seed(7)
+    y0 = torch.empty(M * Bm, Dd, device=dev).exponential_(100.0, generator=g)
+    a = torch.zeros(T, Bm, 1, device=dev)
+    a[torch.randint(0, T_MAX, (Bm,), device=dev, generator=g), torch.arange(Bm, device=dev), 0] = \
+        torch.rand(Bm, device=dev, generator=g) * 10 + 1e-3
+    for f in fs:
+        f.set_action(a)
+    tt = torch.arange(0, T_MAX + 1, 1, device=dev, dtype=torch.float32)
+    W = torch.randn(T, M * Bm, Dd, device=dev, generator=g)
+
+    def step():
+        for f in fs:
+            f.zero_grad(set_to_none=True)
+        z = y0.detach().requires_grad_(True)
+        h = H.odeint_ensemble(fs, z, tt, method="rk4", options={"step_size": STEP, "expert_grads": False})
+        (h * W).sum().backward()
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    s_, e_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s_.record()
+    for _ in range(3):
+        step()
+    e_.record(); torch.cuda.synchronize()
+    ms = s_.elapsed_time(e_) / 3
+    return {"value": M * Bm * N_STEPS / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "members": M, "patients_per_member": Bm,
+            "latent_dim": Dd, "solver": "rk4(3/8) h=1/16", "note": "odeint_ensemble fwd + reverse sweep through autograd, one "
+            "parameter set per member (shared-memory staging instead of the constant bank)"}
 
 
 def dopri5_cpu_baselines():
@@ -623,7 +794,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--patients", type=int, default=1 << 20, help="patients per GPU")
+    ap.add_argument("--patients", type=int, default=1 << 20, help="patients per GPU (weak scaling) or in total (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--cpu-patients", type=int, default=8192, help="bounded CPU-baseline sample")
     ap.add_argument("--ref-patients", type=int, default=4096, help="patients per step of --impl reference")
     ap.add_argument("--e2e-chunks", type=int, default=8, help="host mini-batches per step of the end-to-end measurement")

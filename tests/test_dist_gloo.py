@@ -3,6 +3,7 @@ gradient all-reduce give the same parameter gradients and loss as one process on
 import os
 import socket
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -30,7 +31,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, flat=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -40,17 +41,27 @@ def _worker(rank, world, port, q):
     dec = OF.OracleDecoder(obs, D, method="rk4", options={"step_size": 0.25})
     y0, a, x, mask = make_cohort(B, D, obs=obs, seed=1)
     lo, hi = hd.shard_range(B, rank, world)
-    xh, _ = dec(y0[lo:hi], a[:, lo:hi])
-    loss = torch.sum((x[:, lo:hi] - xh) ** 2 * mask[:, lo:hi]) / B  # global batch in the normalisation
-    loss.backward()
     params = [p for n, p in dec.named_parameters() if "ml_net" in n or "output_function" in n]
-    total = hd.allreduce_grads(params, extra=loss.detach().reshape(1))
+    fg = hd.FlatGrads(params, extra=1) if flat else None  # gradients as views of one flat buffer (bench.py's path)
+    for _ in range(2 if flat else 1):  # the flat buffer is zeroed, not re-created, between steps
+        if flat:
+            fg.zero_()
+        xh, _ = dec(y0[lo:hi], a[:, lo:hi])
+        loss = torch.sum((x[:, lo:hi] - xh) ** 2 * mask[:, lo:hi]) / B  # global batch in the normalisation
+        loss.backward()
+    if flat:
+        assert all(p.grad.data_ptr() >= fg.flat.data_ptr() and p.grad._base is fg.flat for p in params)  # still views
+        fg.extra.copy_(loss.detach().reshape(1))
+        total = fg.allreduce()
+    else:
+        total = hd.allreduce_grads(params, extra=loss.detach().reshape(1))
     if rank == 0:
         q.put((total.item(), [p.grad.clone() for p in params]))
     dist.destroy_process_group()
 
 
-def test_two_rank_allreduce_equals_single_process():
+@pytest.mark.parametrize("flat", [False, True])
+def test_two_rank_allreduce_equals_single_process(flat):
     D, obs, B = 6, 20, 12
     torch.manual_seed(0)
     dec = OF.OracleDecoder(obs, D, method="rk4", options={"step_size": 0.25})
@@ -62,7 +73,7 @@ def test_two_rank_allreduce_equals_single_process():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, flat)) for r in range(2)]
     for p in procs:
         p.start()
     total, grads = q.get(timeout=120)
