@@ -7,7 +7,8 @@ Workload (BASELINE.json configs[1] shape, metric "patient-trajectory solver step
   2**20 synthetic patients per GPU, dim-8 hybrid RocheODE (generate_data_dim8.py shape: D=8, obs=40, T=15), fixed-step
   RK4 (torchdiffeq 'rk4' = 3/8 rule) with step 1/16 over the full 14-day horizon = 224 solver steps per patient.
   One "step" of the bench = one pass of the hot path over the cohort:
-      set_action -> forward solve (with tape) -> fused read-out + masked SSE -> reverse sweep (dL/dy0, dL/dtheta)
+      set_action -> forward solve with tape, read-out + masked SSE consumed at the output times (one launch)
+                 -> reverse sweep (dL/dy0, dL/dtheta)
       [-> one NCCL all-reduce of the packed parameter gradients when N > 1]
   1 trajectory-step = one RK step of one patient (forward and backward of that step counted once).
   `fwd_only` reports the forward-only sweep of the same cohort (the configs[1] wording) next to the headline.
@@ -350,8 +351,7 @@ def run_ours(args):
         def cohort_grad(lo, hi):
             fg.zero_()
             z = y0c[lo:hi].detach().requires_grad_(True)
-            h = dec.solve(z, ac[:, lo:hi])
-            loss = H.masked_sse(dec, h, xc[:, lo:hi], mc[:, lo:hi], n_norm=Bc)
+            loss = dec.loss(z, ac[:, lo:hi].contiguous(), xc[:, lo:hi].contiguous(), mc[:, lo:hi].contiguous(), n_norm=Bc)
             loss.backward()
             fg.extra.copy_(loss.detach().reshape(1))
 
@@ -380,8 +380,7 @@ def run_ours(args):
     def device_step():
         fg.zero_()
         z = y0.detach().requires_grad_(True)
-        h = dec.solve(z, a)
-        loss = H.masked_sse(dec, h, x, mask, n_norm=B_global)
+        loss = dec.loss(z, a, x, mask, n_norm=B_global)  # solve + read-out + masked SSE: one forward launch
         loss.backward()
         fg.extra.copy_(loss.detach().reshape(1))
         return fg.allreduce()
@@ -405,8 +404,7 @@ def run_ours(args):
                 t.record_stream(main)
             keep.append(dev_c)
             z = dev_c[0].requires_grad_(True)
-            h = dec.solve(z, dev_c[1])
-            loss = H.masked_sse(dec, h, dev_c[2], dev_c[3], n_norm=B_global)
+            loss = dec.loss(z, dev_c[1], dev_c[2], dev_c[3], n_norm=B_global)
             loss.backward()
             fg.extra.add_(loss.detach().reshape(1))
         fg.allreduce()
@@ -543,6 +541,9 @@ def run_ours(args):
         t_fwd, (h, tape) = ev_time(lambda: ops.fixed_fwd(lib, pb, y0, grid, tt, True))
         t_dec, (loss, gh, gw, gb) = ev_time(lambda: ops.decode_sse(lib, h, lin.weight.detach(), lin.bias.detach(), x, mask, B))
         t_bwd, _ = ev_time(lambda: ops.fixed_bwd(lib, pb, grid, tt, gh, tape))
+        # the training step's forward launch: solve + read-out + masked SSE consumed at the output times (no h, no decode pass)
+        t_fused, _ = ev_time(lambda: ops.fixed_fwd_sse(lib, pb, y0, grid, tt, lin.weight.detach(), lin.bias.detach(), x, mask, B,
+                                                       want_tape=True))
         # tape-free alternative: forward without a tape + the continuous adjoint (odeint_adjoint)
         adj_grid, adj_count = solver.adjoint_grid_points(tt.cpu(), STEP)
         adj_grid, adj_count = adj_grid.to(dev), adj_count.to(dev)
@@ -569,13 +570,20 @@ def run_ours(args):
         }
         dec_bytes = T * B * (2 * OBS + 2 * D) * 4
         extra = {
-            "kernels_ms": {"fixed_fwd(+tape)": t_fwd, "decode_sse": t_dec, "fixed_bwd": t_bwd,
+            "kernels_ms": {"fixed_fwd_sse(+tape) [in the step]": t_fused, "fixed_bwd [in the step]": t_bwd,
+                           "fixed_fwd(+tape) [two-launch path]": t_fwd, "decode_sse [two-launch path]": t_dec,
                            "fixed_fwd(no tape)": t_fwd_nt, "fixed_adjoint(no tape)": t_adj},
             "adjoint_path": {"note": "odeint_adjoint: forward without a tape + continuous adjoint sweep (4 evals + 4 VJPs "
                                      "per step, same flop count as the reverse sweep); saves the {:.2f} GB tape".format(
                                          B * N_STEPS * D * 4 / 1e9),
                              "value": B * N_STEPS / ((t_fwd_nt + t_dec + t_adj) * 1e-3), "unit": "trajectory-steps/s",
                              "roofline_frac": bwd_flops / (t_adj * 1e-3) / 1e12 / fma_peak},
+            "roofline_fwd_fused": {"bound": "fp32_fma", "kernel": "fixed_fwd_sse_kernel<Roche<8>, RK4_38>",
+                                   "achieved": (fwd_flops + B * T * (6 * OBS * D + 5 * OBS)) / (t_fused * 1e-3) / 1e12, "peak": fma_peak,
+                                   "unit": "TFLOP/s", "frac": (fwd_flops + B * T * (6 * OBS * D + 5 * OBS)) / (t_fused * 1e-3) / 1e12 / fma_peak,
+                                   "launch_ms": t_fused, "hbm_gbs": (dec_bytes - B * T * D * 4 + B * N_STEPS * D * 4) / (t_fused * 1e-3) / 1e9,
+                                   "note": "flops = 560 per trajectory-step + (6 obs D + 5 obs) per (output time, trajectory) for "
+                                           "read-out, grad_h and grad_W; streams x + mask in, tape + grad_h out"},
             "roofline_fwd": {"bound": "fp32_fma", "achieved": fwd_flops / (t_fwd * 1e-3) / 1e12, "peak": fma_peak,
                              "unit": "TFLOP/s", "frac": fwd_flops / (t_fwd * 1e-3) / 1e12 / fma_peak,
                              "algorithmic_flops_per_traj_step": FLOPS_FWD_STEP},
@@ -615,8 +623,8 @@ def run_ours(args):
         "clocks": sampler.summary() if sampler else None,
         "e2e": e2e,
         "gpu_launches": 6 * args.steps,
-        "gpu_launches_per_step": {"dose_schedule_kernel": 1, "prep_params_kernel": 2, "fixed_fwd_kernel": 1,
-                                  "decode_sse_fast_kernel": 1, "fixed_bwd_kernel": 1},
+        "gpu_launches_per_step": {"dose_schedule_kernel": 1, "prep_params_kernel": 2, "prep_readout_kernel": 1,
+                                  "fixed_fwd_sse_kernel": 1, "fixed_bwd_kernel": 1},
         "roofline": roof,
         "cpu_baseline": cpu_baseline,
         "fwd_only": {"value": rate(ms_f), "unit": UNIT, "ms_per_step": ms_f / args.steps},

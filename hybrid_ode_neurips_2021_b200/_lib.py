@@ -58,6 +58,9 @@ SIGNATURES = {
     "hode_dose_schedule": (_I32, [_P, _I64, _I64, _I32, _I64, _P, _P, _P, _P]),
     "hode_fixed_tape_bytes": (C.c_size_t, [_CFG, _I64, _I32]),
     "hode_fixed_fwd": (_I32, [_CFG, _I64, _I64, _P, _P, _P, _I64, _P, _P, _P, _I32, _P, _I32, _P, _P, _P]),
+    "hode_fixed_fwd_sse_supported": (_I32, [_CFG, _I32, _I32]),
+    "hode_fixed_fwd_sse": (_I32, [_CFG, _I64, _P, _P, _P, _I64, _P, _P, _I32, _P, _I32, _P, _P, _I32, _P, _P, _F64, _P, _P, _P,
+                                  _P, _P, _P, _P]),
     "hode_fixed_bwd": (_I32, [_CFG, _I64, _I64, _P, _P, _I64, _P, _P, _I32, _P, _I32, _P, _I32, _P, _P, _P, _P, _P]),
     "hode_fixed_adjoint": (_I32, [_CFG, _I64, _I64, _P, _P, _I64, _P, _P, _I32, _P, _I32, _P, _I32, _P, _P, _P, _P, _P]),
     "hode_dopri5_max_batch": (_I64, [_CFG]),

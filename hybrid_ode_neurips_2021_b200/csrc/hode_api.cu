@@ -2,12 +2,14 @@
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdint.h>
 
 #include "hode_bodies.cuh"
 #include "hode_real_args.cuh"
 
 namespace hode {
 template <class F> int launch_fixed_fwd(const hode_cfg&, const SolveArgs&, cudaStream_t);
+template <class F> int launch_fixed_fwd_sse(const hode_cfg&, const SolveArgs&, cudaStream_t);
 template <class F> int launch_fixed_bwd(const hode_cfg&, const SolveArgs&, cudaStream_t);
 template <class F> int launch_fixed_adj(const hode_cfg&, const SolveArgs&, cudaStream_t);
 template <class F> int launch_dopri5_fwd(const hode_cfg&, const SolveArgs&, cudaStream_t);
@@ -33,7 +35,7 @@ static int fail(int code, const char* fmt, const char* a = "", long long b = 0) 
     return code;
 }
 
-enum Op { OP_FIXED_FWD, OP_FIXED_BWD, OP_DOPRI5_FWD, OP_DOPRI5_BWD, OP_FIXED_ADJ };
+enum Op { OP_FIXED_FWD, OP_FIXED_BWD, OP_DOPRI5_FWD, OP_DOPRI5_BWD, OP_FIXED_ADJ, OP_FIXED_FWD_SSE };
 
 template <class F>
 static int run(Op op, const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) {
@@ -43,6 +45,7 @@ static int run(Op op, const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) 
         case OP_DOPRI5_FWD: return launch_dopri5_fwd<F>(cfg, a, st);
         case OP_DOPRI5_BWD: return launch_dopri5_bwd<F>(cfg, a, st);
         case OP_FIXED_ADJ: return launch_fixed_adj<F>(cfg, a, st);
+        case OP_FIXED_FWD_SSE: return launch_fixed_fwd_sse<F>(cfg, a, st);
     }
     return -1;
 }
@@ -80,6 +83,9 @@ static int dispatch(Op op, const hode_cfg& cfg, const SolveArgs& a, cudaStream_t
     }
     if (rc == 0) return HODE_OK;
     if (rc == -2) return fail(HODE_ERR_UNSUPPORTED, "batch-coupled dopri5 group larger than %s%lld trajectories", "", hode_dopri5_max_batch(&cfg));
+    if (rc == -1 && op == OP_FIXED_FWD_SSE)
+        return fail(HODE_ERR_UNSUPPORTED, "no fused solve + read-out kernel for this field / method / obs / n_dose / parameter-set "
+                                          "combination (use hode_fixed_fwd + hode_decode_sse)%s%lld", "", 0);
     if (rc == -1) return fail(HODE_ERR_UNSUPPORTED, "method %s%lld is not valid for this entry point", "", cfg.method);
     if (rc == (int)cudaErrorNoKernelImageForDevice || rc == (int)cudaErrorNoDevice || rc == (int)cudaErrorInsufficientDriver)
         return fail(HODE_ERR_NO_DEVICE, "%s (libhode_b200 holds sm_100a code only)", cudaGetErrorString((cudaError_t)rc));
@@ -166,6 +172,43 @@ int32_t hode_fixed_fwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, con
     fill_common(a, cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, param_set_of_group);
     a.y0 = y0; a.grid = grid; a.n_grid = n_grid; a.t_eval_f = t_eval; a.n_t = n_t; a.h_out = h_out; a.tape_y = tape;
     return dispatch(OP_FIXED_FWD, *cfg, a, (cudaStream_t)stream);
+}
+
+int32_t hode_fixed_fwd_sse_supported(const hode_cfg* cfg, int32_t obs, int32_t n_param_sets) {
+    if (!cfg || cfg->field != HODE_FIELD_ROCHE || cfg->method == HODE_DOPRI5) return 0;
+    if (!(cfg->flags & HODE_FLAG_HILL2) || (cfg->flags & HODE_FLAG_ABLATE)) return 0;
+    const int d = cfg->latent_dim;
+    if (d != 4 && d != 6 && d != 8) return 0;
+    if (cfg->n_dose != 1 || n_param_sets != 1) return 0;
+    return (obs == 20 || obs == 24 || obs == 40 || obs == 80) ? 1 : 0;  // the reference's observation widths
+}
+
+int32_t hode_fixed_fwd_sse(const hode_cfg* cfg, int64_t n_traj, const float* y0, const float* dose_amt, const float* dose_t,
+                           int64_t dose_t_stride, const float* params, const float* grid, int32_t n_grid,
+                           const float* t_eval, int32_t n_t, const float* W, const float* b, int32_t obs, const float* x,
+                           const float* mask, double n_norm, float* h_out, float* tape, float* loss, float* grad_h,
+                           float* grad_w, float* grad_b, void* stream) {
+    int rc = check_common(cfg, 1, n_traj, dose_amt, dose_t, dose_t_stride, params, n_t);
+    if (rc) return rc;
+    if (!hode_fixed_fwd_sse_supported(cfg, obs, 1))
+        return fail(HODE_ERR_UNSUPPORTED, "no fused solve + read-out kernel for this configuration (use hode_fixed_fwd + hode_decode_sse)");
+    if (n_grid < 1 || !grid || !t_eval || !W || !b || !loss) return fail(HODE_ERR_ARG, "bad grid / t_eval / W / b / loss");
+    if (((uintptr_t)x | (uintptr_t)mask) & 15) return fail(HODE_ERR_ARG, "x / mask must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(loss, 0, sizeof(float), st);
+    if (e == cudaSuccess && grad_w) e = cudaMemsetAsync(grad_w, 0, sizeof(float) * (size_t)obs * cfg->latent_dim, st);
+    if (e == cudaSuccess && grad_b) e = cudaMemsetAsync(grad_b, 0, sizeof(float) * (size_t)obs, st);
+    if (e != cudaSuccess) return fail(HODE_ERR_CUDA, "CUDA error: %s (%lld)", cudaGetErrorString(e), (long long)e);
+    if (n_traj == 0) return HODE_OK;
+    if (!y0 || !x || !mask) return fail(HODE_ERR_ARG, "NULL y0 / x / mask");
+    if (grad_b && !grad_w) return fail(HODE_ERR_ARG, "grad_b without grad_w");
+    SolveArgs a;
+    fill_common(a, cfg, 1, n_traj, dose_amt, dose_t, dose_t_stride, params, nullptr);
+    a.y0 = y0; a.grid = grid; a.n_grid = n_grid; a.t_eval_f = t_eval; a.n_t = n_t; a.h_out = h_out; a.tape_y = tape;
+    a.sse_x = x; a.sse_mask = mask; a.sse_w = W; a.sse_b = b; a.sse_obs = obs;
+    a.sse_scale = (float)(-2.0 / n_norm); a.sse_inv_norm = (float)(1.0 / n_norm);
+    a.sse_loss = loss; a.sse_grad_h = grad_h; a.sse_grad_w = grad_w; a.sse_grad_b = grad_b;
+    return dispatch(OP_FIXED_FWD_SSE, *cfg, a, st);
 }
 
 int32_t hode_fixed_bwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,

@@ -40,6 +40,17 @@ struct SolveArgs {
     const float* grad_h;
     float* grad_y0;
     float* grad_params;
+    // fused read-out + masked SSE (hode_fixed_fwd_sse): x / mask [n_t, n_traj, obs] contiguous float32, W [obs, D], b [obs]
+    const float* sse_x;
+    const float* sse_mask;
+    const float* sse_w;
+    const float* sse_b;
+    int32_t sse_obs;
+    float sse_scale, sse_inv_norm;  // -2 / n_norm, 1 / n_norm
+    float* sse_loss;
+    float* sse_grad_h;
+    float* sse_grad_w;
+    float* sse_grad_b;
     // continuous adjoint: `grid` holds the n_t - 1 reversed-time interval grids back to back (n_grid points in total),
     // adj_cnt[iv] = number of grid points of interval iv (iv = 0 is the LAST output interval)
     const int32_t* adj_cnt;
@@ -99,60 +110,84 @@ HODE_HD void store_vec(float* __restrict__ p, const float (&v)[D]) {
 // ==============================================================================================================
 // fixed grid (tde solvers.py FixedGridODESolver.integrate)
 // ==============================================================================================================
-template <class F, int METHOD, class PS, class Dose>
-HODE_HD void fixed_fwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t idx) {
+// Where the solution at an output time goes.  HSink: into h_out [n_t, n_traj, D] (what torchdiffeq.odeint returns).  The
+// training kernels use a sink that consumes h(t_j) on the spot -- read-out, masked squared error and its gradients
+// (SseSink, hode_sse.cuh) -- so that the latent solution is not written and re-read at all.
+template <int D>
+struct HSink {
+    float* h_out;
+    int64_t n_traj, idx;
+    HODE_HD void emit(int j, const float (&v)[D]) { store_vec<D>(h_out + ((int64_t)j * n_traj + idx) * D, v); }
+};
+
+template <class F, int METHOD, class PS, class Dose, class Sink>
+HODE_HD void fixed_fwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t idx, Sink& sink, bool write_tape = true) {
     constexpr int D = F::D;
     const int64_t n_traj = a.n_groups * a.batch;
     float y[D], y1[D];
     load_vec<D>(a.y0 + idx * D, y);
-    store_vec<D>(a.h_out + idx * D, y);  // solution[0] = y0
-    if (!F::params_ok(sp)) {  // kernel variant and parameters disagree (hode_cfg.flags): fail loudly
 #pragma unroll
-        for (int d = 0; d < D; ++d) y[d] = nanf("");
-    }
-    int j = 1;
+    for (int d = 0; d < D; ++d) y1[d] = y[d];
     const bool perturb = a.perturb != 0;
     // loop-carried scalars instead of per-step index arithmetic: grid time, tape cursor, next output time
-    float t0 = a.grid[0];
-    float* tp = a.tape_y != nullptr ? a.tape_y + idx * D : nullptr;
+    float t0 = a.grid[0], t1 = t0;
+    float* tp = (a.tape_y != nullptr && write_tape) ? a.tape_y + idx * D : nullptr;
     const int64_t tape_stride = n_traj * D;
-    float tj = (j < a.n_t) ? a.t_eval_f[j] : INFINITY;
-    // one grid step ya -> yb, with the outputs it emits
-    auto one_step = [&](int s, float (&ya)[D], float (&yb)[D]) {
-        const float t1 = a.grid[s + 1];
-        const float dt = sub_rn(t1, t0);
-        if (tp != nullptr) {
-            store_vec<D>(tp, ya);
-            tp += tape_stride;
-        }
-        fixed_step<F, METHOD>(sp, ds, t0, t1, dt, perturb, ya, yb);
-        if (t1 >= tj) {  // rare: an output time is reached (false for NaN times, like the reference's `while`)
+    int j = 0, s = 0;
+    float tj = a.t_eval_f[0];  // == grid[0]: solution[0] = y0 is emitted by the first trip below
+    // The grid is walked in two nested loops.  The inner one takes steps until an output time is reached and contains nothing
+    // but the step; the outer one holds the ONE place where outputs are emitted (y at t0, y1 at t1, or the linear
+    // interpolant).  A sink that does real work (SseSink) therefore appears once in the code and outside the hot loop.
+    for (;;) {
+        if (t1 >= tj) {  // false for NaN times, like the reference's `while`
             while (j < a.n_t && t1 >= a.t_eval_f[j]) {
                 const float te = a.t_eval_f[j];
-                float* o = a.h_out + ((int64_t)j * n_traj + idx) * D;
+                float v[D];
                 if (te == t0) {
-                    store_vec<D>(o, ya);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) v[d] = y[d];
                 } else if (te == t1) {
-                    store_vec<D>(o, yb);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) v[d] = y1[d];
                 } else {  // _linear_interp
                     const float slope = div_rn(sub_rn(te, t0), sub_rn(t1, t0));
-                    float v[D];
 #pragma unroll
-                    for (int d = 0; d < D; ++d) v[d] = ya[d] + slope * (yb[d] - ya[d]);
-                    store_vec<D>(o, v);
+                    for (int d = 0; d < D; ++d) v[d] = y[d] + slope * (y1[d] - y[d]);
                 }
+                sink.emit(j, v);
                 ++j;
             }
             tj = (j < a.n_t) ? a.t_eval_f[j] : INFINITY;
+            if (s == 0 && !F::params_ok(sp)) {  // kernel variant and parameters disagree (hode_cfg.flags): fail loudly
+#pragma unroll
+                for (int d = 0; d < D; ++d) y1[d] = nanf("");
+            }
         }
-        t0 = t1;
-    };
-    // (a two-steps-per-trip variant with y / y1 swapping roles was measured: no difference)
-    for (int s = 0; s + 1 < a.n_grid; ++s) {
-        one_step(s, y, y1);
 #pragma unroll
         for (int d = 0; d < D; ++d) y[d] = y1[d];
+        t0 = t1;
+        if (s + 1 >= a.n_grid) break;
+        for (;;) {
+            t1 = a.grid[s + 1];
+            const float dt = sub_rn(t1, t0);
+            if (tp != nullptr) {
+                store_vec<D>(tp, y);
+                tp += tape_stride;
+            }
+            fixed_step<F, METHOD>(sp, ds, t0, t1, dt, perturb, y, y1);
+            ++s;
+            if (t1 >= tj || s + 1 >= a.n_grid) break;
+#pragma unroll
+            for (int d = 0; d < D; ++d) y[d] = y1[d];
+            t0 = t1;
+        }
     }
+}
+// default sink: the latent solution
+template <class F, int METHOD, class PS, class Dose>
+HODE_HD void fixed_fwd_traj(const SolveArgs& a, PS sp, const Dose& ds, int64_t idx) {
+    HSink<F::D> sink{a.h_out, a.n_groups * a.batch, idx};
+    fixed_fwd_traj<F, METHOD>(a, sp, ds, idx, sink);
 }
 
 template <class F, int METHOD, bool EG, class PS, class Dose, class ACC>

@@ -11,6 +11,7 @@
 #include <mutex>
 
 #include "hode_bodies.cuh"
+#include "hode_sse.cuh"
 
 #ifndef HODE_FWD_MINBLOCKS
 #define HODE_FWD_MINBLOCKS 1
@@ -24,11 +25,16 @@
 #ifndef HODE_D5_FWD_MINBLOCKS_REG
 #define HODE_D5_FWD_MINBLOCKS_REG 4
 #endif
+#ifndef HODE_SSE_MINBLOCKS
+#define HODE_SSE_MINBLOCKS 4
+#endif
 #ifndef HODE_DOPRI5_MAX_THREADS
 #define HODE_DOPRI5_MAX_THREADS 512
 #endif
 
 namespace hode {
+
+__host__ __device__ constexpr int round4(int n) { return (n + 3) / 4 * 4; }
 
 // ---- group operations of the dopri5 controller: a sum over the controller group (batch-coupled: the CTA or a lane
 //      segment; per-trajectory: nothing) that is bit-identical in every thread of the group, and any() -------------------
@@ -292,6 +298,45 @@ __global__ void __launch_bounds__(128, HODE_FWD_MINBLOCKS) fixed_fwd_kernel(cons
     else { HODE_WITH_DOSE(ND, a, idx, (fixed_fwd_traj<F, METHOD>(a, (const float*)smem, ds, idx))); }
 }
 
+// Forward fixed-grid solve with the read-out + masked SSE consumed at every output time (SseSink, hode_sse.cuh): one launch
+// produces loss, grad_h, grad_W, grad_b and the tape; the latent solution is only written if the caller asks for it.
+// One parameter set (constant bank), 128-thread CTAs, every lane of every warp runs (padding lanes on a clamped trajectory
+// with an empty tile row): the sink is a warp-wide cooperation.
+template <class F, int METHOD, int OBS>
+__global__ void __launch_bounds__(128, HODE_SSE_MINBLOCKS) fixed_fwd_sse_kernel(const SolveArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int D = F::D;
+    using Sink = SseSink<D, OBS>;
+    // shared memory: 4 warps x (x tile, mask tile) | sred [OBS * D + OBS] | accumulators [kAccFloats][128] | 4 mbarriers
+    constexpr int kSred = 4 * Sink::kTileFloats, kAcc = kSred + round4(OBS * D + OBS), kBar = kAcc + Sink::kAccFloats * 128;
+    const int warp = threadIdx.x >> 5;
+    float* sred = smem + kSred;
+    const int64_t n_traj = a.batch;  // flat launch: n_groups == 1
+    const int64_t first = ((int64_t)blockIdx.x * 4 + warp) * 32;
+    const int64_t mine = first + (threadIdx.x & 31);
+    const int64_t idx = mine < n_traj ? mine : n_traj - 1;
+    for (int i = threadIdx.x; i < OBS * D + OBS; i += blockDim.x) sred[i] = 0.0f;
+    Sink sink;
+    sink.init(a, warp * Sink::kTileFloats, kAcc, kBar + 2 * warp, first, n_traj);
+    {
+        const DoseReg<1> ds = load_dose_reg<1>(a, idx);
+        fixed_fwd_traj<F, METHOD>(a, ParamConst(), ds, idx, sink, /*write_tape=*/mine < n_traj);  // padding lanes write nothing
+    }
+    __syncthreads();  // sred zeroed by all, solves done
+    sink.flush(sred, a.sse_loss, a.sse_inv_norm);
+    __syncthreads();
+    if (a.sse_grad_w != nullptr) {
+        for (int i = threadIdx.x; i < OBS * D; i += blockDim.x) atomicAdd(&a.sse_grad_w[i], sred[i]);
+        if (a.sse_grad_b != nullptr)
+            for (int i = threadIdx.x; i < OBS; i += blockDim.x) atomicAdd(&a.sse_grad_b[i], sred[OBS * D + i]);
+    }
+}
+template <int D, int OBS>
+constexpr size_t sse_smem_bytes() {
+    using Sink = SseSink<D, OBS>;
+    return (4 * (size_t)Sink::kTileFloats + round4(OBS * D + OBS) + (size_t)Sink::kAccFloats * 128 + 8) * sizeof(float);
+}
+
 // Does the field accumulate its parameter gradients warp-cooperatively?  NeuralODE (846 - 3 132 parameters) always;
 // RocheODE at D = 12 (104 ml_net accumulators) in the dopri5 reverse sweep and the continuous adjoint, where the
 // per-thread accumulators spill (the fixed-grid reverse sweep keeps them: 3 recomputed stages fit next to them).
@@ -465,7 +510,6 @@ struct D5Store {
     __host__ __device__ static constexpr size_t fwd_floats(int threads) { return kSmem ? (size_t)kFwdRows * F::D * threads : 0; }
     __host__ __device__ static constexpr size_t bwd_floats(int threads) { return kSmem ? (size_t)kBwdRows * F::D * threads : 0; }
 };
-__host__ __device__ constexpr int round4(int n) { return (n + 3) / 4 * 4; }
 
 // runs `fn(rows)` with the storage D5Store selects; `base` = the CTA's row area in shared memory (16-byte aligned)
 // THREADS > 0: the CTA size is known at compile time (row strides become immediates)
@@ -589,6 +633,11 @@ __global__ void __launch_bounds__(128, D5Store<F>::kBwdMinBlocks) dopri5_bwd_ker
 // launchers (explicitly instantiated per field in inst_*.cu)
 // ---------------------------------------------------------------------------------------------------------------
 inline int round_up32(int64_t n) { return (int)(((n + 31) / 32) * 32); }
+template <class K>
+inline int set_smem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    return 0;
+}
 
 #define HODE_LAUNCH_CHECK()                                   \
     do {                                                      \
@@ -649,6 +698,57 @@ int launch_fixed_fwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st
 #undef HODE_FF
     HODE_LAUNCH_CHECK();
     return 0;
+}
+
+// -1: this (field, method, obs, n_dose, parameter-set) combination has no fused kernel (the caller falls back to the
+// separate solve + decode launches); otherwise a CUDA error code or 0.
+template <class F> struct SseOk { static constexpr bool value = false; };
+template <int D> struct SseOk<Roche<D, true, false>> { static constexpr bool value = (D == 4 || D == 6 || D == 8); };
+
+template <class F>
+int launch_fixed_fwd_sse(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st) {
+    if constexpr (!SseOk<F>::value) {
+        return -1;
+    } else {
+        constexpr int D = F::D;
+        const SolveArgs a = flatten(a_in);
+        const int obs = a.sse_obs;
+        if (a.pset != nullptr || a.n_groups != 1 || cfg.n_dose != 1 || !use_const_params<F>(a)) return -1;
+        if (obs != 20 && obs != 24 && obs != 40 && obs != 80) return -1;
+        if (cfg.method != HODE_EULER && cfg.method != HODE_MIDPOINT && cfg.method != HODE_RK4_38) return -1;
+        const int64_t nblk = (a.batch + 127) / 128;
+        ConstParamLease lease((F*)nullptr, a.params, st);
+        if (lease.rc != 0) return lease.rc;
+        prep_readout_kernel<<<1, 128, 0, st>>>(a.sse_w, a.sse_b, obs, D);
+        void* stage_ptr = nullptr;
+        cudaError_t e = cudaGetSymbolAddress(&stage_ptr, g_readout_stage);
+        if (e != cudaSuccess) return (int)e;
+        e = cudaMemcpyToSymbolAsync(c_readout, stage_ptr, sizeof(float) * (2 * obs * D + obs), 0, cudaMemcpyDeviceToDevice, st);
+        if (e != cudaSuccess) return (int)e;
+#define HODE_FS(M, OBS)                                                                        \
+    do {                                                                                       \
+        int e_ = set_smem(fixed_fwd_sse_kernel<F, M, OBS>, sse_smem_bytes<D, OBS>());          \
+        if (e_ != 0) return e_;                                                                \
+        fixed_fwd_sse_kernel<F, M, OBS><<<(unsigned)nblk, 128, sse_smem_bytes<D, OBS>(), st>>>(a); \
+    } while (0)
+#define HODE_FS_M(M)                                        \
+    do {                                                    \
+        if (obs == 20) HODE_FS(M, 20);                      \
+        else if (obs == 24) HODE_FS(M, 24);                 \
+        else if (obs == 40) HODE_FS(M, 40);                 \
+        else HODE_FS(M, 80);                                \
+    } while (0)
+        switch (cfg.method) {
+            case HODE_EULER: HODE_FS_M(M_EULER); break;
+            case HODE_MIDPOINT: HODE_FS_M(M_MIDPOINT); break;
+            default: HODE_FS_M(M_RK4_38); break;
+        }
+#undef HODE_FS_M
+#undef HODE_FS
+        lease.done();
+        HODE_LAUNCH_CHECK();
+        return 0;
+    }
 }
 
 template <class F>
@@ -718,12 +818,6 @@ int launch_fixed_adj(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st
 #undef HODE_FA_M
 #undef HODE_FA
     HODE_LAUNCH_CHECK();
-    return 0;
-}
-
-template <class K>
-inline int set_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024) return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     return 0;
 }
 

@@ -78,8 +78,13 @@ struct NeuralReal {
     HODE_HD static bool params_ok(PS) { return true; }
 
     HODE_HD static float dose(const DoseTab& ds, float t) {
-        const int n = (int)t;  // Python int(t): truncation
-        return (n >= ds.T || n < 0) ? 0.0f : ds.s[(int64_t)n * ds.stride];
+        int n = (int)t;  // Python int(t): truncation toward zero
+        if (n >= ds.T) return 0.0f;
+        // cumsum(action)[int(t)] (model.py:753-760): a negative index counts from the END in Python, so int(t) = -1 -- the
+        // first grid point of DecoderReal's default t = arange(t0 - 1, ...) when perturb is off -- reads the LAST row (the
+        // total dose); below -T the reference raises IndexError: NaN here
+        if (n < 0) n += ds.T;
+        return n < 0 ? nanf("") : ds.s[(int64_t)n * ds.stride];
     }
 
     struct Params {

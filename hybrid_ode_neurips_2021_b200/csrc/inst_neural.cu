@@ -7,6 +7,7 @@
 
 namespace hode {
 template int launch_fixed_fwd<Neural<HODE_INST_D>>(const hode_cfg&, const SolveArgs&, cudaStream_t);
+template int launch_fixed_fwd_sse<Neural<HODE_INST_D>>(const hode_cfg&, const SolveArgs&, cudaStream_t);
 template int launch_fixed_bwd<Neural<HODE_INST_D>>(const hode_cfg&, const SolveArgs&, cudaStream_t);
 template int launch_fixed_adj<Neural<HODE_INST_D>>(const hode_cfg&, const SolveArgs&, cudaStream_t);
 template int launch_dopri5_fwd<Neural<HODE_INST_D>>(const hode_cfg&, const SolveArgs&, cudaStream_t);

@@ -14,6 +14,7 @@ using InstField = Roche<HODE_INST_D, true, true>;
 using InstField = Roche<HODE_INST_D, (HODE_INST_HILL2 != 0)>;
 #endif
 template int launch_fixed_fwd<InstField>(const hode_cfg&, const SolveArgs&, cudaStream_t);
+template int launch_fixed_fwd_sse<InstField>(const hode_cfg&, const SolveArgs&, cudaStream_t);
 template int launch_fixed_bwd<InstField>(const hode_cfg&, const SolveArgs&, cudaStream_t);
 template int launch_fixed_adj<InstField>(const hode_cfg&, const SolveArgs&, cudaStream_t);
 template int launch_dopri5_fwd<InstField>(const hode_cfg&, const SolveArgs&, cudaStream_t);

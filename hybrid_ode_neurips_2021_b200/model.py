@@ -20,7 +20,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from . import ops
-from .solver import odeint, odeint_adjoint
+from .solver import odeint, odeint_adjoint, odeint_sse
 
 DTYPE = torch.float32
 
@@ -192,3 +192,16 @@ class RocheExpertDecoder(nn.Module):
     def forward(self, init, a):
         h = self.solve(init, a)
         return self.output_function(h), h
+
+    def loss(self, init, a, x, mask, n_norm=None):
+        """The likelihood of ``VariationalInference.loss`` (``model.py:1172-1179``): ``forward`` followed by
+        ``sum((x - x_hat)**2 * mask) / x.shape[1]``, as one fused launch where the kernel exists (:func:`solver.odeint_sse`);
+        ``x_hat`` and ``h`` are not materialised.  The continuous-adjoint decoder keeps its two-call path."""
+        if self.adjoint:
+            from .loss import masked_sse
+
+            return masked_sse(self, self.solve(init, a), x, mask, n_norm)
+        self.ode.set_action(a)
+        lin = self.output_function[0]
+        return odeint_sse(self.ode, init, self.t, lin.weight, lin.bias, x, mask, n_norm=n_norm, rtol=self.options["rtol"],
+                          atol=self.options["atol"], method=self.options["method"], options=self.solver_options)

@@ -100,6 +100,42 @@ def fixed_fwd(lib, pb: Problem, y0, grid, t_eval, want_tape):
     return h, tape
 
 
+def fixed_fwd_sse_supported(lib, pb: Problem, obs, x=None, mask=None) -> bool:
+    """Is there a fused solve + read-out + masked-SSE kernel for this problem (and are x / mask laid out for it)?"""
+    if pb.pset is not None or pb.params.shape[0] != 1:
+        return False
+    if not lib.hode_fixed_fwd_sse_supported(C.byref(pb.cfg), int(obs), int(pb.params.shape[0])):
+        return False
+    for t in (x, mask):
+        if t is not None and not (t.dtype == torch.float32 and t.is_contiguous() and t.data_ptr() % 16 == 0):
+            return False
+    return True
+
+
+def fixed_fwd_sse(lib, pb: Problem, y0, grid, t_eval, W, b, x, mask, n_norm, want_tape, want_h=False, want_param_grads=True):
+    """``hode_fixed_fwd_sse``: forward solve with read-out + masked SSE consumed at every output time.
+    Returns ``loss [1], grad_h [n_t, n_traj, D], grad_W, grad_b, h or None, tape or None``."""
+    D = pb.cfg.latent_dim
+    y0, W, b = _f32c(y0), _f32c(W), _f32c(b)
+    n_traj = pb.n_traj
+    n_t, n_grid, obs = t_eval.numel(), grid.numel(), W.shape[0]
+    assert x.shape == (n_t, n_traj, obs) and mask.shape == x.shape and x.is_contiguous() and mask.is_contiguous()
+    dev = y0.device
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    gh = torch.empty(n_t, n_traj, D, dtype=torch.float32, device=dev)
+    gw = torch.empty(obs, D, dtype=torch.float32, device=dev) if want_param_grads else None
+    gb = torch.empty(obs, dtype=torch.float32, device=dev) if want_param_grads else None
+    h = torch.empty(n_t, n_traj, D, dtype=torch.float32, device=dev) if want_h else None
+    tape = torch.empty(max(n_grid - 1, 0), n_traj, D, dtype=torch.float32, device=dev) if want_tape else None
+    with _on(y0):
+        rc = lib.hode_fixed_fwd_sse(C.byref(pb.cfg), n_traj, _ptr(y0), _ptr(pb.dose_amt), _ptr(pb.dose_t), pb.dose_t.stride(0),
+                                    _ptr(pb.params), _ptr(grid), n_grid, _ptr(t_eval), n_t, _ptr(W), _ptr(b), obs, _ptr(x),
+                                    _ptr(mask), float(n_norm), _ptr(h), _ptr(tape), _ptr(loss), _ptr(gh), _ptr(gw), _ptr(gb),
+                                    _stream(y0))
+    lib.check(rc, "hode_fixed_fwd_sse")
+    return loss, gh, gw, gb, h, tape
+
+
 def fixed_bwd(lib, pb: Problem, grid, t_eval, grad_h, tape):
     D = pb.cfg.latent_dim
     grad_h = _f32c(grad_h)

@@ -26,7 +26,7 @@ import torch
 from . import _lib as L
 from . import ops
 
-__all__ = ["odeint", "odeint_adjoint", "odeint_ensemble", "SolveInfo", "last_solve_info", "fixed_grid_points"]
+__all__ = ["odeint", "odeint_adjoint", "odeint_ensemble", "odeint_sse", "SolveInfo", "last_solve_info", "fixed_grid_points"]
 
 EXPERT_NAMES = (
     "HillCure", "HillPatho", "ec50_patho", "emax_patho", "k_dexa", "k_discure_immunereact", "k_discure_immunity",
@@ -225,6 +225,31 @@ class _FixedSolve(torch.autograd.Function):
         return gy0, gp.reshape(-1), None, None, None, None
 
 
+class _FixedSolveSSE(torch.autograd.Function):
+    """Forward solve with the read-out and the masked SSE consumed at every output time (``hode_fixed_fwd_sse``): returns
+    the scalar loss; ``d loss / d h`` is produced in the same launch and fed to the reverse sweep in ``backward``."""
+
+    @staticmethod
+    def forward(ctx, y0, packed, W, b, pb, grid, t_eval, x, mask, n_norm, need_grad):
+        lib = L.get_lib()
+        pb.params = packed.detach().reshape(pb.params_shape).contiguous()
+        loss, gh, gw, gb, _, tape = ops.fixed_fwd_sse(lib, pb, y0.detach(), grid, t_eval, W.detach(), b.detach(), x, mask, n_norm,
+                                                      want_tape=need_grad, want_param_grads=need_grad)
+        ctx.pb, ctx.grid, ctx.t_eval, ctx.tape = pb, grid, t_eval, tape
+        if need_grad:
+            ctx.save_for_backward(gh, gw, gb)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.tape is None:
+            raise RuntimeError("backward through a solve that was run without a tape")
+        gh, gw, gb = ctx.saved_tensors
+        gy0, gp = ops.fixed_bwd(L.get_lib(), ctx.pb, ctx.grid, ctx.t_eval, gh, ctx.tape)
+        # the loss is a scalar: its upstream gradient scales the (small) results instead of the [n_t, n_traj, D] grad_h
+        return g * gy0, g * gp.reshape(-1), g * gw, g * gb, None, None, None, None, None, None, None
+
+
 class _FixedAdjointSolve(torch.autograd.Function):
     """torchdiffeq's ``OdeintAdjointMethod`` for the fixed-grid methods: forward without a tape, backward = ONE launch
     integrating the augmented system backwards over every output interval (``hode_fixed_adjoint``)."""
@@ -361,6 +386,42 @@ def odeint_ensemble(funcs, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=
     return _odeint_impl(funcs, y0, t, rtol, atol, method, options, None)
 
 
+def odeint_sse(func, y0, t, weight, bias, x, mask, *, n_norm=None, rtol=1e-7, atol=1e-9, method=None, options=None):
+    """The likelihood term of ``VariationalInference.loss`` in one call: ``h = odeint(func, y0, t, ...)`` (``model.py:1116``),
+    ``x_hat = h @ weight.T + bias`` (``model.py:1120``) and ``sum((x - x_hat)**2 * mask) / n_norm`` (``model.py:1179``,
+    ``n_norm = x.shape[1]`` by default), returned as a scalar that back-propagates to ``y0``, the vector-field parameters,
+    ``weight`` and ``bias``.
+
+    For the fixed-grid methods on the RocheODE field this is ONE forward launch (the read-out and the loss are evaluated
+    while ``h(t_j)`` is in registers; ``h`` and ``x_hat`` never exist in memory) plus the reverse sweep in ``backward``.  Where
+    the fused kernel does not apply (dopri5, NeuralODE, several parameter sets, ``obs % 4 != 0``, strided data) the same
+    result comes from ``odeint`` + the fused read-out / SSE kernel (``loss.decode_sse_loss``) -- also CUDA, two launches more."""
+    global _last_info
+    from .loss import decode_sse_loss
+    from .real import real_field_kind
+
+    n_norm = float(x.shape[1] if n_norm is None else n_norm)
+    fusable = real_field_kind(func) is None and (method is not None and method != "dopri5")
+    if fusable:
+        su = _setup([func], y0, t, rtol, atol, method, options, None)
+        opts = su["options"]
+        xm = x if x.dtype == torch.float32 else x.float()
+        mm = mask if mask.dtype == torch.float32 else mask.float()
+        if xm.stride() != mm.stride() or not xm.is_contiguous():
+            xm, mm = xm.contiguous(), mm.contiguous()
+        pb = su["pb"]
+        pb.params = su["packed"].detach().reshape(pb.params_shape)
+        if (opts.get("grid_constructor") is None and opts.get("interp", "linear") == "linear"
+                and ops.fixed_fwd_sse_supported(L.get_lib(), pb, weight.shape[0], xm, mm)):
+            t_dev, grid = _times_for(t, opts.get("step_size"), y0.device, True)
+            loss = _FixedSolveSSE.apply(y0, su["packed"], weight, bias, pb, grid, t_dev, xm, mm, n_norm, su["need_grad"] or
+                                        (torch.is_grad_enabled() and (weight.requires_grad or bias.requires_grad)))
+            _last_info = SolveInfo(None, (grid.numel() - 1) * su["B"])
+            return loss
+    h = odeint(func, y0, t, rtol=rtol, atol=atol, method=method, options=options)
+    return decode_sse_loss(h, weight, bias, x, mask, n_norm)
+
+
 def _odeint_real(func, kind, y0, t, method, options):
     """Real-data fields (model.py:570-769): fixed-grid solvers only, one parameter set, dose tables built per launch."""
     global _last_info
@@ -389,21 +450,12 @@ def _odeint_real(func, kind, y0, t, method, options):
     return h
 
 
-def _odeint_impl(funcs, y0, t, rtol, atol, method, options, event_fn, adjoint=None):
-    global _last_info
+def _setup(funcs, y0, t, rtol, atol, method, options, event_fn):
+    """Argument checking shared by every entry point for the simulation fields; returns the launch description."""
     func = funcs[0]
     M = len(funcs)
     if event_fn is not None:
         raise NotImplementedError("event_fn is not used by the reference and has no fused kernel")
-    from .real import real_field_kind
-
-    rk = real_field_kind(func)
-    if rk is not None:
-        if M != 1:
-            raise NotImplementedError("odeint_ensemble is built for the simulation fields only")
-        if adjoint is not None:
-            raise NotImplementedError("odeint_adjoint is built for the simulation fields (RocheODE / NeuralODE) only")
-        return _odeint_real(func, rk, y0, t, method, options)
     kind = field_kind(func)
     for f in funcs[1:]:
         if field_kind(f) != kind or int(f.latent_dim) != int(func.latent_dim):
@@ -480,6 +532,29 @@ def _odeint_impl(funcs, y0, t, rtol, atol, method, options, event_fn, adjoint=No
         pset = torch.arange(M, dtype=torch.int32, device=y0.device).repeat_interleave(groups_per_member).contiguous()
     pb = ops.Problem(cfg, n_groups, batch, dose_amt, dose_t, None, pset)
     pb.params_shape = (M, packed.numel() // M)
+    return dict(pb=pb, cfg=cfg, packed=packed, pset=pset, method=method, options=options, fixed=fixed, need_grad=need_grad,
+                ctrl_name=ctrl_name, B=B, D=D, batch=batch, n_groups=n_groups, dose_amt=dose_amt, dose_t=dose_t)
+
+
+def _odeint_impl(funcs, y0, t, rtol, atol, method, options, event_fn, adjoint=None):
+    global _last_info
+    func = funcs[0]
+    M = len(funcs)
+    from .real import real_field_kind
+
+    rk = real_field_kind(func)
+    if rk is not None:
+        if event_fn is not None:
+            raise NotImplementedError("event_fn is not used by the reference and has no fused kernel")
+        if M != 1:
+            raise NotImplementedError("odeint_ensemble is built for the simulation fields only")
+        if adjoint is not None:
+            raise NotImplementedError("odeint_adjoint is built for the simulation fields (RocheODE / NeuralODE) only")
+        return _odeint_real(func, rk, y0, t, method, options)
+    su = _setup(funcs, y0, t, rtol, atol, method, options, event_fn)
+    pb, cfg, packed, pset, method, options = su["pb"], su["cfg"], su["packed"], su["pset"], su["method"], su["options"]
+    fixed, need_grad, ctrl_name, B, batch, n_groups = su["fixed"], su["need_grad"], su["ctrl_name"], su["B"], su["batch"], su["n_groups"]
+    dose_amt, dose_t = su["dose_amt"], su["dose_t"]
 
     if fixed:
         if options.get("grid_constructor") is not None:

@@ -133,6 +133,22 @@ int32_t hode_fixed_fwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, con
                        const float* dose_t, int64_t dose_t_stride, const float* params,
                        const int32_t* param_set_of_group, const float* grid, int32_t n_grid, const float* t_eval,
                        int32_t n_t, float* h_out, float* tape, void* stream);
+/* Training forward pass in ONE launch: hode_fixed_fwd with the read-out and the likelihood consumed at every output time
+ * -- model.py:1116 (odeint), 1120 (output_function) and 1179 (masked SSE) fused.  While h(t_j) is still in registers the kernel
+ * forms x_hat = W h + b, the loss term and ALL gradients of the (scalar) loss that do not need the reverse sweep:
+ *   loss [1] = sum (x - x_hat)^2 mask / n_norm,  grad_h [n_t, n_traj, D] = d loss / d h  (the input of hode_fixed_bwd),
+ *   grad_w [obs, D], grad_b [obs]  (grad_w may be NULL together with grad_b: forward / evaluation only).
+ * h_out may be NULL (the latent solution is then never written), tape as in hode_fixed_fwd.
+ * x, mask: [n_t, n_traj, obs] CONTIGUOUS float32, 16-byte aligned (rows travel by TMA bulk copies).  One group, one
+ * parameter set.  hode_fixed_fwd_sse_supported() tells whether this (field, D, method, flags, n_dose, obs) has the fused
+ * kernel (RocheODE with HODE_FLAG_HILL2, D in {4, 6, 8}, obs in {20, 24, 40, 80}, n_dose == 1); otherwise the call
+ * returns HODE_ERR_UNSUPPORTED and the caller issues hode_fixed_fwd + hode_decode_sse. */
+int32_t hode_fixed_fwd_sse_supported(const hode_cfg* cfg, int32_t obs, int32_t n_param_sets);
+int32_t hode_fixed_fwd_sse(const hode_cfg* cfg, int64_t n_traj, const float* y0, const float* dose_amt, const float* dose_t,
+                           int64_t dose_t_stride, const float* params, const float* grid, int32_t n_grid,
+                           const float* t_eval, int32_t n_t, const float* W, const float* b, int32_t obs, const float* x,
+                           const float* mask, double n_norm, float* h_out, float* tape, float* loss, float* grad_h,
+                           float* grad_w, float* grad_b, void* stream);
 /* backward (autograd through every step, training_utils.py:50 `loss.backward()`):
  * grad_h [n_t, n_traj, D] -> grad_y0 [n_traj, D] (overwritten), grad_params [n_param_sets, P] (overwritten). */
 int32_t hode_fixed_bwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,

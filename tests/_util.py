@@ -46,3 +46,19 @@ def nan_pattern_equal(a, b):
 
 def grads_of(module):
     return {n: (p.grad.detach().clone() if p.grad is not None else None) for n, p in module.named_parameters()}
+
+
+def check(name, value, gate):
+    """Assert ``value <= gate`` and log the measured error next to its gate (``gpurun_out/parity_report.jsonl`` when that
+    directory exists): the report is how the gates are kept close to what the hardware actually delivers."""
+    import json
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = os.path.join(root, "gpurun_out")
+    rec = {"check": name, "value": float(value), "gate": float(gate), "ok": bool(value <= gate)}
+    if os.path.isdir(out):
+        with open(os.path.join(out, "parity_report.jsonl"), "a") as f:
+            f.write(json.dumps(rec) + "\n")
+    print("[parity] {:<70} {:.3e}  (gate {:.1e})".format(name, float(value), float(gate)))
+    assert value <= gate, rec

@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../hybrid_ode_neurips_2021_b200/csrc/hode_bodies.cuh"
+#include "../../hybrid_ode_neurips_2021_b200/csrc/hode_sse.cuh"
 #include "../../hybrid_ode_neurips_2021_b200/csrc/hode_real.cuh"
 
 using namespace hode;
@@ -94,6 +95,22 @@ void fixed_fwd(const SolveArgs& a) {
         for (int64_t b = 0; b < a.batch; ++b) { const int64_t idx = g * a.batch + b; fixed_fwd_traj<F, M>(a, sp.data(), dose(a, idx), idx); }
     }
 }
+// fused forward + read-out + masked SSE (SseSinkHost): one parameter set, one group
+template <class F, int M>
+void fixed_fwd_sse(const SolveArgs& a) {
+    auto sp = stage<F>(a, 0);
+    const int obs = a.sse_obs;
+    std::vector<float> gw((size_t)obs * F::D + obs, 0.f);
+    double loss = 0.0;
+    for (int64_t idx = 0; idx < a.batch; ++idx) {
+        SseSinkHost<F::D> sink{&a, a.batch, idx, gw.data(), 0.0};
+        fixed_fwd_traj<F, M>(a, sp.data(), dose(a, idx), idx, sink);
+        loss += sink.loss;
+    }
+    *a.sse_loss = (float)(loss * (double)a.sse_inv_norm);
+    if (a.sse_grad_w) for (int i = 0; i < obs * F::D; ++i) a.sse_grad_w[i] = gw[i];
+    if (a.sse_grad_b) for (int i = 0; i < obs; ++i) a.sse_grad_b[i] = gw[obs * F::D + i];
+}
 template <class F, int M>
 void fixed_bwd(const SolveArgs& a, bool eg) {
     for (int64_t g = 0; g < a.n_groups; ++g) {
@@ -171,7 +188,7 @@ void dopri5_bwd(const SolveArgs& a, bool eg) {
     }
 }
 
-enum Op { FF, FB, DF, DB, FA };
+enum Op { FF, FB, DF, DB, FA, FS };
 template <class F>
 int run(Op op, const hode_cfg& cfg, const SolveArgs& a) {
     const bool eg = cfg.expert_grads != 0;
@@ -190,6 +207,11 @@ int run(Op op, const hode_cfg& cfg, const SolveArgs& a) {
             if (cfg.method == HODE_EULER) fixed_adj<F, M_EULER>(a, eg);
             else if (cfg.method == HODE_MIDPOINT) fixed_adj<F, M_MIDPOINT>(a, eg);
             else fixed_adj<F, M_RK4_38>(a, eg);
+            return 0;
+        case FS:
+            if (cfg.method == HODE_EULER) fixed_fwd_sse<F, M_EULER>(a);
+            else if (cfg.method == HODE_MIDPOINT) fixed_fwd_sse<F, M_MIDPOINT>(a);
+            else fixed_fwd_sse<F, M_RK4_38>(a);
             return 0;
         case DF: dopri5_fwd<F>(a); return 0;
         case DB: dopri5_bwd<F>(a, eg); return 0;
@@ -246,6 +268,29 @@ int32_t hode_fixed_fwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, con
     SolveArgs a; fill(a, cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, pset);
     a.y0 = y0; a.grid = grid; a.n_grid = n_grid; a.t_eval_f = t_eval; a.n_t = n_t; a.h_out = h_out; a.tape_y = tape;
     return dispatch(FF, *cfg, a);
+}
+int32_t hode_fixed_fwd_sse_supported(const hode_cfg* cfg, int32_t obs, int32_t n_param_sets) {
+    // same rule as the device library (csrc/hode_api.cu)
+    if (!cfg || cfg->field != HODE_FIELD_ROCHE || cfg->method == HODE_DOPRI5) return 0;
+    if (!(cfg->flags & HODE_FLAG_HILL2) || (cfg->flags & HODE_FLAG_ABLATE)) return 0;
+    const int d = cfg->latent_dim;
+    if (d != 4 && d != 6 && d != 8) return 0;
+    if (cfg->n_dose != 1 || n_param_sets != 1) return 0;
+    return (obs == 20 || obs == 24 || obs == 40 || obs == 80) ? 1 : 0;  // the reference's observation widths
+}
+int32_t hode_fixed_fwd_sse(const hode_cfg* cfg, int64_t n_traj, const float* y0, const float* dose_amt, const float* dose_t,
+                           int64_t dose_t_stride, const float* params, const float* grid, int32_t n_grid,
+                           const float* t_eval, int32_t n_t, const float* W, const float* b, int32_t obs, const float* x,
+                           const float* mask, double n_norm, float* h_out, float* tape, float* loss, float* grad_h,
+                           float* grad_w, float* grad_b, void*) {
+    if (!hode_fixed_fwd_sse_supported(cfg, obs, 1)) return HODE_ERR_UNSUPPORTED;
+    SolveArgs a; fill(a, cfg, 1, n_traj, dose_amt, dose_t, dose_t_stride, params, nullptr);
+    a.y0 = y0; a.grid = grid; a.n_grid = n_grid; a.t_eval_f = t_eval; a.n_t = n_t; a.h_out = h_out; a.tape_y = tape;
+    a.sse_x = x; a.sse_mask = mask; a.sse_w = W; a.sse_b = b; a.sse_obs = obs;
+    a.sse_scale = (float)(-2.0 / n_norm); a.sse_inv_norm = (float)(1.0 / n_norm);
+    a.sse_loss = loss; a.sse_grad_h = grad_h; a.sse_grad_w = grad_w; a.sse_grad_b = grad_b;
+    *loss = 0.f;
+    return dispatch(FS, *cfg, a);
 }
 int32_t hode_fixed_bwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,
                        const float* dose_t, int64_t dose_t_stride, const float* params, const int32_t* pset,

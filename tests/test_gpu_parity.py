@@ -712,3 +712,72 @@ def test_masked_sse_accepts_one_byte_masks():
         # the loss and grad_W are reduced with atomics (order varies from launch to launch): rounding-level agreement
         assert abs(r[0].item() - res[0][0].item()) <= 1e-6 * abs(res[0][0].item())
         assert relerr(r[2], res[0][2]) < 1e-5
+
+
+@pytest.mark.parametrize("D,obs,B", [(8, 40, 300), (8, 40, 77), (6, 20, 129), (4, 24, 64), (8, 80, 33), (8, 20, 1)])
+def test_fused_solve_readout_sse_against_the_two_launch_path_and_the_oracle(D, obs, B):
+    """decoder.loss = ONE forward launch (solve + read-out + masked SSE consumed at the output times, hode_fixed_fwd_sse) +
+    the reverse sweep, against (i) decoder.solve + masked_sse (the same arithmetic in three launches) and (ii) the CPU oracle.
+    Partial warps (B not a multiple of 32), every owner-lane geometry (D = 4, 6, 8; obs = 20, 24, 40, 80)."""
+    from hybrid_ode_neurips_2021_b200 import _lib as L, ops, solver
+
+    od = OF.OracleDecoder(obs, D, method="rk4", options={"step_size": 0.125})
+    dec = H.RocheExpertDecoder(obs, D, 1, 14, 1, method="rk4", device=DEV, solver_options={"step_size": 0.125})
+    dec.load_state_dict(od.state_dict())
+    y0, a, x, mask = make_cohort(B, D, obs=obs, seed=40 + B)
+    # (ii) oracle
+    z = y0.clone().requires_grad_(True)
+    xh, _ = od(z, a)
+    loss_ref = OF.masked_sse(x, xh, mask)
+    loss_ref.backward()
+    # fused
+    zf = y0.clone().to(DEV).requires_grad_(True)
+    dec.ode.set_action(a.to(DEV))
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.RK4_38, n_dose=1, hill2=True)
+    pb = ops.Problem(cfg, 1, B, dec.ode.dosage, dec.ode._dose_t_f32, solver.pack_params(dec.ode, L.FIELD_ROCHE).detach()[None], None)
+    assert ops.fixed_fwd_sse_supported(L.get_lib(), pb, obs, x.to(DEV), mask.to(DEV))  # the fused kernel is what runs below
+    loss = dec.loss(zf, a.to(DEV), x.to(DEV), mask.to(DEV))
+    loss.backward()
+    fused = (loss.item(), zf.grad.clone(), dec.output_function[0].weight.grad.clone(), dec.output_function[0].bias.grad.clone(),
+             dec.ode.ml_net[0].weight.grad.clone() if D > 4 else None)
+    # (i) two-launch path
+    dec.zero_grad()
+    zu = y0.clone().to(DEV).requires_grad_(True)
+    loss_u = H.masked_sse(dec, dec.solve(zu, a.to(DEV)), x.to(DEV), mask.to(DEV))
+    loss_u.backward()
+    assert abs(fused[0] - loss_u.item()) <= 2e-6 * abs(loss_u.item())
+    assert relerr(fused[1], zu.grad) < 2e-6  # same grad_h arithmetic up to the pairing of the FMAs
+    assert relerr(fused[2], dec.output_function[0].weight.grad) < 1e-5
+    assert relerr(fused[3], dec.output_function[0].bias.grad) < 1e-5
+    # oracle
+    assert abs(fused[0] - loss_ref.item()) <= 1e-5 * abs(loss_ref.item())
+    assert relerr(fused[1], z.grad) < 2e-5
+    assert relerr(fused[2], od.output_function[0].weight.grad) < 2e-5
+    assert relerr(fused[3], od.output_function[0].bias.grad) < 2e-5
+    if D > 4:
+        assert relerr(fused[4], od.ode.ml_net[0].weight.grad) < 2e-5
+
+
+def test_decoder_loss_falls_back_to_the_separate_launches_where_no_fused_kernel_exists():
+    """D = 12, dopri5, one-byte masks and strided measurements: same API, same result, solve + decode launches."""
+    B = 20
+    for D, obs, method, kw in ((12, 80, "rk4", {"step_size": 0.125}), (6, 20, "dopri5", None)):
+        od = OF.OracleDecoder(obs, D, method=method, options=dict(kw or {}))
+        dec = H.RocheExpertDecoder(obs, D, 1, 14, 1, method=method, device=DEV, solver_options=kw)
+        dec.load_state_dict(od.state_dict())
+        y0, a, x, mask = make_cohort(B, D, obs=obs, seed=9)
+        xh, _ = od(y0, a)
+        ref = OF.masked_sse(x, xh, mask).item()
+        z = y0.clone().to(DEV).requires_grad_(True)
+        loss = dec.loss(z, a.to(DEV), x.to(DEV), mask.to(DEV))
+        loss.backward()
+        assert abs(loss.item() - ref) <= 2e-4 * abs(ref) and z.grad is not None
+    # fused kernel with inputs it must first normalise: uint8 mask, non-contiguous x
+    D, obs = 8, 40
+    dec = H.RocheExpertDecoder(obs, D, 1, 14, 1, method="rk4", device=DEV, solver_options={"step_size": 0.125})
+    y0, a, x, mask = make_cohort(B, D, obs=obs, seed=10)
+    base = dec.loss(y0.to(DEV), a.to(DEV), x.to(DEV), mask.to(DEV)).item()
+    xs = x.permute(1, 2, 0).contiguous().permute(2, 0, 1).to(DEV)  # the reference's [N][obs][T] storage
+    assert not xs.is_contiguous()
+    again = dec.loss(y0.to(DEV), a.to(DEV), xs, mask.to(torch.uint8).to(DEV)).item()
+    assert abs(again - base) <= 1e-6 * abs(base)

@@ -12,7 +12,7 @@ from torch import nn
 import hybrid_ode_neurips_2021_b200 as H
 from oracle import fields as OF
 
-from _util import relerr
+from _util import check, relerr
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -38,8 +38,7 @@ def iteration(enc, dec, data, fused):
     x, a, mask = data["measurements"], data["actions"], data["masks"]
     mu, log_var = enc(x, a, mask)
     if fused:
-        h = dec.solve(mu, a)
-        lik = H.masked_sse(dec, h, x, mask)
+        lik = dec.loss(mu, a, x, mask)  # rk4: solve + read-out + masked SSE in one launch; dopri5 / adjoint: solve, then fused decode
     else:
         x_hat, _ = dec(mu, a)
         lik = torch.sum((x - x_hat) ** 2 * mask) / x.shape[1]
@@ -48,9 +47,10 @@ def iteration(enc, dec, data, fused):
 
 
 @pytest.mark.parametrize("method,opts,adjoint,tol", [
-    ("rk4", {"step_size": 0.0625}, False, 2e-4),
-    ("dopri5", None, False, 1e-3),
-    ("rk4", {"step_size": 0.0625}, True, 2e-4),
+    # loss gate (1e-6); gradients are gated at 10x = 1e-5.  Measured on B200: loss <= 1e-7, gradients <= 2.2e-6
+    ("rk4", {"step_size": 0.0625}, False, 1e-6),
+    ("dopri5", None, False, 1e-6),
+    ("rk4", {"step_size": 0.0625}, True, 1e-6),
 ])
 def test_training_iteration_matches_cpu_oracle_and_learns(method, opts, adjoint, tol):
     D, obs, B = 6, 20, 50
@@ -90,12 +90,13 @@ def test_training_iteration_matches_cpu_oracle_and_learns(method, opts, adjoint,
     loss_c.backward()
     loss_g = iteration(enc_g, dec_g, batch, fused=True)
     loss_g.backward()
-    assert abs(loss_g.item() - loss_c.item()) <= tol * abs(loss_c.item())
+    tag = "training iteration [{}{}]".format(method, " adjoint" if adjoint else "")
+    check(tag + " loss", abs(loss_g.item() - loss_c.item()) / abs(loss_c.item()), tol)
     # the encoder only sees the decoder through dL/dy0 of the custom autograd op
-    assert relerr(enc_g.lstm.weight_ih_l0.grad, enc_c.lstm.weight_ih_l0.grad) < 5 * tol
-    assert relerr(enc_g.lin.weight.grad, enc_c.lin.weight.grad) < 5 * tol
-    assert relerr(dec_g.ode.ml_net[0].weight.grad, dec_c.ode.ml_net[0].weight.grad) < 5 * tol
-    assert relerr(dec_g.output_function[0].weight.grad, dec_c.output_function[0].weight.grad) < 5 * tol
+    check(tag + " grad lstm.weight_ih", relerr(enc_g.lstm.weight_ih_l0.grad, enc_c.lstm.weight_ih_l0.grad), 10 * tol)
+    check(tag + " grad encoder.lin", relerr(enc_g.lin.weight.grad, enc_c.lin.weight.grad), 10 * tol)
+    check(tag + " grad ml_net", relerr(dec_g.ode.ml_net[0].weight.grad, dec_c.ode.ml_net[0].weight.grad), 10 * tol)
+    check(tag + " grad output_function", relerr(dec_g.output_function[0].weight.grad, dec_c.output_function[0].weight.grad), 10 * tol)
 
     params = list(enc_g.parameters()) + list(dec_g.ode.ml_net.parameters()) + list(dec_g.output_function.parameters())
     opt = torch.optim.Adam(params, lr=0.01)

@@ -387,3 +387,111 @@ def test_continuous_adjoint_parameter_sets_single_time_and_empty_cohort(lib_adj)
     pb0 = ops.Problem(cfg, 1, 0, os_[0].dosage.float()[:0], os_[0].times.float()[:0], pack_roche(os_[0]), None)
     gy, gp = ops.fixed_adjoint(lib, pb0, adj_grid, adj_count, h2[:, :0].contiguous(), W[:, :0].contiguous())
     assert gy.shape == (0, D) and float(gp.abs().max()) == 0.0
+
+
+@pytest.fixture(scope="module")
+def lib_sse():
+    subprocess.run(["make", "-C", HS_DIR], check=True, capture_output=True)
+    return L.HodeLib(HS, required=SYMS + ["hode_fixed_fwd_sse", "hode_fixed_fwd_sse_supported"])
+
+
+@pytest.mark.parametrize("D,obs", [(8, 40), (6, 20), (4, 24), (8, 80)])
+@pytest.mark.parametrize("method,opts", [("rk4", {"step_size": 0.125}), ("midpoint", {"step_size": 0.3, "perturb": True}),
+                                         ("euler", {"step_size": 0.0625})])
+def test_fused_forward_readout_sse(lib_sse, D, obs, method, opts):
+    """hode_fixed_fwd_sse (forward solve with read-out + masked SSE consumed at the output times) + hode_fixed_bwd against
+    autograd through the oracle decoder: loss, d loss / d h, read-out gradients, d loss / d y0 and d loss / d theta."""
+    lib, B = lib_sse, 11
+    o = oracle_roche(D, 3, True)
+    y0, a, x, mask = make_cohort(B, D, obs=obs, seed=21 + D)
+    o.set_action(a)
+    t = torch.arange(0, 15.0)
+    torch.manual_seed(5)
+    lin = torch.nn.Linear(D, obs)
+    y0c = y0.clone().requires_grad_(True)
+    h_ref = OI.odeint(o, y0c, t, method=method, options=dict(opts))
+    h_ref.retain_grad()
+    loss_ref = OF.masked_sse(x, lin(h_ref), mask)
+    loss_ref.backward()
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.METHODS[method], n_dose=1, perturb=opts.get("perturb", False), hill2=True)
+    pb = problem(o, cfg, B)
+    assert ops.fixed_fwd_sse_supported(lib, pb, obs, x, mask)
+    grid = __import__("hybrid_ode_neurips_2021_b200").solver.fixed_grid_points(t, opts["step_size"])
+    loss, gh, gw, gb, h, tape = ops.fixed_fwd_sse(lib, pb, y0, grid, t, lin.weight.detach(), lin.bias.detach(), x, mask, B,
+                                                  want_tape=True, want_h=True)
+    assert abs(loss.item() - loss_ref.item()) <= 2e-6 * abs(loss_ref.item())
+    assert relerr(h, h_ref) < 1e-5
+    assert relerr(gh, h_ref.grad) < 1e-5
+    assert relerr(gw, lin.weight.grad) < 1e-5 and relerr(gb, lin.bias.grad) < 1e-5
+    gy0, gp = ops.fixed_bwd(lib, pb, grid, t, gh, tape)
+    assert relerr(gy0, y0c.grad) < 2e-5
+    ref = grads_vec(o, False)
+    if D > 4:
+        assert relerr(gp[0][13:], ref[13:]) < 2e-5  # ml_net weights + biases
+    # forward-only form: no tape, no latent solution, no parameter gradients
+    loss2, gh2, gw2, gb2, h2, tape2 = ops.fixed_fwd_sse(lib, pb, y0, grid, t, lin.weight.detach(), lin.bias.detach(), x, mask, B,
+                                                        want_tape=False, want_param_grads=False)
+    assert gw2 is None and h2 is None and tape2 is None and loss2.item() == loss.item() and torch.equal(gh2, gh)
+
+
+def test_fused_forward_support_rule(lib_sse):
+    lib = lib_sse
+    ok = lambda **kw: bool(lib.hode_fixed_fwd_sse_supported(__import__("ctypes").byref(ops.make_cfg(  # noqa: E731
+        kw.get("field", L.FIELD_ROCHE), kw.get("D", 8), kw.get("method", L.RK4_38), n_dose=kw.get("n_dose", 1),
+        hill2=kw.get("hill2", True), ablate=kw.get("ablate", False))), kw.get("obs", 40), kw.get("sets", 1)))
+    assert ok() and ok(D=6, obs=20) and ok(D=4, obs=24) and ok(obs=80) and ok(method=L.EULER)
+    assert not ok(D=12) and not ok(obs=42) and not ok(method=L.DOPRI5) and not ok(hill2=False) and not ok(ablate=True)
+    assert not ok(n_dose=2) and not ok(sets=2) and not ok(field=L.FIELD_NEURAL) and not ok(obs=128) and not ok(obs=44)
+
+
+@pytest.mark.parametrize("method,step", [("rk4", 0.125), ("midpoint", 0.0625), ("euler", 0.03125)])
+def test_generic_hill_exponents_forward_and_all_expert_gradients(lib, method, step):
+    """HillCure / HillPatho != 2: the general ``powf`` path of the field and of its VJP (d/dx x**p, d/dp x**p, the ec50 and
+    Hill-exponent gradient terms) against autograd through the reference formula -- the path that becomes live as soon as a
+    caller trains the expert scalars (``expert_grads=True`` is the default of ``odeint``).  Fixed grids only: with fractional
+    exponents an adaptive trial stage that overshoots to a negative state is NaN, which ends a torchdiffeq solve as
+    'underflow in dt nan' (oracle and kernels alike)."""
+    D, B = 6, 4
+    o = oracle_roche(D, 7, True)
+    with torch.no_grad():
+        o.HillCure.fill_(1.5)
+        o.HillPatho.fill_(2.5)
+        o.ec50_patho.fill_(0.8)
+    y0, a, _, _ = make_cohort(B, D, seed=31)
+    y0 = y0 + 0.05  # states stay positive: every power and logarithm is finite
+    o.set_action(a)
+    t = torch.arange(0, 6.0)
+    W = torch.randn(6, B, D, generator=torch.Generator().manual_seed(2))
+    z = y0.clone().requires_grad_(True)
+    ref = OI.odeint(o, z, t, method=method, options={"step_size": step})
+    (ref * W).sum().backward()
+    gref = grads_vec(o, False)
+    assert bool(torch.isfinite(gref).all()) and float(gref[:2].abs().min()) > 0  # the two exponents do receive gradients
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.METHODS[method], n_dose=1, hill2=False)
+    pb = problem(o, cfg, B)
+    grid = OI.fixed_grid_points(t, step).contiguous()
+    h, tape = ops.fixed_fwd(lib, pb, y0, grid, t, True)
+    gy0, gp = ops.fixed_bwd(lib, pb, grid, t, W, tape)
+    assert relerr(h, ref) < 1e-5
+    assert relerr(gy0, z.grad) < 2e-5
+    assert relerr(gp[0], gref) < 5e-5  # all 13 expert scalars (incl. HillCure, HillPatho, ec50) + ml_net
+
+
+def test_generic_hill_exponents_nan_pattern_for_negative_states(lib):
+    """A negative ImmuneReact with HillPatho = 2.5 is NaN in the reference (``model.py:537-538``) and must be
+    NaN here -- for that patient only; x == 0 is finite."""
+    D, B = 4, 3
+    o = oracle_roche(D, 8, False)
+    with torch.no_grad():
+        o.HillPatho.fill_(2.5)
+    y0 = torch.tensor([[0.5, 0.3, 0.2, 0.1], [0.5, -0.3, 0.2, 0.1], [0.5, 0.0, 0.2, 0.1]])
+    a = torch.zeros(15, B, 1)
+    a[2, :, 0] = 1.0
+    o.set_action(a)
+    t = torch.arange(0, 3.0)
+    ref = OI.odeint(o, y0, t, method="euler", options={"step_size": 0.5})
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.EULER, n_dose=1, hill2=False)
+    h, _ = ops.fixed_fwd(lib, problem(o, cfg, B), y0, OI.fixed_grid_points(t, 0.5).contiguous(), t, False)
+    assert torch.equal(torch.isnan(h), torch.isnan(ref)) and bool(torch.isnan(h[1:, 1]).any()) and not bool(torch.isnan(h[:, [0, 2]]).any())
+    ok = ~torch.isnan(ref)
+    assert relerr(h[ok], ref[ok]) < 1e-5

@@ -99,3 +99,21 @@ def test_dose_tables_equal_the_reference_sums(lib):
         got = tabn[0, n] if n < T else torch.zeros(B)
         # torch.cumsum adds in scan order, the table sequentially: last-bit differences only
         assert torch.allclose(got, n_.dose_at_time(torch.tensor(t))[:, 0], rtol=2e-6, atol=0), t
+
+
+def test_neural_real_negative_time_index_wraps_like_python(lib):
+    """``cumsum(action)[int(t)]`` (model.py:753-760) with ``int(t) == -1`` is Python negative indexing: the LAST row.  It is
+    what a direct ``odeint`` call sees at ``t[0] = -1`` without ``perturb`` (DecoderReal's default grid starts at ``t0 - 1``)."""
+    B, T, Z, H = 3, 12, 4, 7
+    kind = L.FIELD_NEURAL_REAL
+    o = make_oracle(kind, Z, H, seed=3)
+    y0, a, s = icu_cohort(B, Z, T, seed=5)
+    o.set_action_static(a, s)
+    t = torch.arange(-1.0, 4.0, 1.0)
+    ref = OI.odeint(o, y0, t, method="euler", options={"step_size": 1.0})
+    assert float((o.dose_at_time(torch.tensor(-1.0)) - torch.cumsum(a, 0)[-1]).abs().max()) == 0.0
+    params = R.pack_real_params(o, kind).detach().contiguous()
+    tab = ops.real_dose_tables(lib, kind, a, params)
+    grid = OI.fixed_grid_points(t, 1.0).contiguous()
+    h, _ = ops.real_fixed_fwd(lib, kind, Z, H, L.EULER, False, y0, tab, params, grid, t, False)
+    assert relerr(h, ref) < 5e-6

@@ -3,8 +3,8 @@ encoder output and every parameter gradient of ``VariationalInference.loss`` + `
 ``EncoderLSTM`` / ``RocheExpertDecoder`` / ``VariationalInference`` classes (``oracle/make_golden_training.py``; only the
 missing torchdiffeq is restated).  The CPU test checks the fixture against the oracle decoder + the test's encoder replica
 (same state_dict keys as the reference's); the GPU test runs the drop-in decoder with the fused loss against the fixture.
-Tolerances: CPU 1e-5 (same arithmetic); GPU 1e-3 on the loss and norm-wise on gradients (dopri5 at the reference's
-1e-7 / 1e-8 tolerances sits in float32 rounding noise, and the fixture's first step carries gradient -- DESIGN.md section 4)."""
+Tolerances: CPU 1e-5 (same arithmetic); GPU 1e-6 on the loss, 2e-5 on x_hat and 1e-4 norm-wise on the gradients (the fixture's
+first step carries gradient -- SURVEY.md App. D.5 -- which the kernels' constant-first-step gradient differs from by 3.5e-5)."""
 import os
 
 import numpy as np
@@ -14,7 +14,7 @@ import torch
 import hybrid_ode_neurips_2021_b200 as H
 from oracle import fields as OF
 
-from _util import relerr
+from _util import check as gate, relerr
 from test_gpu_training import Encoder, iteration
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden", "training_iter_d6.npz")
@@ -29,14 +29,16 @@ def load():
     return g, sd, grads, data
 
 
-def check(enc, dec, loss, grads, g, tol):
-    assert abs(loss.item() - float(g["loss"])) <= tol * abs(float(g["loss"]))
+def check(enc, dec, loss, grads, g, tol, tag="cpu", grad_tol=None):
+    grad_tol = 5 * tol if grad_tol is None else grad_tol
+    gate("training fixture [{}] loss".format(tag), abs(loss.item() - float(g["loss"])) / abs(float(g["loss"])), tol)
     for name, ref in grads["enc"].items():
         got = dict(enc.named_parameters())[name].grad
-        assert got is not None and relerr(got, ref) < 5 * tol, name
+        assert got is not None
+        gate("training fixture [{}] grad encoder.{}".format(tag, name), relerr(got, ref), grad_tol)
     for name in ("ode.ml_net.0.weight", "ode.ml_net.0.bias", "output_function.0.weight", "output_function.0.bias"):
         got = dict(dec.named_parameters())[name].grad
-        assert relerr(got, grads["dec"][name]) < 5 * tol, name
+        gate("training fixture [{}] grad decoder.{}".format(tag, name), relerr(got, grads["dec"][name]), grad_tol)
 
 
 def test_fixture_is_reproduced_by_the_oracle_iteration_on_cpu():
@@ -70,5 +72,8 @@ def test_drop_in_iteration_matches_the_reference_fixture():
     h = dec.solve(mu, batch["actions"])
     loss = H.masked_sse(dec, h, batch["measurements"], batch["masks"])
     loss.backward()
-    assert relerr(dec.output_function(h), torch.from_numpy(g["x_hat"])) < 1e-3
-    check(enc, dec, loss, grads, g, 1e-3)
+    gate("training fixture [gpu] x_hat", relerr(dec.output_function(h), torch.from_numpy(g["x_hat"])), 2e-5)
+    # loss 1e-6.  Gradients 1e-4: the fixture was produced with torchdiffeq's differentiable first
+    # step (the open point) while the kernels implement the constant-first-step gradient; the measured gap
+    # is 3.5e-5 on the encoder gradients / ml_net bias and 3.6e-6 on the ml_net weights (B200, round 2).
+    check(enc, dec, loss, grads, g, 1e-6, tag="gpu", grad_tol=1e-4)
