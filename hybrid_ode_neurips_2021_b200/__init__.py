@@ -13,6 +13,7 @@ from .real import RocheODEReal, NeuralODEReal, NeuralODEReal2nd, DecoderReal  # 
 from .loss import masked_sse, decode_sse_loss  # noqa: F401
 from .integrate import install_as_torchdiffeq, patch_model  # noqa: F401
 from .datagen import DataGeneratorRoche  # noqa: F401
-from .evaluation import crps_ensemble, mc_solve, decode_crps, evaluate_chunk  # noqa: F401
+from .evaluation import (crps_ensemble, mc_solve, decode_crps, evaluate_chunk, evaluate, evaluate_horizon,  # noqa: F401
+                         evaluate_ensemble, evaluate_ensemble_horizon, bootstrap_RMSE)
 
 __version__ = "0.1.0"

@@ -18,7 +18,7 @@ FIELD_ROCHE, FIELD_NEURAL = 0, 1
 FIELD_ROCHE_REAL, FIELD_NEURAL_REAL, FIELD_NEURAL_REAL_2ND = 2, 3, 4
 EULER, MIDPOINT, RK4_38, DOPRI5 = 0, 1, 2, 3
 CTRL_BATCH, CTRL_TRAJ = 0, 1
-FLAG_HILL2, FLAG_ABLATE = 1, 2
+FLAG_HILL2, FLAG_ABLATE, FLAG_ADJ_SEMINORM = 1, 2, 4
 METHODS = {"euler": EULER, "midpoint": MIDPOINT, "rk4": RK4_38, "dopri5": DOPRI5}
 SOLVE_OK, SOLVE_DT_UNDERFLOW, SOLVE_NONFINITE, SOLVE_MAX_STEPS, SOLVE_TAPE_FULL = 0, 1, 2, 3, 4
 OK, ERR_ARG, ERR_UNSUPPORTED, ERR_CUDA, ERR_NO_DEVICE = 0, -1, -2, -3, -4
@@ -69,6 +69,7 @@ SIGNATURES = {
         _I32,
         [_CFG, _I64, _I64, _P, _P, _I64, _P, _P, _I32, _P, _I32, _P, _P, _P, _I32, _P, _P, _P, _P],
     ),
+    "hode_dopri5_adjoint": (_I32, [_CFG, _I64, _I64, _P, _P, _I64, _P, _P, _I32, _P, _I32, _P, _P, _P, _P, _P, _P]),
     "hode_bench_ffma": (_I64, [_I32, _I32, _P, _P]),
     "hode_real_param_count": (_I64, [_I32, _I32, _I32]),
     "hode_real_dose_tables": (_I32, [_I32, _P, _I64, _I64, _I32, _I64, _P, _P, _P]),

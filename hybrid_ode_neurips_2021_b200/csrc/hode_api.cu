@@ -14,6 +14,7 @@ template <class F> int launch_fixed_bwd(const hode_cfg&, const SolveArgs&, cudaS
 template <class F> int launch_fixed_adj(const hode_cfg&, const SolveArgs&, cudaStream_t);
 template <class F> int launch_dopri5_fwd(const hode_cfg&, const SolveArgs&, cudaStream_t);
 template <class F> int launch_dopri5_bwd(const hode_cfg&, const SolveArgs&, cudaStream_t);
+template <class F> int launch_dopri5_adj(const hode_cfg&, const SolveArgs&, cudaStream_t);
 int launch_dose_schedule(const float*, int64_t, int64_t, int32_t, int64_t, float*, int32_t*, int32_t*, cudaStream_t);
 int launch_decode_sse(int32_t, int32_t, int32_t, int64_t, double, const float*, const float*, const float*,
                       const float*, const float*, int64_t, int64_t, int64_t, float*, float*, float*, float*,
@@ -35,7 +36,7 @@ static int fail(int code, const char* fmt, const char* a = "", long long b = 0) 
     return code;
 }
 
-enum Op { OP_FIXED_FWD, OP_FIXED_BWD, OP_DOPRI5_FWD, OP_DOPRI5_BWD, OP_FIXED_ADJ, OP_FIXED_FWD_SSE };
+enum Op { OP_FIXED_FWD, OP_FIXED_BWD, OP_DOPRI5_FWD, OP_DOPRI5_BWD, OP_FIXED_ADJ, OP_FIXED_FWD_SSE, OP_DOPRI5_ADJ };
 
 template <class F>
 static int run(Op op, const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) {
@@ -46,6 +47,7 @@ static int run(Op op, const hode_cfg& cfg, const SolveArgs& a, cudaStream_t st) 
         case OP_DOPRI5_BWD: return launch_dopri5_bwd<F>(cfg, a, st);
         case OP_FIXED_ADJ: return launch_fixed_adj<F>(cfg, a, st);
         case OP_FIXED_FWD_SSE: return launch_fixed_fwd_sse<F>(cfg, a, st);
+        case OP_DOPRI5_ADJ: return launch_dopri5_adj<F>(cfg, a, st);
     }
     return -1;
 }
@@ -83,6 +85,7 @@ static int dispatch(Op op, const hode_cfg& cfg, const SolveArgs& a, cudaStream_t
     }
     if (rc == 0) return HODE_OK;
     if (rc == -2) return fail(HODE_ERR_UNSUPPORTED, "batch-coupled dopri5 group larger than %s%lld trajectories", "", hode_dopri5_max_batch(&cfg));
+    if (rc == -3) return fail(HODE_ERR_UNSUPPORTED, "the adaptive adjoint of the NeuralODE field is built for the batch-coupled controller only%s%lld", "", 0);
     if (rc == -1 && op == OP_FIXED_FWD_SSE)
         return fail(HODE_ERR_UNSUPPORTED, "no fused solve + read-out kernel for this field / method / obs / n_dose / parameter-set "
                                           "combination (use hode_fixed_fwd + hode_decode_sse)%s%lld", "", 0);
@@ -254,6 +257,31 @@ int32_t hode_fixed_adjoint(const hode_cfg* cfg, int64_t n_groups, int64_t batch,
     a.grid = adj_grid; a.n_grid = n_adj_grid; a.adj_cnt = adj_count; a.n_t = n_t;
     a.h_out = const_cast<float*>(h); a.grad_h = grad_h; a.grad_y0 = grad_y0; a.grad_params = grad_params;
     return dispatch(OP_FIXED_ADJ, *cfg, a, (cudaStream_t)stream);
+}
+
+int32_t hode_dopri5_adjoint(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,
+                            const float* dose_t, int64_t dose_t_stride, const float* params,
+                            const int32_t* param_set_of_group, int32_t n_param_sets, const double* t_eval, int32_t n_t,
+                            const float* h, const float* grad_h, float* grad_y0, float* grad_params, hode_stats* stats,
+                            void* stream) {
+    int rc = check_common(cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, n_t);
+    if (rc) return rc;
+    if (cfg->method != HODE_DOPRI5) return fail(HODE_ERR_ARG, "hode_dopri5_adjoint called with a fixed-grid method (use hode_fixed_adjoint)");
+    if (!(cfg->flags & HODE_FLAG_ADJ_SEMINORM))
+        return fail(HODE_ERR_UNSUPPORTED, "the adaptive adjoint is built for torchdiffeq's 'seminorm' (adjoint_options={'norm': 'seminorm'}, "
+                                          "HODE_FLAG_ADJ_SEMINORM): the default mixed norm also controls the step size by the parameter adjoints");
+    if (!t_eval || !stats || n_param_sets < 1 || !grad_params) return fail(HODE_ERR_ARG, "NULL / bad t_eval, stats or grad_params");
+    const int64_t P = hode_param_count(cfg);
+    cudaError_t e = cudaMemsetAsync(grad_params, 0, sizeof(float) * (size_t)P * (size_t)n_param_sets, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail(HODE_ERR_CUDA, "CUDA error: %s (%lld)", cudaGetErrorString(e), (long long)e);
+    if (n_groups * batch == 0) return HODE_OK;
+    if (!h || !grad_h || !grad_y0) return fail(HODE_ERR_ARG, "NULL h / grad_h / grad_y0");
+    SolveArgs a;
+    fill_common(a, cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, param_set_of_group);
+    a.n_param_sets = n_param_sets;
+    a.t_eval_d = t_eval; a.n_t = n_t; a.h_out = const_cast<float*>(h); a.grad_h = grad_h;
+    a.stats = stats; a.grad_y0 = grad_y0; a.grad_params = grad_params;
+    return dispatch(OP_DOPRI5_ADJ, *cfg, a, (cudaStream_t)stream);
 }
 
 int32_t hode_dopri5_fwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* y0,

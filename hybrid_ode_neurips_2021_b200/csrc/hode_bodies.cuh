@@ -332,16 +332,30 @@ HODE_HD bool any_nonfinite(const float (&v)[D]) {
 // Stage inputs of one attempt: Y_i = y0 + sum_{j <= i} k_j (beta[i][j] dt), j ascending (tde: `y0 + k[..., :i+1] @ (beta_i*dt)`).
 // Rows 0 .. i-1 come from storage, row i (`klast`) is still in registers from the evaluation that produced it.
 template <int D, bool UNROLL, class KS>
-HODE_HD void d5_stage_input(const KS& k, int i, float dtf, const float (&y0)[D], const float (&klast)[D], float (&yi)[D]) {
+HODE_HD void d5_stage_input(const KS& k, int i, float dtf, const float (&y0)[D], const float (&klast)[D], float (&yi)[D],
+                            int base = 0) {
     float acc[D];
 #pragma unroll
     for (int d = 0; d < D; ++d) acc[d] = 0.0f;
     range_up<UNROLL, 6>(0, i, [&](int j) {
         float row[D];
-        k.load(j, row);
+        k.load(base + j, row);
         v_axpy<D>(acc, mul_rn(d5_beta(i, j), dtf), row, acc);
     });
     v_axpy<D>(acc, mul_rn(d5_beta(i, i), dtf), klast, acc);
+    v_add<D>(yi, y0, acc);
+}
+// same combination with every row read from storage: y0 + sum_{j <= i} rows[base + j] (beta[i][j] dt)
+template <int D, bool UNROLL, class KS>
+HODE_HD void d5_stage_input_rows(const KS& k, int i, float dtf, const float (&y0)[D], float (&yi)[D], int base) {
+    float acc[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) acc[d] = 0.0f;
+    range_up<UNROLL, 6>(0, i + 1, [&](int j) {
+        float row[D];
+        k.load(base + j, row);
+        v_axpy<D>(acc, mul_rn(d5_beta(i, j), dtf), row, acc);
+    });
     v_add<D>(yi, y0, acc);
 }
 HODE_HD float d5_stage_time(int i, float t0f, float dtf, float t1f) {
@@ -737,6 +751,238 @@ HODE_HD void dopri5_bwd_traj(const SolveArgs& a, PS sp, const Dose& ds, KS& R, i
 #pragma unroll
     for (int d = 0; d < D; ++d) lam[d] += g0[d];
     if (!F::params_ok(sp)) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) lam[d] = nanf("");
+    }
+    store_vec<D>(a.grad_y0 + idx * D, lam);
+}
+
+
+// ==============================================================================================================
+// Adaptive continuous adjoint (tde adjoint.py OdeintAdjointMethod.backward with method dopri5): for every output interval
+// i = n_t-1 .. 1 the augmented state (y, a, g_theta) is integrated with the dopri5 controller from t[i] back to t[i-1] in
+// negated time s = -t (tde _ReverseFunc):  dy/ds = -f(-s, y),  da/ds = +J^T a,  dg/ds = +(df/dtheta)^T a;  then
+// a += grad_h[i-1] and y is reset to the forward solution h[i-1].  O(1) memory: no tape.
+// Error control: the 'seminorm' of tde (adjoint_options={'norm': 'seminorm'}): max(rms(err_y / tol_y), rms(err_a / tol_a)) over
+// the controller group -- the parameter part g_theta is integrated (same weights, same dense output) but takes no part in
+// the step-size decisions, so its stage values are only needed for ACCEPTED steps: they are formed in a second pass over the
+// stored stage rows (df/dtheta^T is linear in its cotangent: stage m is called with (w_m ds) A_m, w = the 5th-order weights,
+// or the dense-output weights w_m(x) for the last step of an interval, which tde interpolates back to t[i-1]).
+//   rows 0..6   f(Y_m) of the attempt's stages (positive sign; dy/ds = -f is applied in the combinations)
+//   rows 7..13  J(Y_m)^T A_m
+// ==============================================================================================================
+HODE_HD float d5_dense_weight(int m, float x) {
+    // y(x) = y0 + dt sum_m w_m(x) k_m for tde's quartic (_interp_fit / _interp_evaluate); w_m(1) = c_sol[m]
+    const float x2 = x * x, x3 = x2 * x, x4 = x3 * x;
+    const float bm = m < 6 ? d5_beta(5, m) : 0.0f;
+    float w = bm * (-5.0f * x2 + 14.0f * x3 - 8.0f * x4) + d5_cmid(m) * (16.0f * x2 - 32.0f * x3 + 16.0f * x4);
+    if (m == 0) w += x - 4.0f * x2 + 5.0f * x3 - 2.0f * x4;
+    if (m == 6) w += x2 - 3.0f * x3 + 2.0f * x4;
+    return w;
+}
+
+template <class F, bool EG, bool ROLLED, class PS, class Dose, class Comm, class KS, class ACC>
+HODE_HD void dopri5_adj_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds, KS& R, int64_t idx, bool valid, int64_t ctrl,
+                             bool leader, float count, ACC acc) {
+    constexpr int D = F::D;
+    constexpr bool UNROLL = !ROLLED;
+    static_assert(UNROLL || KS::kDynamic, "rolled stage loops need rows that can be indexed at run time");
+    const int64_t n_traj = a.n_groups * a.batch;
+    const float rtol = a.rtol_f, atol = a.atol_f;
+    const float inv_count = 1.0f / count;
+    const float safety = (float)a.safety, ifactor = (float)a.ifactor, dfactor = (float)a.dfactor;
+    const int max_steps = (int)(a.max_num_steps < 0x7fffffffLL ? a.max_num_steps : 0x7fffffffLL);
+    const int attempt_cap = (int)(a.attempt_cap < 0x7fffffffLL ? a.attempt_cap : 0x7fffffffLL);
+    int nacc = 0, nrej = 0, status = HODE_SOLVE_OK, attempts = 0;
+    float lam[D], y[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) lam[d] = 0.0f;
+    const bool poisoned = !F::params_ok(sp);
+
+    for (int iv = 0; iv + 1 < a.n_t && status == HODE_SOLVE_OK; ++iv) {
+        const int i = a.n_t - 1 - iv;
+        {
+            float g[D];
+            load_vec<D>(a.grad_h + ((int64_t)i * n_traj + idx) * D, g);
+            load_vec<D>(a.h_out + ((int64_t)i * n_traj + idx) * D, y);
+#pragma unroll
+            for (int d = 0; d < D; ++d) lam[d] += valid ? g[d] : 0.0f;
+        }
+        double s0 = -a.t_eval_d[i];
+        const double s_end = -a.t_eval_d[i - 1];
+        float flast[D], glast[D];
+        // f0 of the interval's solve: func(s0, state), no perturbation
+        F::eval(sp, -(float)s0, ds, y, flast);
+        vjp_state_only<F>(sp, -(float)s0, ds, y, (const float*)flast, lam, glast, acc);
+        R.store(0, flast);
+        R.store(7, glast);
+        // ---- _select_initial_step on the augmented state with the seminorm (dy/ds = -f: signs cancel inside the norms) ----
+        double dt;
+        if (a.first_step > 0.0) {
+            dt = a.first_step;
+        } else {
+            float sy[D], sa[D], q0 = 0.0f, q1 = 0.0f, r0 = 0.0f, r1 = 0.0f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                sy[d] = atol + fabsf(y[d]) * rtol;
+                sa[d] = atol + fabsf(lam[d]) * rtol;
+                const float u0 = y[d] / sy[d], u1 = flast[d] / sy[d], v0 = lam[d] / sa[d], v1 = glast[d] / sa[d];
+                q0 += u0 * u0; q1 += u1 * u1; r0 += v0 * v0; r1 += v1 * v1;
+            }
+            if (!valid) { q0 = q1 = r0 = r1 = 0.0f; }
+            cm.sum2(q0, q1);
+            cm.sum2(r0, r1);
+            const float d0 = nan_maxf(sqrtf(q0 / count), sqrtf(r0 / count)), d1 = nan_maxf(sqrtf(q1 / count), sqrtf(r1 / count));
+            float h0;
+            if (d0 < 1e-5f || d1 < 1e-5f) h0 = 1e-6f;
+            else h0 = (0.01f * d0) / d1;
+            float y1[D], a1[D], f1[D], g1[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) { y1[d] = y[d] - h0 * flast[d]; a1[d] = lam[d] + h0 * glast[d]; }
+            const float th = -add_rn((float)s0, h0);
+            F::eval(sp, th, ds, y1, f1);
+            vjp_state_only<F>(sp, th, ds, y1, (const float*)f1, a1, g1, acc);
+            float q2 = 0.0f, r2 = 0.0f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const float u = (f1[d] - flast[d]) / sy[d], v = (g1[d] - glast[d]) / sa[d];
+                q2 += u * u; r2 += v * v;
+            }
+            if (!valid) { q2 = r2 = 0.0f; }
+            cm.sum2(q2, r2);
+            const float d2 = nan_maxf(sqrtf(q2 / count), sqrtf(r2 / count)) / h0;
+            float h1;
+            if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
+            else h1 = powf(0.01f / ((d2 > d1) ? d2 : d1), 0.2f);
+            dt = (double)nan_minf(100.0f * h0, h1);
+        }
+        int n_steps = 0;
+        bool first = true;  // first step of this interval: k_1 was evaluated at s0 itself, later ones at prev(s1) (FSAL)
+        bool done = false;
+        while (!done) {
+            if (poisoned) { status = HODE_SOLVE_NONFINITE; break; }
+            if (n_steps >= max_steps || attempts >= attempt_cap) { status = HODE_SOLVE_MAX_STEPS; break; }
+            if (!(s0 + dt > s0)) { status = HODE_SOLVE_DT_UNDERFLOW; break; }
+            const double s1 = s0 + dt;
+            const float s0f = (float)s0, dsf = (float)dt, s1f = (float)s1;
+            float y1[D], a1[D], ey[D], ea[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) { ey[d] = 0.0f; ea[d] = 0.0f; }
+            R.load(0, flast);
+            R.load(7, glast);
+            stage_up<UNROLL, 0, 6>([&](auto il) {
+                float ts;
+                stage_switch<ROLLED, 6>(il, [&](auto ic) {
+                    const int m = ic;
+                    d5_stage_input<D, true>(R, m, -dsf, y, flast, y1, 0);
+                    d5_stage_input<D, true>(R, m, dsf, lam, glast, a1, 7);
+                    const float ce = mul_rn(dsf, d5_cerr(m));
+                    v_axpy<D>(ey, ce, flast, ey);
+                    v_axpy<D>(ea, ce, glast, ea);
+                    ts = d5_stage_time(m, s0f, dsf, s1f);
+                });
+                F::eval(sp, -ts, ds, y1, flast);
+                vjp_state_only<F>(sp, -ts, ds, y1, (const float*)flast, a1, glast, acc);
+                R.store((int)il + 1, flast);
+                R.store((int)il + 8, glast);
+            });
+            {
+                const float ce = mul_rn(dsf, d5_cerr(6));
+                v_axpy<D>(ey, ce, flast, ey);
+                v_axpy<D>(ea, ce, glast, ea);
+            }
+            float ssy = 0.0f, ssa = 0.0f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const float qy = div_tol(ey[d], fmaf(rtol, nan_maxf(fabsf(y[d]), fabsf(y1[d])), atol));
+                const float qa = div_tol(ea[d], fmaf(rtol, nan_maxf(fabsf(lam[d]), fabsf(a1[d])), atol));
+                ssy = fmaf(qy, qy, ssy);
+                ssa = fmaf(qa, qa, ssa);
+            }
+            if (!valid) { ssy = 0.0f; ssa = 0.0f; }
+            cm.sum2(ssy, ssa);
+            const float ratio = nan_maxf(fast_sqrt(ssy * inv_count), fast_sqrt(ssa * inv_count));
+            const bool accept = ratio <= 1.0f;
+            ++attempts; ++n_steps;
+            if (accept) {
+                ++nacc;
+                const bool last = s_end <= s1;  // the interval's output time is reached: tde interpolates back to it
+                const float x = last ? (float)((s_end - s0) / (s1 - s0)) : 1.0f;
+                // ---- parameter part of the accepted step: g_theta += ds sum_m w_m (df/dtheta(Y_m))^T A_m -------------------
+                stage_up<UNROLL, 0, 7>([&](auto il) {
+                    float Ym[D], Am[D], cot[D], frow[D], gdead[D], ts, w;
+                    stage_switch<ROLLED, 7>(il, [&](auto ic) {
+                        const int m = ic;
+                        w = last ? d5_dense_weight(m, x) : (m < 6 ? d5_beta(5, m) : 0.0f);
+                        if (m == 0) {
+#pragma unroll
+                            for (int d = 0; d < D; ++d) { Ym[d] = y[d]; Am[d] = lam[d]; }
+                            ts = first ? s0f : t_prev(s0f);
+                        } else {
+                            d5_stage_input_rows<D, true>(R, m - 1, -dsf, y, Ym, 0);
+                            d5_stage_input_rows<D, true>(R, m - 1, dsf, lam, Am, 7);
+                            ts = d5_stage_time(m - 1, s0f, dsf, s1f);
+                        }
+                    });
+                    if (w != 0.0f) {  // group-uniform (the tableau has c_sol[1] = c_sol[6] = 0)
+                        R.load((int)il, frow);
+                        v_scale<D>(cot, mul_rn(w, dsf), Am);
+                        F::template vjp<EG>(sp, -ts, ds, Ym, (const float*)frow, cot, gdead, acc);
+                    }
+                });
+                if (last) {
+                    // dense output of the adjoint at s_end (the state y is reset to the forward solution, g_theta was
+                    // interpolated through its weights above)
+                    float m_[D], g0[D];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) m_[d] = 0.0f;
+                    range_up<UNROLL, 7>(0, 7, [&](int mm) {
+                        float row[D];
+                        R.load(7 + mm, row);
+                        const float c = mul_rn(dsf, d5_cmid(mm));
+#pragma unroll
+                        for (int d = 0; d < D; ++d) m_[d] = fmaf(row[d], c, m_[d]);
+                    });
+                    R.load(7, g0);
+                    const float x2 = x * x, x3 = x2 * x, x4 = x3 * x;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        const float amid = lam[d] + m_[d], f0 = g0[d], f1 = glast[d];
+                        const float ca = 2.0f * dsf * (f1 - f0) - 8.0f * (a1[d] + lam[d]) + 16.0f * amid;
+                        const float cb = dsf * (5.0f * f0 - 3.0f * f1) + 18.0f * lam[d] + 14.0f * a1[d] - 32.0f * amid;
+                        const float cc = dsf * (f1 - 4.0f * f0) - 11.0f * lam[d] - 5.0f * a1[d] + 16.0f * amid;
+                        float tot = lam[d] + x * (dsf * f0);
+                        tot = tot + x2 * cc;
+                        tot = tot + x3 * cb;
+                        tot = tot + x4 * ca;
+                        lam[d] = tot;
+                    }
+                    done = true;
+                } else {
+                    R.store(0, flast);  // FSAL
+                    R.store(7, glast);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) { y[d] = y1[d]; lam[d] = a1[d]; }
+                    s0 = s1;
+                    first = false;
+                }
+            } else {
+                ++nrej;
+            }
+            dt = optimal_step(dt, ratio, safety, ifactor, dfactor);
+        }
+    }
+    if (leader) {
+        hode_stats st;
+        st.accepted = nacc; st.rejected = nrej; st.nfe = 0; st.status = status;
+        a.stats[ctrl] = st;
+    }
+    if (!valid) return;
+    float g0[D];
+    load_vec<D>(a.grad_h + idx * D, g0);
+#pragma unroll
+    for (int d = 0; d < D; ++d) lam[d] += g0[d];
+    if (poisoned) {
 #pragma unroll
         for (int d = 0; d < D; ++d) lam[d] = nanf("");
     }

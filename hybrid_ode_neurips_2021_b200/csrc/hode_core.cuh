@@ -1067,7 +1067,11 @@ struct RowsMem {
 // std::integral_constant<int, I> or an int; both convert to int.
 template <int I>
 struct IdxC {
+#if HODE_DEVICE_BUILD
+    __host__ __device__ constexpr operator int() const { return I; }
+#else
     constexpr operator int() const { return I; }
+#endif
 };
 template <bool UNROLL, int LO, int HI, class Fn>  // i = LO .. HI-1 ascending
 HODE_HD void stage_up(Fn&& fn) {

@@ -629,6 +629,54 @@ __global__ void __launch_bounds__(128, D5Store<F>::kBwdMinBlocks) dopri5_bwd_ker
     reduce_param_grads<F>(a, tl.group, acc, sred);
 }
 
+// Adaptive continuous adjoint (dopri5_adj_traj): one controller per CTA (batch-coupled, torchdiffeq semantics) or per
+// trajectory (flat launch).  14 rows per thread always live in shared memory (7 field values + 7 adjoint derivatives).
+// Parameter gradients: warp-cooperative accumulators where the field has them and the warp is converged (batch-coupled
+// groups: accept / reject is CTA-uniform); per-thread accumulators otherwise.
+template <class F, bool PER_TRAJ, bool EG, int ND, int MAXT, bool CP>
+__global__ void __launch_bounds__(MAXT, MAXT <= 128 ? 2 : 1) dopri5_adj_kernel(const SolveArgs a, int tiles_per_group) {
+    extern __shared__ __align__(16) float smem[];
+    float* sp = smem;
+    float* red = smem + (CP ? 0 : round4(F::SP));
+    float* sred = red + 128;
+    float* rows = sred + round4(F::P);
+    using RM = RowsMem<F::D, 14>;
+    float* coop_stage = rows + (size_t)RM::kFloatsPerThread * blockDim.x;
+    const Tile tl = tile_of(a, tiles_per_group);
+    if constexpr (!CP) stage_params<F>(a, tl.group, sp);
+    const bool valid = tl.b < a.batch;
+    const int64_t b = valid ? tl.b : (a.batch - 1);
+    const int64_t idx = tl.group * a.batch + b;
+    const int64_t ctrl = PER_TRAJ ? idx : tl.group;
+    const bool leader = PER_TRAJ ? valid : (threadIdx.x == 0);
+    const float count = PER_TRAJ ? (float)F::D : (float)(a.batch * F::D);
+    RM R{rows + threadIdx.x * RM::VEC, (int)blockDim.x * RM::VEC};
+    auto run = [&](auto& cm, auto accp) {
+        if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_adj_traj<F, EG, true>(a, cm, ParamConst(), ds, R, idx, valid, ctrl, leader, count, accp))); }
+        else { HODE_WITH_DOSE(ND, a, idx, (dopri5_adj_traj<F, EG, true>(a, cm, (const float*)sp, ds, R, idx, valid, ctrl, leader, count, accp))); }
+    };
+    if constexpr (!PER_TRAJ && CoopD5<F>::value) {
+        typename CoopD5<F>::type cp;
+        coop_init(cp, coop_stage);
+        CommCta cm{red, (int)(blockDim.x >> 5), 0};
+        run(cm, &cp);
+        if constexpr (!CoopOf<F>::value) coop_flush<F, EG>(a, tl.group, cp, sred);
+        else coop_flush(a, tl.group, cp, sred);
+    } else {
+        float acc[F::P];
+        zero_acc<F>(acc);
+        if (PER_TRAJ) {
+            CommNone cm;
+            if (valid) run(cm, (float*)acc);
+        } else {
+            CommCta cm{red, (int)(blockDim.x >> 5), 0};
+            run(cm, (float*)acc);
+        }
+        if (!valid) zero_acc<F>(acc);
+        reduce_param_grads<F>(a, tl.group, acc, sred);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // launchers (explicitly instantiated per field in inst_*.cu)
 // ---------------------------------------------------------------------------------------------------------------
@@ -895,6 +943,44 @@ int launch_dopri5_bwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t s
     HODE_DISPATCH_CP(F, a, st, HODE_DB_CP);
 #undef HODE_DB_CP
 #undef HODE_DB
+    HODE_LAUNCH_CHECK();
+    return 0;
+}
+
+template <class F>
+int launch_dopri5_adj(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st) {
+    const bool nd1 = cfg.n_dose == 1;
+    const bool eg = cfg.expert_grads != 0;
+    if (!a_in.per_traj && a_in.batch > HODE_DOPRI5_MAX_THREADS) return -2;
+    if (a_in.per_traj && CoopOf<F>::value) return -3;  // NeuralODE: cooperative accumulators need converged warps
+    const SolveArgs a = a_in.per_traj ? flatten(a_in) : a_in;
+    const int threads = a.per_traj ? (a.batch >= 128 ? 128 : round_up32(a.batch)) : round_up32(a.batch);
+    const int tiles = a.per_traj ? (int)((a.batch + threads - 1) / threads) : 1;
+    const int64_t nblk = a.n_groups * tiles;
+    size_t coop_floats = 0;
+    if constexpr (CoopD5<F>::value) coop_floats = (size_t)CoopD5<F>::type::kStageFloats * (size_t)(threads / 32);
+    const size_t sh_base = (size_t)128 + round4(F::P) + (size_t)14 * F::D * threads + coop_floats;
+#define HODE_DA(PT, EG, ND, MAXT, CP)                                                                              \
+    do {                                                                                                           \
+        const size_t sh_ = ((CP ? 0 : round4(F::SP)) + sh_base) * sizeof(float);                                   \
+        if (sh_ > 227 * 1024) return -2;                                                                           \
+        int e_ = set_smem(dopri5_adj_kernel<F, PT, EG, ND, MAXT, CP>, sh_);                                        \
+        if (e_ != 0) return e_;                                                                                    \
+        dopri5_adj_kernel<F, PT, EG, ND, MAXT, CP><<<(unsigned)nblk, threads, sh_, st>>>(a, tiles);                \
+    } while (0)
+#define HODE_DA_ND(PT, EG, MAXT, CP) do { if (nd1) HODE_DA(PT, EG, 1, MAXT, CP); else HODE_DA(PT, EG, 0, MAXT, CP); } while (0)
+#define HODE_DA_EG(PT, MAXT, CP) do { if (eg) HODE_DA_ND(PT, true, MAXT, CP); else HODE_DA_ND(PT, false, MAXT, CP); } while (0)
+#define HODE_DA_CP(CP)                                                              \
+    do {                                                                            \
+        if (a.per_traj) HODE_DA_EG(true, 128, CP);                                  \
+        else if (threads <= 128) HODE_DA_EG(false, 128, CP);                        \
+        else HODE_DA_EG(false, HODE_DOPRI5_MAX_THREADS, CP);                        \
+    } while (0)
+    HODE_DISPATCH_CP(F, a, st, HODE_DA_CP);
+#undef HODE_DA_CP
+#undef HODE_DA_EG
+#undef HODE_DA_ND
+#undef HODE_DA
     HODE_LAUNCH_CHECK();
     return 0;
 }

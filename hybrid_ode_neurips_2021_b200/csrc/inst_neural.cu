@@ -12,4 +12,5 @@ template int launch_fixed_bwd<Neural<HODE_INST_D>>(const hode_cfg&, const SolveA
 template int launch_fixed_adj<Neural<HODE_INST_D>>(const hode_cfg&, const SolveArgs&, cudaStream_t);
 template int launch_dopri5_fwd<Neural<HODE_INST_D>>(const hode_cfg&, const SolveArgs&, cudaStream_t);
 template int launch_dopri5_bwd<Neural<HODE_INST_D>>(const hode_cfg&, const SolveArgs&, cudaStream_t);
+template int launch_dopri5_adj<Neural<HODE_INST_D>>(const hode_cfg&, const SolveArgs&, cudaStream_t);
 }  // namespace hode

@@ -19,4 +19,5 @@ template int launch_fixed_bwd<InstField>(const hode_cfg&, const SolveArgs&, cuda
 template int launch_fixed_adj<InstField>(const hode_cfg&, const SolveArgs&, cudaStream_t);
 template int launch_dopri5_fwd<InstField>(const hode_cfg&, const SolveArgs&, cudaStream_t);
 template int launch_dopri5_bwd<InstField>(const hode_cfg&, const SolveArgs&, cudaStream_t);
+template int launch_dopri5_adj<InstField>(const hode_cfg&, const SolveArgs&, cudaStream_t);
 }  // namespace hode

@@ -149,9 +149,10 @@ class NeuralODE(_DoseMixin, nn.Module):
 
 class RocheExpertDecoder(nn.Module):
     def __init__(self, obs_dim, latent_dim, action_dim, t_max, step_size, roche=True, ablate=False, method="dopri5",
-                 ode_step_size=None, device=None, dtype=DTYPE, solver_options=None, adjoint=False):
+                 ode_step_size=None, device=None, dtype=DTYPE, solver_options=None, adjoint=False, adjoint_options=None):
         super().__init__()
         self.adjoint = bool(adjoint)  # True: backward by the continuous adjoint (model.py:9's alternative import)
+        self.adjoint_options = adjoint_options  # e.g. {'norm': 'seminorm'} for the adaptive (dopri5) adjoint
         self.time_dim = int(t_max / step_size)
         self.obs_dim = obs_dim
         self.latent_dim = latent_dim
@@ -185,9 +186,10 @@ class RocheExpertDecoder(nn.Module):
     def solve(self, init, a):
         """Latent trajectories ``h [T, B, D]`` only (no read-out)."""
         self.ode.set_action(a)
-        solve = odeint_adjoint if self.adjoint else odeint
-        return solve(self.ode, init, self.t, rtol=self.options["rtol"], atol=self.options["atol"],
-                     method=self.options["method"], options=self.solver_options)
+        kw = dict(rtol=self.options["rtol"], atol=self.options["atol"], method=self.options["method"], options=self.solver_options)
+        if self.adjoint:
+            return odeint_adjoint(self.ode, init, self.t, adjoint_options=self.adjoint_options, **kw)
+        return odeint(self.ode, init, self.t, **kw)
 
     def forward(self, init, a):
         h = self.solve(init, a)

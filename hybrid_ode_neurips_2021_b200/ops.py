@@ -43,9 +43,9 @@ def _f32c(t: torch.Tensor) -> torch.Tensor:
 
 def make_cfg(field, latent_dim, method, *, controller=L.CTRL_BATCH, perturb=False, n_dose=1, expert_grads=True,
              rtol=1e-7, atol=1e-9, safety=0.9, ifactor=10.0, dfactor=0.2, first_step=None,
-             max_num_steps=2 ** 31 - 1, attempt_cap=ATTEMPT_CAP_DEFAULT, hill2=False, ablate=False) -> L.HodeCfg:
+             max_num_steps=2 ** 31 - 1, attempt_cap=ATTEMPT_CAP_DEFAULT, hill2=False, ablate=False, adj_seminorm=False) -> L.HodeCfg:
     cfg = L.HodeCfg()
-    cfg.flags = (L.FLAG_HILL2 if hill2 else 0) | (L.FLAG_ABLATE if ablate else 0)
+    cfg.flags = (L.FLAG_HILL2 if hill2 else 0) | (L.FLAG_ABLATE if ablate else 0) | (L.FLAG_ADJ_SEMINORM if adj_seminorm else 0)
     cfg.field, cfg.latent_dim, cfg.method, cfg.controller = int(field), int(latent_dim), int(method), int(controller)
     cfg.perturb, cfg.n_dose, cfg.expert_grads = int(bool(perturb)), int(n_dose), int(bool(expert_grads))
     cfg.rtol, cfg.atol, cfg.safety, cfg.ifactor, cfg.dfactor = float(rtol), float(atol), float(safety), float(ifactor), float(dfactor)
@@ -203,6 +203,24 @@ def dopri5_bwd(lib, pb: Problem, t_eval64, grad_h, tape, stats):
                                  _ptr(gy0), _ptr(gp), _stream(grad_h))
     lib.check(rc, "hode_dopri5_bwd")
     return gy0, gp
+
+
+def dopri5_adjoint(lib, pb: Problem, t_eval64, h, grad_h):
+    """Adaptive continuous adjoint (``hode_dopri5_adjoint``): no tape, needs the forward solution ``h``.
+    Returns ``grad_y0, grad_params, stats [n_ctrl, 4]``."""
+    D = pb.cfg.latent_dim
+    grad_h, h = _f32c(grad_h), _f32c(h)
+    dev = grad_h.device
+    n_ctrl = pb.n_traj if pb.cfg.controller == L.CTRL_TRAJ else pb.n_groups
+    gy0 = torch.empty(pb.n_traj, D, dtype=torch.float32, device=dev)
+    gp = torch.empty_like(pb.params)
+    stats = torch.zeros(n_ctrl, 4, dtype=torch.int32, device=dev)
+    with _on(grad_h):
+        rc = lib.hode_dopri5_adjoint(C.byref(pb.cfg), pb.n_groups, pb.batch, _ptr(pb.dose_amt), _ptr(pb.dose_t),
+                                     pb.dose_t.stride(0), _ptr(pb.params), _ptr(pb.pset), pb.params.shape[0], _ptr(t_eval64),
+                                     t_eval64.numel(), _ptr(h), _ptr(grad_h), _ptr(gy0), _ptr(gp), _ptr(stats), _stream(grad_h))
+    lib.check(rc, "hode_dopri5_adjoint")
+    return gy0, gp, stats
 
 
 def decode_sse(lib, h, W, b, x, mask, n_norm, want_grads=True):

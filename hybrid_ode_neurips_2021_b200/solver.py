@@ -298,6 +298,32 @@ class _Dopri5Solve(torch.autograd.Function):
         return gy0, gp.reshape(-1), None, None, None, None, None
 
 
+class _Dopri5AdjointSolve(torch.autograd.Function):
+    """torchdiffeq's ``OdeintAdjointMethod`` with the adaptive solver: forward = the dopri5 solve without a tape, backward = ONE
+    launch integrating the augmented system backwards over every output interval with the dopri5 controller
+    (``hode_dopri5_adjoint``; 'seminorm' error control)."""
+
+    @staticmethod
+    def forward(ctx, y0, packed, pb, adj_pb, t_eval, holder):
+        lib = L.get_lib()
+        pb.params = packed.detach().reshape(pb.params_shape).contiguous()
+        adj_pb.params = pb.params
+        h, stats, _ = ops.dopri5_fwd(lib, pb, y0.detach(), t_eval, 0)
+        st = stats.cpu()
+        holder.append(st)
+        _raise_on_failure(st)
+        ctx.adj_pb, ctx.t_eval = adj_pb, t_eval
+        ctx.save_for_backward(h)
+        return h
+
+    @staticmethod
+    def backward(ctx, grad_h):
+        (h,) = ctx.saved_tensors
+        gy0, gp, stats = ops.dopri5_adjoint(L.get_lib(), ctx.adj_pb, ctx.t_eval, h, grad_h)
+        _raise_on_failure(stats.cpu())
+        return gy0, gp.reshape(-1), None, None, None, None
+
+
 def _raise_on_failure(st: torch.Tensor):
     status = st[:, 3]
     if bool((status == L.SOLVE_OK).all()):
@@ -342,8 +368,10 @@ def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=No
                    adjoint_atol=None, adjoint_method=None, adjoint_options=None, adjoint_params=None):
     """torchdiffeq's ``odeint_adjoint`` (the import the reference keeps commented out at ``model.py:9``): same forward
     result as :func:`odeint`, but the backward pass is the CONTINUOUS adjoint -- no tape, O(1) memory in the number of
-    solver steps.  Built for the fixed-grid methods (``euler`` / ``midpoint`` / ``rk4``); the adjoint solve uses the
-    forward method and options unless ``adjoint_method`` / ``adjoint_options`` say otherwise (torchdiffeq's defaults).
+    solver steps.  Fixed-grid methods (``euler`` / ``midpoint`` / ``rk4``) and ``dopri5`` (the reference's default method;
+    the adaptive adjoint solve needs ``adjoint_options={'norm': 'seminorm'}``, tolerances ``adjoint_rtol`` / ``adjoint_atol``
+    defaulting to the forward ones); the adjoint solve uses the forward method and options unless ``adjoint_method`` /
+    ``adjoint_options`` say otherwise (torchdiffeq's defaults).
     ``adjoint_params`` must be the vector field's own parameters (the default): gradients are produced for the packed
     parameter vector as a whole.  Gradients differ from :func:`odeint`'s discrete backprop by the method's
     discretisation error, exactly as they do in torchdiffeq."""
@@ -356,18 +384,22 @@ def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=No
     for m in (method, adjoint_method):
         if m not in L.METHODS:
             raise ValueError('Invalid method "{}". Must be one of {}'.format(m, "{" + ", ".join(L.METHODS) + "}"))
-    if method == "dopri5" or adjoint_method == "dopri5":
-        raise NotImplementedError(
-            "odeint_adjoint has fused kernels for the fixed-grid methods only; dopri5 trains through odeint's discrete "
-            "backprop over the tape of accepted steps")
+    if (method == "dopri5") != (adjoint_method == "dopri5"):
+        raise NotImplementedError("odeint_adjoint: the forward and the adjoint solve must both be fixed-grid or both dopri5")
     if adjoint_options is None:  # torchdiffeq: the forward options (minus a user norm) drive the adjoint solve too
         adjoint_options = {k: v for k, v in options.items() if k != "norm"} if options is not None else {}
     else:
         adjoint_options = dict(adjoint_options)
-        unused = {k: v for k, v in adjoint_options.items() if k not in (_FIXED_KEYS | _OUR_KEYS)}
+        known = (_FIXED_KEYS if adjoint_method != "dopri5" else _ADAPTIVE_KEYS) | _OUR_KEYS
+        unused = {k: v for k, v in adjoint_options.items() if k not in known}
         if unused:
             warnings.warn("{}: Unexpected arguments {}".format(_NAMES[adjoint_method], unused))
-    adjoint = {"method": adjoint_method, "options": adjoint_options}
+    if adjoint_method == "dopri5" and adjoint_options.get("norm") != "seminorm":
+        raise NotImplementedError(
+            "odeint_adjoint(method='dopri5') is built for adjoint_options={'norm': 'seminorm'} (error control by the state and "
+            "the state adjoint); torchdiffeq's default mixed norm additionally lets every parameter adjoint veto a step")
+    adjoint = {"method": adjoint_method, "options": adjoint_options,
+               "rtol": rtol if adjoint_rtol is None else adjoint_rtol, "atol": atol if adjoint_atol is None else adjoint_atol}
     return _odeint_impl([func], y0, t, rtol, atol, method, options, event_fn, adjoint=adjoint)
 
 
@@ -590,6 +622,23 @@ def _odeint_impl(funcs, y0, t, rtol, atol, method, options, event_fn, adjoint=No
             )
     t_dev, _ = _times_for(t, None, y0.device, False)
     holder = []
+    if adjoint is not None and need_grad:
+        aopt = adjoint["options"]
+        acfg = L.HodeCfg.from_buffer_copy(cfg)
+        acfg.rtol, acfg.atol = float(adjoint["rtol"]), float(adjoint["atol"])
+        acfg.flags |= L.FLAG_ADJ_SEMINORM
+        for key, attr in (("safety", "safety"), ("ifactor", "ifactor"), ("dfactor", "dfactor")):
+            if key in aopt:
+                setattr(acfg, attr, float(aopt[key]))
+        acfg.first_step = float(aopt["first_step"]) if aopt.get("first_step") is not None else -1.0
+        if "max_num_steps" in aopt:
+            acfg.max_num_steps = int(aopt["max_num_steps"])
+        if "controller" in aopt:
+            acfg.controller = L.CTRL_TRAJ if aopt["controller"] == "trajectory" else L.CTRL_BATCH
+        adj_pb = ops.Problem(acfg, n_groups, batch, dose_amt, dose_t, None, pset)
+        h = _Dopri5AdjointSolve.apply(y0, packed, pb, adj_pb, t_dev, holder)
+        _last_info = SolveInfo(holder[0] if holder else None)
+        return h
     h = _Dopri5Solve.apply(y0, packed, pb, t_dev, int(options.get("tape_capacity", 1024)), need_grad, holder)
     _last_info = SolveInfo(holder[0] if holder else None)
     return h

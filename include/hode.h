@@ -87,8 +87,10 @@ typedef struct hode_stats {
  * the device and reported loudly: NaN in the solution / gradients (dopri5: status HODE_SOLVE_NONFINITE).
  * HODE_FLAG_ABLATE: RocheODE(ablate=True), the ablation study's expert part (model.py:545-549):
  * dx = (ImmuneReact, -Disease theta_1, Dose2, -Immunity theta_2); the packed parameters gain theta_1, theta_2 at the END
- * (after ml_net's bias); the dose schedule is unused. */
-typedef enum hode_flags { HODE_FLAG_HILL2 = 1, HODE_FLAG_ABLATE = 2 } hode_flags;
+ * (after ml_net's bias); the dose schedule is unused.
+ * HODE_FLAG_ADJ_SEMINORM (hode_dopri5_adjoint): the adjoint solve is controlled by torchdiffeq's 'seminorm' (state and state
+ * adjoint; the parameter adjoints are integrated but take no part in the step-size decisions). */
+typedef enum hode_flags { HODE_FLAG_HILL2 = 1, HODE_FLAG_ABLATE = 2, HODE_FLAG_ADJ_SEMINORM = 4 } hode_flags;
 
 typedef struct hode_cfg {
     int32_t field;        /* hode_field */
@@ -188,6 +190,19 @@ int32_t hode_dopri5_bwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, co
                         const int32_t* param_set_of_group, int32_t n_param_sets, const double* t_eval, int32_t n_t,
                         const float* grad_h, const double* tape_t, const float* tape_y, int32_t tape_capacity,
                         const hode_stats* stats, float* grad_y0, float* grad_params, void* stream);
+
+/* Adaptive continuous adjoint: torchdiffeq odeint_adjoint(method='dopri5') -> OdeintAdjointMethod.backward (the import the
+ * reference keeps commented out at model.py:9; dopri5 is its default method, sim_config.py:50).  For i = n_t-1 .. 1 the
+ * augmented state (y = h[i], a, g_params) is integrated by the dopri5 controller from t[i] back to t[i-1] (negated time),
+ * interpolated to t[i-1] by the quartic dense output; then a += grad_h[i-1], y = h[i-1].  No tape.
+ * cfg: rtol / atol = the ADJOINT tolerances; controller BATCH (one controller per group, batch <= hode_dopri5_max_batch())
+ * or TRAJ; flags must contain HODE_FLAG_ADJ_SEMINORM.  h [n_t, n_traj, D]: the forward solution (hode_dopri5_fwd without a
+ * tape).  stats [n_ctrl]: accepted / rejected attempts summed over the intervals, status as in hode_dopri5_fwd. */
+int32_t hode_dopri5_adjoint(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,
+                            const float* dose_t, int64_t dose_t_stride, const float* params,
+                            const int32_t* param_set_of_group, int32_t n_param_sets, const double* t_eval, int32_t n_t,
+                            const float* h, const float* grad_h, float* grad_y0, float* grad_params, hode_stats* stats,
+                            void* stream);
 
 /* ---- decode + masked SSE: output_function (model.py:1097-1100, 1120) and the likelihood of
  * VariationalInference.loss (model.py:1179): loss = sum_{t,b,o} (x - (W h + b))^2 mask / n_norm.

@@ -188,7 +188,46 @@ void dopri5_bwd(const SolveArgs& a, bool eg) {
     }
 }
 
-enum Op { FF, FB, DF, DB, FA, FS };
+// adaptive continuous adjoint: 14 rows in memory, rolled stage loops (the device's only variant)
+template <class F>
+void dopri5_adj(const SolveArgs& a, bool eg) {
+    using RM = RowsMem<F::D, 14>;
+    for (int64_t g = 0; g < a.n_groups; ++g) {
+        auto sp = stage<F>(a, g);
+        std::vector<float> acc(F::P, 0.f);
+        auto one = [&](auto& cm, int64_t idx, int64_t ctrl, bool leader, float count, float* accp) {
+            std::vector<float> buf(RM::kFloatsPerThread);
+            RM R{buf.data(), RM::VEC};
+            if (eg) dopri5_adj_traj<F, true, true>(a, cm, sp.data(), dose(a, idx), R, idx, true, ctrl, leader, count, accp);
+            else dopri5_adj_traj<F, false, true>(a, cm, sp.data(), dose(a, idx), R, idx, true, ctrl, leader, count, accp);
+        };
+        if (a.per_traj) {
+            for (int64_t b = 0; b < a.batch; ++b) {
+                const int64_t idx = g * a.batch + b;
+                CommNone cm;
+                one(cm, idx, idx, true, (float)F::D, acc.data());
+            }
+        } else {
+            const int n = (int)a.batch;
+            std::barrier<> bar(n);
+            std::vector<float> buf(2 * n);
+            std::vector<std::vector<float>> accs(n, std::vector<float>(F::P, 0.f));
+            std::vector<std::thread> th;
+            for (int b = 0; b < n; ++b)
+                th.emplace_back([&, b]() {
+                    CommThreads cm{&bar, buf.data(), n, b};
+                    one(cm, g * a.batch + b, g, b == 0, (float)(a.batch * F::D), accs[b].data());
+                });
+            for (auto& t : th) t.join();
+            for (int b = 0; b < n; ++b)
+                for (int i = 0; i < F::P; ++i) acc[i] += accs[b][i];
+        }
+        const int set = a.pset ? a.pset[g] : 0;
+        for (int i = 0; i < F::P; ++i) a.grad_params[(int64_t)set * F::P + i] += acc[i];
+    }
+}
+
+enum Op { FF, FB, DF, DB, FA, FS, DA };
 template <class F>
 int run(Op op, const hode_cfg& cfg, const SolveArgs& a) {
     const bool eg = cfg.expert_grads != 0;
@@ -215,6 +254,7 @@ int run(Op op, const hode_cfg& cfg, const SolveArgs& a) {
             return 0;
         case DF: dopri5_fwd<F>(a); return 0;
         case DB: dopri5_bwd<F>(a, eg); return 0;
+        case DA: dopri5_adj<F>(a, eg); return 0;
     }
     return -1;
 }
@@ -332,6 +372,17 @@ int32_t hode_dopri5_bwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, co
     a.stats = const_cast<hode_stats*>(stats); a.grad_y0 = grad_y0; a.grad_params = grad_params;
     memset(grad_params, 0, sizeof(float) * pcount(cfg) * n_param_sets);
     return dispatch(DB, *cfg, a);
+}
+int32_t hode_dopri5_adjoint(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,
+                            const float* dose_t, int64_t dose_t_stride, const float* params, const int32_t* pset,
+                            int32_t n_param_sets, const double* t_eval, int32_t n_t, const float* h, const float* grad_h,
+                            float* grad_y0, float* grad_params, hode_stats* stats, void*) {
+    if (!(cfg->flags & HODE_FLAG_ADJ_SEMINORM)) return HODE_ERR_UNSUPPORTED;
+    SolveArgs a; fill(a, cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, pset);
+    a.n_param_sets = n_param_sets; a.t_eval_d = t_eval; a.n_t = n_t; a.h_out = const_cast<float*>(h); a.grad_h = grad_h;
+    a.stats = stats; a.grad_y0 = grad_y0; a.grad_params = grad_params;
+    memset(grad_params, 0, sizeof(float) * pcount(cfg) * n_param_sets);
+    return dispatch(DA, *cfg, a);
 }
 // ---- real-data fields (csrc/hode_real.cuh) --------------------------------------------------------------------------
 }  // extern "C"

@@ -13,7 +13,7 @@ import hybrid_ode_neurips_2021_b200 as H
 from oracle import fields as OF
 from oracle import odeint as OI
 
-from _util import EXPERT_NAMES, make_cohort, nan_pattern_equal, oracle_roche, relerr
+from _util import EXPERT_NAMES, check, make_cohort, nan_pattern_equal, oracle_roche, relerr
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -106,24 +106,52 @@ def smooth_cohort(B, D, seed):
     return y0, a
 
 
+def _cohort_with_margin(o, D, B, rtol, atol, margin=0.05):
+    """A smooth cohort on which every attempt of the ORACLE's solve keeps its error ratio at least `margin` away from the
+    accept threshold 1: the accept / reject sequence is then a stable property that the CUDA path must reproduce exactly
+    (north_star: "identical accepted-step sequences within tolerance").  Deterministic search over seeds on the CPU."""
+    t = torch.arange(0, 15.0)
+    for seed in range(10 + D, 60 + D):
+        y0, a = smooth_cohort(B, D, seed=seed)
+        o.set_action(a)
+        tr = OI.SolveTrace()
+        with torch.no_grad():
+            OI.odeint(o, y0, t, rtol=rtol, atol=atol, method="dopri5", options={"trace": tr})
+        if all(abs(r - 1.0) >= margin for (_, _, r, _) in tr.attempts):
+            return y0, a, seed
+    raise AssertionError("no cohort with a {} margin found".format(margin))
+
+
 @pytest.mark.parametrize("D", [4, 6, 8, 12])
 @pytest.mark.parametrize("rtol,atol", [(1e-3, 1e-4), (1e-5, 1e-6)])
 def test_dopri5_identical_step_sequence_on_smooth_problem(D, rtol, atol):
+    from hybrid_ode_neurips_2021_b200 import _lib as L, ops
+    from hybrid_ode_neurips_2021_b200.solver import pack_params
+
     B = 10
     o, m = build_pair(D)
-    y0, a = smooth_cohort(B, D, seed=10 + D)
+    if rtol >= 1e-3:
+        y0, a, _ = _cohort_with_margin(o, D, B, rtol, atol)
+    else:
+        y0, a = smooth_cohort(B, D, seed=10 + D)
     t = torch.arange(0, 15.0)
     W = torch.randn(15, B, D, generator=torch.Generator().manual_seed(2))
     ref, gref, out, gout, tr = run_both(o, m, y0, a, t, W, method="dopri5", rtol=rtol, atol=atol)
     info = H.last_solve_info()
-    borderline = any(abs(r - 1.0) < 0.02 for (_, _, r, _) in tr.attempts)
     n_ref, n_out = tr.accepted + tr.rejected, int(info.accepted[0] + info.rejected[0])
     if rtol >= 1e-3:
-        # exact accept/reject sequence equality is only a stable property at loose tolerances (BASELINE.md section 4:
-        # at 1e-5/1e-6 a 1-ulp perturbation of y0 already moves the oracle's own sequence)
-        if not borderline:
-            assert int(info.accepted[0]) == tr.accepted and int(info.rejected[0]) == tr.rejected
-            assert int(info.nfe[0]) == tr.nfe
+        # UNCONDITIONAL: same number of accepted and rejected attempts, same nfe ...
+        assert int(info.accepted[0]) == tr.accepted and int(info.rejected[0]) == tr.rejected
+        assert int(info.nfe[0]) == tr.nfe
+        # ... and the same (t0, dt) for every accepted step: the kernel's tape against the oracle's attempt trace
+        cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.DOPRI5, n_dose=1, rtol=rtol, atol=atol)
+        pb = ops.Problem(cfg, 1, B, m.dosage, m._dose_t_f32, pack_params(m, L.FIELD_ROCHE).detach()[None].contiguous(), None)
+        _, stats, tape = ops.dopri5_fwd(L.get_lib(), pb, y0.to(DEV), t.double().to(DEV), 256)
+        tape_t = tape[0][0, : int(stats[0, 0])].cpu()
+        acc = torch.tensor([[t0, dt] for (t0, dt, _, ok) in tr.attempts if ok], dtype=torch.float64)
+        assert tape_t.shape == acc.shape
+        check("dopri5 step sequence D={} (t0, dt) of {} accepted steps".format(D, acc.shape[0]),
+              float(((tape_t - acc).abs() / acc.abs().clamp_min(1e-3)).max()), 1e-4)
     else:
         assert abs(n_out - n_ref) <= max(2, 0.05 * n_ref), (n_out, n_ref)
         assert int(info.nfe[0]) == 2 + 6 * n_out
@@ -781,3 +809,47 @@ def test_decoder_loss_falls_back_to_the_separate_launches_where_no_fused_kernel_
     assert not xs.is_contiguous()
     again = dec.loss(y0.to(DEV), a.to(DEV), xs, mask.to(torch.uint8).to(DEV)).item()
     assert abs(again - base) <= 1e-6 * abs(base)
+
+
+@pytest.mark.parametrize("D,B,groups,ctrl", [(6, 12, 1, "batch"), (12, 10, 3, "batch"), (8, 40, 1, "trajectory"), (12, 70, 1, "batch")])
+def test_dopri5_continuous_adjoint_against_the_oracle(D, B, groups, ctrl):
+    """odeint_adjoint(method='dopri5', adjoint_options={'norm': 'seminorm'}): forward without a tape, backward = one launch of
+    the adaptive adjoint kernel, against the restatement of torchdiffeq's OdeintAdjointMethod (same norm, same tolerances)
+    group by group, and against the discrete backprop through the tape."""
+    rtol, atol = 1e-6, 1e-7
+    o, m = build_pair(D)
+    y0, a, _, _ = make_cohort(B * groups, D, seed=60 + D)
+    t = torch.arange(0, 8.0)
+    W = torch.randn(8, B * groups, D, generator=torch.Generator().manual_seed(5))
+    opts = {"n_groups": groups, "controller": ctrl}
+    m.zero_grad(); m.set_action(a.to(DEV))
+    zg = y0.clone().to(DEV).requires_grad_(True)
+    out = H.odeint_adjoint(m, zg, t.to(DEV), rtol=rtol, atol=atol, method="dopri5", options=opts,
+                           adjoint_options={"norm": "seminorm", "controller": ctrl})
+    (out * W.to(DEV)).sum().backward()
+    g_adj, gw_adj = zg.grad.clone(), m.ml_net[0].weight.grad.clone()
+    # discrete backprop through the accepted steps (the tape path)
+    m.zero_grad()
+    zd = y0.clone().to(DEV).requires_grad_(True)
+    out_d = H.odeint(m, zd, t.to(DEV), rtol=rtol, atol=atol, method="dopri5", options=opts)
+    (out_d * W.to(DEV)).sum().backward()
+    assert torch.equal(out, out_d)  # same forward kernel, with and without a tape
+    check("dopri5 adjoint vs tape D={} {} dL/dy0".format(D, ctrl), relerr(g_adj, zd.grad), 1e-3)
+    check("dopri5 adjoint vs tape D={} {} dL/dW".format(D, ctrl), relerr(gw_adj, m.ml_net[0].weight.grad), 1e-3)
+    # oracle, one odeint_adjoint call per controller group (first two groups / trajectories)
+    n_ref = 2 if (groups > 1 or ctrl == "trajectory") else 1
+    for g in range(n_ref):
+        sl = slice(g * B, (g + 1) * B) if ctrl == "batch" else slice(g, g + 1)
+        o.zero_grad(); o.set_action(a[:, sl])
+        z = y0[sl].clone().requires_grad_(True)
+        ref = OI.odeint_adjoint(o, z, t, rtol=rtol, atol=atol, method="dopri5", adjoint_options={"norm": "seminorm"})
+        (ref * W[:, sl]).sum().backward()
+        check("dopri5 adjoint vs oracle D={} {} group {} dL/dy0".format(D, ctrl, g), relerr(g_adj[sl], z.grad), 5e-4)
+    if groups == 1 and ctrl == "batch":
+        check("dopri5 adjoint vs oracle D={} dL/dW".format(D), relerr(gw_adj, o.ml_net[0].weight.grad), 1e-3)
+    # decoder drop-in with the adaptive adjoint
+    dec = H.RocheExpertDecoder(20, D, 1, 14, 1, method="dopri5", device=DEV, adjoint=True, adjoint_options={"norm": "seminorm"})
+    z2 = y0[:B].clone().to(DEV).requires_grad_(True)
+    x_hat, _ = dec(z2, a[:, :B].to(DEV))
+    x_hat.square().sum().backward()
+    assert bool(torch.isfinite(z2.grad).all()) and dec.ode.ml_net[0].weight.grad is not None

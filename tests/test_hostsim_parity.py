@@ -495,3 +495,60 @@ def test_generic_hill_exponents_nan_pattern_for_negative_states(lib):
     assert torch.equal(torch.isnan(h), torch.isnan(ref)) and bool(torch.isnan(h[1:, 1]).any()) and not bool(torch.isnan(h[:, [0, 2]]).any())
     ok = ~torch.isnan(ref)
     assert relerr(h[ok], ref[ok]) < 1e-5
+
+
+@pytest.fixture(scope="module")
+def lib_dadj():
+    subprocess.run(["make", "-C", HS_DIR], check=True, capture_output=True)
+    return L.HodeLib(HS, required=SYMS + ["hode_dopri5_adjoint"])
+
+
+@pytest.mark.parametrize("D", [4, 6, 12])
+@pytest.mark.parametrize("ctrl", ["batch", "trajectory"])
+def test_dopri5_continuous_adjoint_seminorm(lib_dadj, D, ctrl):
+    """hode_dopri5_adjoint (adaptive continuous adjoint, seminorm) against the restatement of torchdiffeq's
+    OdeintAdjointMethod with method='dopri5', adjoint_options={'norm': 'seminorm'}: d/dy0 and all parameter gradients."""
+    lib = lib_dadj
+    B = 4 if ctrl == "batch" else 1
+    rtol, atol = 1e-6, 1e-7
+    o = oracle_roche(D, 9, True)
+    y0, a, _, _ = make_cohort(B, D, seed=50 + D)
+    o.set_action(a)
+    t = torch.arange(0, 6.0)
+    W = torch.randn(6, B, D, generator=torch.Generator().manual_seed(3))
+    z = y0.clone().requires_grad_(True)
+    ref = OI.odeint_adjoint(o, z, t, rtol=rtol, atol=atol, method="dopri5", adjoint_options={"norm": "seminorm"})
+    (ref * W).sum().backward()
+    gref = grads_vec(o, False)
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.DOPRI5, n_dose=1, rtol=rtol, atol=atol, adj_seminorm=True,
+                       controller=L.CTRL_TRAJ if ctrl == "trajectory" else L.CTRL_BATCH)
+    pb = problem(o, cfg, B)
+    h, stats, _ = ops.dopri5_fwd(lib, pb, y0, t.double(), 0)
+    assert relerr(h, ref) < 1e-4  # two forward solves at rtol 1e-6 with their own step sequences
+    gy0, gp, st = ops.dopri5_adjoint(lib, pb, t.double(), h, W)
+    assert int(st[:, 3].max()) == 0 and int(st[:, 0].min()) >= 5
+    # two adaptive solves with their own accept / reject sequences at rtol 1e-6: the adjoint itself is only accurate to the
+    # tolerance, so is the agreement
+    assert relerr(gy0, z.grad) < 2e-4
+    ok = ~torch.isnan(gref)
+    assert relerr(gp[0][ok][2:], gref[ok][2:]) < 5e-4
+    # and the continuous adjoint is close to the discrete backprop through the forward steps
+    cfg2 = ops.make_cfg(L.FIELD_ROCHE, D, L.DOPRI5, n_dose=1, rtol=rtol, atol=atol,
+                        controller=L.CTRL_TRAJ if ctrl == "trajectory" else L.CTRL_BATCH)
+    pb2 = problem(o, cfg2, B)
+    _, stats2, tape = ops.dopri5_fwd(lib, pb2, y0, t.double(), 512)
+    gy0_d, _ = ops.dopri5_bwd(lib, pb2, t.double(), W, tape, stats2)
+    assert relerr(gy0, gy0_d) < 5e-4
+
+
+def test_dopri5_adjoint_requires_the_seminorm_flag(lib_dadj):
+    D, B = 6, 2
+    o = oracle_roche(D, 1, False)
+    y0, a, _, _ = make_cohort(B, D, seed=1)
+    o.set_action(a)
+    t = torch.arange(0, 3.0)
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.DOPRI5, n_dose=1, rtol=1e-5, atol=1e-6)
+    pb = problem(o, cfg, B)
+    h, _, _ = ops.dopri5_fwd(lib_dadj, pb, y0, t.double(), 0)
+    with pytest.raises(NotImplementedError):
+        ops.dopri5_adjoint(lib_dadj, pb, t.double(), h, torch.ones_like(h))
