@@ -559,7 +559,7 @@ def run_ours(args):
         hbm_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s"
         bwd_flops = B * N_STEPS * FLOPS_BWD_STEP
         fwd_flops = B * N_STEPS * FLOPS_FWD_STEP
-        traffic, traffic_src = ncu_traffic("r01_fixed_bwd_kernel.txt", B)
+        traffic, traffic_src = ncu_traffic("r02_fixed_bwd_kernel.txt", B)
         roof = {
             "bound": "fp32_fma", "kernel": "fixed_bwd_kernel<Roche<8>, RK4_38> (reverse sweep; largest share of the step)",
             "achieved": bwd_flops / (t_bwd * 1e-3) / 1e12, "peak": fma_peak, "unit": "TFLOP/s",
@@ -723,6 +723,25 @@ def dopri5_extras(lib, dev, fma_peak):
                                   "bwd": {"kernel": "dopri5_bwd_kernel", "achieved": bwd_tf, "frac": bwd_tf / fma_peak,
                                           "launch_ms": t_b, "flops_per_accepted_step": 3 * (fl_att + fl_acc)},
                                   "frac": min(fwd_tf, bwd_tf) / fma_peak}}
+        # tape-free alternative: forward without a tape + the adaptive continuous adjoint (odeint_adjoint, 'seminorm'), on the
+        # first 8 192 odeint calls (one CTA per call: no lane-segment variant of this kernel yet)
+        try:
+            ga = min(groups, 8192)
+            acfg = ops.make_cfg(L.FIELD_ROCHE, Dd, L.DOPRI5, n_dose=1, expert_grads=False, hill2=True, rtol=1e-7, atol=1e-8,
+                                adj_seminorm=True)
+            apb = ops.Problem(acfg, ga, batch, m.dosage[:ga * batch], m._dose_t_f32[:ga * batch], pb.params, None)
+            t_f0, (h0, st0, _) = ev(lambda: ops.dopri5_fwd(lib, apb, y0[:ga * batch], tt, 0))
+            gh0 = gh[:, :ga * batch].contiguous()
+            t_a, (_, _, sta) = ev(lambda: ops.dopri5_adjoint(lib, apb, tt, h0, gh0))
+            sta = sta.cpu()
+            out[name]["adjoint_path"] = {
+                "odeint_calls": ga, "fwd_no_tape_ms": t_f0, "adjoint_ms": t_a, "status_ok": bool(int(sta[:, 3].max()) == 0),
+                "adjoint_accepted_per_call": float(sta[:, 0].float().mean()), "adjoint_rejected_per_call": float(sta[:, 1].float().mean()),
+                "value": int((st0.cpu()[:, 0] + st0.cpu()[:, 1]).sum()) * batch / ((t_f0 + t_a) * 1e-3), "unit": UNIT,
+                "note": "odeint_adjoint(method='dopri5', adjoint_options={'norm': 'seminorm'}): no tape is allocated"}
+            del h0, gh0
+        except Exception as e:
+            out[name]["adjoint_path"] = {"error": repr(e)}
         del h, tape, gh, y0, a
         torch.cuda.empty_cache()
     return out
