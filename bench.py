@@ -606,6 +606,8 @@ def run_ours(args):
                     if name in oc and "roofline" in oc[name]:
                         extra[key] = oc[name]["roofline"]
                 extra["other_configs"]["C4_ensemble_members"] = ensemble_extra(dev)
+                torch.cuda.empty_cache()
+                extra["other_configs"].update(c5_extras(dev, fma_peak))
             except Exception as e:  # secondary figures must never take the headline down
                 extra.setdefault("other_configs", {})["error"] = repr(e)
 
@@ -760,16 +762,15 @@ def ensemble_extra(dev):
     a = torch.zeros(T, Bm, 1, device=dev)
     a[torch.randint(0, T_MAX, (Bm,), device=dev, generator=g), torch.arange(Bm, device=dev), 0] = \
         torch.rand(Bm, device=dev, generator=g) * 10 + 1e-3
-    for f in fs:
-        f.set_action(a)
+    ens = H.EnsembleParams(fs)  # all members' parameters as one [M, P] leaf: one gradient tensor, no per-member packing
     tt = torch.arange(0, T_MAX + 1, 1, device=dev, dtype=torch.float32)
     W = torch.randn(T, M * Bm, Dd, device=dev, generator=g)
 
     def step():
-        for f in fs:
-            f.zero_grad(set_to_none=True)
+        ens.flat.grad = None
+        ens.set_action(a)
         z = y0.detach().requires_grad_(True)
-        h = H.odeint_ensemble(fs, z, tt, method="rk4", options={"step_size": STEP, "expert_grads": False})
+        h = H.odeint_ensemble(ens, z, tt, method="rk4", options={"step_size": STEP, "expert_grads": False})
         (h * W).sum().backward()
 
     for _ in range(2):
@@ -782,8 +783,84 @@ def ensemble_extra(dev):
     e_.record(); torch.cuda.synchronize()
     ms = s_.elapsed_time(e_) / 3
     return {"value": M * Bm * N_STEPS / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "members": M, "patients_per_member": Bm,
-            "latent_dim": Dd, "solver": "rk4(3/8) h=1/16", "note": "odeint_ensemble fwd + reverse sweep through autograd, one "
-            "parameter set per member (shared-memory staging instead of the constant bank)"}
+            "latent_dim": Dd, "solver": "rk4(3/8) h=1/16", "note": "set_action + odeint_ensemble(EnsembleParams) fwd + reverse sweep "
+            "through autograd, one parameter set per member (shared-memory staging instead of the constant bank), all "
+            "members' gradients in one [M, P] tensor"}
+
+
+def c5_extras(dev, fma_peak):
+    """C5 (BASELINE configs[4]): the residual variant's vector field (run_simulation_residual.py trains the NeuralODE field)
+    and the real-data decoder (run_real.py inputs: 48 hourly steps, 24 observed variables, 11 static covariates, latent 20)
+    on a synthetic ICU-shaped cohort, forward + backward through the public API."""
+    import hybrid_ode_neurips_2021_b200 as H
+
+    def timed(fwd, n=3):
+        for _ in range(2):
+            fwd().backward()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        tf = tb = 0.0
+        for _ in range(n):
+            torch.cuda.synchronize()
+            ev[0].record(); loss = fwd(); ev[1].record(); loss.backward(); ev[2].record()
+            torch.cuda.synchronize()
+            tf += ev[0].elapsed_time(ev[1]) / n; tb += ev[1].elapsed_time(ev[2]) / n
+        return tf, tb
+
+    out = {}
+    g = torch.Generator(device=dev).manual_seed(11)
+    # --- NeuralODE field (Linear(D+1, 10D) -> Tanh -> Linear(10D, D) -> Tanh), rk4 on the headline grid ---------------------------
+    Dn, Bn = 6, 131072
+    torch.manual_seed(666)
+    f = H.NeuralODE(Dn, 1, T_MAX, 1, device=dev)
+    a = torch.zeros(T, Bn, 1, device=dev)
+    a[torch.randint(0, T_MAX, (Bn,), device=dev, generator=g), torch.arange(Bn, device=dev), 0] = \
+        torch.rand(Bn, device=dev, generator=g) * 10 + 1e-3
+    f.set_action(a)
+    y0 = (torch.rand(Bn, Dn, device=dev, generator=g) * 0.5).requires_grad_(True)
+    tt = torch.arange(0, T_MAX + 1, 1, device=dev, dtype=torch.float32)
+    W = torch.randn(T, Bn, Dn, device=dev, generator=g)
+
+    def fwd_neural():
+        f.zero_grad(set_to_none=True); y0.grad = None
+        return (H.odeint(f, y0, tt, method="rk4", options={"step_size": STEP}) * W).sum()
+
+    tf, tb = timed(fwd_neural)
+    ff = 2 * (Dn + 1) * 10 * Dn + 10 * Dn + 2 * 10 * Dn * Dn + Dn  # two mat-vecs (FMA = 2) + one flop per tanh
+    step_flops = 4 * ff + 18 * Dn
+    out["C5_residual_neuralode_dim6"] = {
+        "value": Bn * N_STEPS / ((tf + tb) * 1e-3), "unit": UNIT, "fwd_ms": tf, "bwd_ms": tb, "patients": Bn, "latent_dim": Dn,
+        "solver": "rk4(3/8) h=1/16", "roofline": {
+            "bound": "fp32_fma", "peak": fma_peak, "unit": "TFLOP/s", "flops_per_traj_step_fwd": step_flops,
+            "fwd": {"achieved": Bn * N_STEPS * step_flops / (tf * 1e-3) / 1e12,
+                    "frac": Bn * N_STEPS * step_flops / (tf * 1e-3) / 1e12 / fma_peak},
+            "bwd": {"achieved": Bn * N_STEPS * 3 * step_flops / (tb * 1e-3) / 1e12,
+                    "frac": Bn * N_STEPS * 3 * step_flops / (tb * 1e-3) / 1e12 / fma_peak}},
+        "note": "odeint(NeuralODE) + autograd backward (reverse sweep with hidden-unit-owned weight gradients); times include "
+                "the host-side op overhead"}
+    del f, a, y0, W
+    # --- DecoderReal (hybrid: RocheODEReal = learned expert nets + GRU-ODE latent block), midpoint, perturb=True -------------------
+    Tr, obs, Hd, t0, Z, Br = 48, 24, 43, 24, 20, 65536
+    torch.manual_seed(666)
+    dec = H.DecoderReal(obs, Z, 1, 11, Hd, Tr, 1.0, t0=t0, method="midpoint", ode_step_size=1.0, ode_type="hybrid", device=dev)
+    ar = (torch.rand(Tr, Br, 1, device=dev, generator=g) < 0.2).float() * torch.rand(Tr, Br, 1, device=dev, generator=g)
+    sr = torch.randn(Tr, Br, 11, device=dev, generator=g)
+    xr = torch.randn(Tr, Br, obs, device=dev, generator=g)
+    mr = (torch.rand(Tr, Br, obs, device=dev, generator=g) < 0.5).float()
+    z0 = (torch.randn(Br, Z, device=dev, generator=g) * 0.1).requires_grad_(True)
+
+    def fwd_real():
+        dec.zero_grad(set_to_none=True); z0.grad = None
+        x_hat, _ = dec(z0, ar, sr)
+        return torch.sum((xr[t0:] - x_hat) ** 2 * mr[t0:]) / Br  # model.py:1247
+
+    tf, tb = timed(fwd_real)
+    n_steps = dec.t.numel() - 1
+    out["C5_icu_decoder_real_hybrid"] = {
+        "value": Br * n_steps / ((tf + tb) * 1e-3), "unit": UNIT, "fwd_ms": tf, "bwd_ms": tb, "patients": Br,
+        "patients_per_s": Br / ((tf + tb) * 1e-3), "latent_dim": Z, "hidden_dim": Hd, "obs_dim": obs, "t_max": Tr, "t0": t0,
+        "solver": "midpoint h=1 (perturb=True), {} steps".format(n_steps),
+        "note": "DecoderReal.forward (set_action_static + solve) + Linear-ELU-Linear read-out and masked SSE in ATen + backward"}
+    return out
 
 
 def dopri5_cpu_baselines():

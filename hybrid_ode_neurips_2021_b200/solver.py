@@ -26,7 +26,8 @@ import torch
 from . import _lib as L
 from . import ops
 
-__all__ = ["odeint", "odeint_adjoint", "odeint_ensemble", "odeint_sse", "SolveInfo", "last_solve_info", "fixed_grid_points"]
+__all__ = ["odeint", "odeint_adjoint", "odeint_ensemble", "odeint_sse", "EnsembleParams", "SolveInfo", "last_solve_info",
+           "fixed_grid_points"]
 
 EXPERT_NAMES = (
     "HillCure", "HillPatho", "ec50_patho", "emax_patho", "k_dexa", "k_discure_immunereact", "k_discure_immunity",
@@ -93,19 +94,105 @@ def field_kind(func):
     )
 
 
-def pack_params(func, kind) -> torch.Tensor:
-    """Differentiable packed parameter vector, layout of include/hode.h."""
+def packed_order(func, kind):
+    """The vector field's parameters in the order of the packed layout of include/hode.h."""
     if kind == L.FIELD_ROCHE:
-        parts = [getattr(func, n).reshape(1) for n in EXPERT_NAMES]
+        parts = [getattr(func, n) for n in EXPERT_NAMES]
         if int(func.latent_dim) > 4:
             lin = func.ml_net[0]
-            parts += [lin.weight.reshape(-1), lin.bias.reshape(-1)]
+            parts += [lin.weight, lin.bias]
         if getattr(func, "ablate", False):  # the ablation field's two scalars go last (include/hode.h)
-            parts += [func.theta_1.reshape(1), func.theta_2.reshape(1)]
+            parts += [func.theta_1, func.theta_2]
     else:
         l1, l2 = func.ml_net[0], func.ml_net[2]
-        parts = [func.kel.reshape(1), l1.weight.reshape(-1), l1.bias.reshape(-1), l2.weight.reshape(-1), l2.bias.reshape(-1)]
-    return torch.cat(parts).to(torch.float32)
+        parts = [func.kel, l1.weight, l1.bias, l2.weight, l2.bias]
+    return parts
+
+
+def pack_params(func, kind) -> torch.Tensor:
+    """Differentiable packed parameter vector, layout of include/hode.h."""
+    return torch.cat([p.reshape(-1) for p in packed_order(func, kind)]).to(torch.float32)
+
+
+class EnsembleParams:
+    """The parameters of ``M`` ensemble members / restarts as ONE ``[M, P]`` leaf tensor in the packed layout of
+    include/hode.h (BASELINE config 4: ``run_simulation_ensemble.py:98-147`` trains the members one after the other).
+
+    Every member's ``nn.Parameter`` is re-homed as a view of its row of ``flat`` (values preserved, ``state_dict`` keys
+    unchanged), so ``odeint_ensemble(ens, ...)`` hands ``flat`` to the kernels as it is and autograd sees ONE leaf:
+    the gradients of all members arrive in ``flat.grad`` straight from the backward kernel's ``grad_params[M, P]``.
+    Without it a step packs ``M`` x 15 tensors and routes ``M`` x 15 gradient views through autograd -- at 64 members that
+    host work is 6 x the kernels' time.  Train with an optimizer over ``[ens.flat]`` (element-wise optimizers such as
+    Adam / SGD are unchanged by the flattening); ``ens.member_grad(m)`` maps a row of ``flat.grad`` back to names."""
+
+    def __init__(self, funcs):
+        funcs = list(funcs)
+        if len(funcs) == 0:
+            raise ValueError("EnsembleParams needs at least one member")
+        kind = field_kind(funcs[0])
+        if real_kind_of(funcs[0]) is not None:
+            raise NotImplementedError("odeint_ensemble is built for the simulation fields only")
+        self.funcs, self.kind = funcs, kind
+        orders = [packed_order(f, kind) for f in funcs]
+        sizes = [p.numel() for p in orders[0]]
+        for f, o in zip(funcs, orders):
+            if field_kind(f) != kind or [p.numel() for p in o] != sizes:
+                raise ValueError("ensemble members must be vector fields of the same class and latent_dim")
+        dev = orders[0][0].device
+        flat = torch.empty(len(funcs), sum(sizes), device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            for m, o in enumerate(orders):
+                off = 0
+                for p in o:
+                    n = p.numel()
+                    flat[m, off:off + n] = p.detach().reshape(-1).to(torch.float32)
+                    p.data = flat[m, off:off + n].view(p.shape)  # the member keeps reading / loading its own tensors
+                    off += n
+        self.flat = torch.nn.Parameter(flat)
+        self._sizes = sizes
+        self._dose = None
+        self._hill = None
+
+    def __len__(self):
+        return len(self.funcs)
+
+    def parameters(self):
+        return [self.flat]
+
+    def set_action(self, action):
+        """The same dose schedule for every member (the ensemble runs on one cohort): one ``set_action`` call."""
+        f0 = self.funcs[0]
+        f0.set_action(action)
+        for f in self.funcs[1:]:
+            f.dosage, f.times, f._dose_t_f32 = f0.dosage, f0.times, getattr(f0, "_dose_t_f32", None)
+        self._dose = None
+
+    def hill_exponents_are_two(self):
+        """:func:`hill_exponents_are_two` for all members at once, cached per version of ``flat`` (one host read per
+        optimizer step that touches the tensor; the kernels verify the flag on the device either way)."""
+        if self.kind != L.FIELD_ROCHE:
+            return False
+        ver = self.flat._version
+        if self._hill is None or self._hill[0] != ver:
+            with torch.no_grad():
+                self._hill = (ver, bool((self.flat[:, :2] == 2.0).all().item()))
+        return self._hill[1]
+
+    def member_grad(self, m):
+        """``{position in the packed layout: gradient view}`` of member ``m`` after ``backward`` (views of ``flat.grad``)."""
+        if self.flat.grad is None:
+            return None
+        out, off = [], 0
+        for p, n in zip(packed_order(self.funcs[m], self.kind), self._sizes):
+            out.append(self.flat.grad[m, off:off + n].view(p.shape))
+            off += n
+        return out
+
+
+def real_kind_of(func):
+    from .real import real_field_kind
+
+    return real_field_kind(func)
 
 
 _hill_cache = {}
@@ -409,9 +496,12 @@ def odeint_ensemble(funcs, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=
     ``run_simulation.py:95``, ``Fig3.sh:12-50``).
 
     ``funcs``: ``M`` vector fields of the same class and ``latent_dim``, each after its own ``set_action`` on ``B``
-    patients.  ``y0``: ``[M * B, D]``, member-major.  Returns ``[len(t), M * B, D]``; gradients flow to every member's
+    patients -- or an :class:`EnsembleParams` over them (all members' parameters as one ``[M, P]`` leaf: no per-member
+    packing, one gradient tensor; the path to use beyond a handful of members).  ``y0``: ``[M * B, D]``, member-major.  Returns ``[len(t), M * B, D]``; gradients flow to every member's
     parameters.  Each member is its own controller group (``options={'n_groups': g}`` splits a member into ``g`` groups).
     """
+    if isinstance(funcs, EnsembleParams):
+        return _odeint_impl(funcs, y0, t, rtol, atol, method, options, None)
     funcs = list(funcs)
     if len(funcs) == 0:
         raise ValueError("odeint_ensemble needs at least one member")
@@ -484,14 +574,18 @@ def _odeint_real(func, kind, y0, t, method, options):
 
 def _setup(funcs, y0, t, rtol, atol, method, options, event_fn):
     """Argument checking shared by every entry point for the simulation fields; returns the launch description."""
+    ens = funcs if isinstance(funcs, EnsembleParams) else None
+    if ens is not None:
+        funcs = ens.funcs
     func = funcs[0]
     M = len(funcs)
     if event_fn is not None:
         raise NotImplementedError("event_fn is not used by the reference and has no fused kernel")
     kind = field_kind(func)
-    for f in funcs[1:]:
-        if field_kind(f) != kind or int(f.latent_dim) != int(func.latent_dim):
-            raise ValueError("ensemble members must be vector fields of the same class and latent_dim")
+    if ens is None:
+        for f in funcs[1:]:
+            if field_kind(f) != kind or int(f.latent_dim) != int(func.latent_dim):
+                raise ValueError("ensemble members must be vector fields of the same class and latent_dim")
     if not isinstance(y0, torch.Tensor):
         raise NotImplementedError("tuple states are not used by the reference and have no fused kernel")
     if not y0.is_cuda:
@@ -524,21 +618,27 @@ def _setup(funcs, y0, t, rtol, atol, method, options, event_fn):
     if groups_per_member < 1 or (B // M) % groups_per_member != 0:
         raise ValueError("n_groups must divide the batch")
     batch = B // n_groups
+    dose_key = None if ens is None else tuple((id(f.dosage), id(f.times)) for f in funcs)
     if M == 1:
         dose_amt, dose_t = _dose_tensors(func, B, y0.device)
+    elif ens is not None and ens._dose is not None and ens._dose[0] == dose_key and ens._dose[1].shape[0] == B:
+        _, dose_amt, dose_t = ens._dose  # the members' schedules have not been re-assigned since the last call
     else:
         parts = [_dose_tensors(f, B // M, y0.device) for f in funcs]
         if len({p[1].shape[1:] for p in parts}) != 1:
             raise RuntimeError("ensemble members must have the same number of doses per patient")
         dose_amt = torch.cat([p[0] for p in parts]).contiguous()
         dose_t = torch.cat([p[1] for p in parts]).contiguous()
+        if ens is not None:
+            ens._dose = (dose_key, dose_amt, dose_t)
     n_dose = dose_t.shape[1] if dose_t.dim() == 2 else 0
 
     ctrl_name = options.get("controller", "batch")
     if ctrl_name not in ("batch", "trajectory"):
         raise ValueError("controller must be 'batch' or 'trajectory'")
     need_grad = torch.is_grad_enabled() and (
-        y0.requires_grad or any(p.requires_grad for f in funcs for p in f.parameters())
+        y0.requires_grad or (ens.flat.requires_grad if ens is not None else
+                             any(p.requires_grad for f in funcs for p in f.parameters()))
     )
     ablate = kind == L.FIELD_ROCHE and bool(getattr(func, "ablate", False))
     if kind == L.FIELD_ROCHE and any(bool(getattr(f, "ablate", False)) != ablate for f in funcs):
@@ -553,14 +653,14 @@ def _setup(funcs, y0, t, rtol, atol, method, options, event_fn):
         first_step=options.get("first_step", None), max_num_steps=int(options.get("max_num_steps", 2 ** 31 - 1)),
         attempt_cap=int(options.get("attempt_cap", ops.ATTEMPT_CAP_DEFAULT)),
         hill2=(kind == L.FIELD_ROCHE and bool(options.get("hill2_kernels", True))
-               and all(hill_exponents_are_two(f) for f in funcs)),
+               and (ens.hill_exponents_are_two() if ens is not None else all(hill_exponents_are_two(f) for f in funcs))),
         ablate=ablate,
     )
     if M == 1:
         packed = pack_params(func, kind)
         pset = None
     else:
-        packed = torch.stack([pack_params(f, kind) for f in funcs]).reshape(-1)
+        packed = ens.flat.reshape(-1) if ens is not None else torch.stack([pack_params(f, kind) for f in funcs]).reshape(-1)
         pset = torch.arange(M, dtype=torch.int32, device=y0.device).repeat_interleave(groups_per_member).contiguous()
     pb = ops.Problem(cfg, n_groups, batch, dose_amt, dose_t, None, pset)
     pb.params_shape = (M, packed.numel() // M)
@@ -570,7 +670,7 @@ def _setup(funcs, y0, t, rtol, atol, method, options, event_fn):
 
 def _odeint_impl(funcs, y0, t, rtol, atol, method, options, event_fn, adjoint=None):
     global _last_info
-    func = funcs[0]
+    func = funcs.funcs[0] if isinstance(funcs, EnsembleParams) else funcs[0]
     M = len(funcs)
     from .real import real_field_kind
 

@@ -51,6 +51,34 @@ def test_cfg_struct_layout_and_param_counts():
     assert lib.hode_supported(ctypes.byref(cfg)) == 0
 
 
+def test_ensemble_params_rehomes_members_on_one_flat_leaf():
+    torch.manual_seed(3)
+    for make, kind, D in ((H.RocheODE, L.FIELD_ROCHE, 8), (H.NeuralODE, L.FIELD_NEURAL, 6)):
+        members = [make(D, 1, 14, 1, device="cpu") for _ in range(3)]
+        packed = torch.stack([solver.pack_params(m, kind) for m in members]).detach().clone()
+        sds = [{k: v.clone() for k, v in m.state_dict().items()} for m in members]
+        ens = H.EnsembleParams(members)
+        assert len(ens) == 3 and ens.parameters()[0] is ens.flat and ens.flat.requires_grad
+        assert torch.equal(ens.flat.detach(), packed)  # rows are the packed layout of include/hode.h
+        for m, sd in zip(members, sds):
+            assert list(m.state_dict().keys()) == list(sd.keys())
+            assert all(torch.equal(v, sd[k]) for k, v in m.state_dict().items())
+            assert torch.equal(solver.pack_params(m, kind).detach(), packed[members.index(m)])
+        with torch.no_grad():
+            ens.flat.mul_(2.0)  # an optimizer step on the flat tensor is seen by the members
+        assert torch.equal(solver.pack_params(members[1], kind).detach(), 2.0 * packed[1])
+        members[0].load_state_dict(sds[0])  # and a member's checkpoint load writes through
+        assert torch.equal(ens.flat[0].detach(), packed[0])
+    assert ens.hill_exponents_are_two() is False  # NeuralODE members: no Hill flag
+    r = H.EnsembleParams([H.RocheODE(6, 1, 14, 1, device="cpu") for _ in range(2)])
+    assert r.hill_exponents_are_two() is True
+    with torch.no_grad():
+        r.flat[1, 0] = 1.5
+    assert r.hill_exponents_are_two() is False  # cached per version of the flat tensor
+    with pytest.raises(ValueError):
+        H.EnsembleParams([H.RocheODE(6, 1, 14, 1, device="cpu"), H.RocheODE(8, 1, 14, 1, device="cpu")])
+
+
 def test_argument_errors_are_reported_not_crashed():
     lib = L.get_lib()
     cfg = ops.make_cfg(L.FIELD_ROCHE, 6, L.RK4_38)
@@ -106,15 +134,17 @@ def test_fixed_grid_points_equal_the_oracle():
 
 
 def test_adjoint_surface_and_reversed_time_grids():
-    """odeint_adjoint: torchdiffeq's signature, fixed-grid methods only, no CPU fallback; the adjoint's per-interval grids
+    """odeint_adjoint: torchdiffeq's signature, dopri5 with the seminorm only, no CPU fallback; the adjoint's per-interval grids
     are torchdiffeq's fixed grid of the negated interval (what the oracle's reverse-time odeint constructs)."""
     m = H.RocheODE(6, 1, 14, 1, device="cpu")
     a = torch.zeros(15, 2, 1)
     a[3, :, 0] = 1.0
     m.set_action(a)
     t = torch.arange(0, 15.0)
-    with pytest.raises(NotImplementedError, match="fixed-grid"):
-        H.odeint_adjoint(m, torch.zeros(2, 6), t)  # default method dopri5
+    with pytest.raises(NotImplementedError, match="seminorm"):
+        H.odeint_adjoint(m, torch.zeros(2, 6), t)  # default method dopri5 with torchdiffeq's default mixed norm: not built
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        H.odeint_adjoint(m, torch.zeros(2, 6), t, adjoint_options={"norm": "seminorm"})
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         H.odeint_adjoint(m, torch.zeros(2, 6), t, method="rk4", options={"step_size": 0.25})
     with pytest.raises(ValueError, match="Invalid method"):

@@ -326,6 +326,41 @@ def test_ensemble_members_with_own_weights_in_one_launch(method, kw):
         H.odeint_ensemble(members, zg[:-1], t, method=method, **kw)
 
 
+def test_ensemble_params_flat_leaf_equals_member_lists():
+    """EnsembleParams: all members' parameters as one [M, P] leaf -- same values, same gradients (now rows of flat.grad),
+    members still read / load their own tensors, and an in-place optimizer step on the flat tensor reaches the members."""
+    D, B, M = 8, 12, 3
+    members = [build_pair(D, seed=40 + i)[1] for i in range(M)]
+    y0, a = smooth_cohort(B * M, D, seed=19)
+    t = torch.arange(0, 15.0).to(DEV)
+    W = torch.randn(15, B * M, D, generator=torch.Generator().manual_seed(5)).to(DEV)
+    for i, m in enumerate(members):
+        m.zero_grad(); m.set_action(a[:, i * B:(i + 1) * B].to(DEV))
+    kw = dict(method="rk4", options={"step_size": 0.125})
+    zg = y0.clone().to(DEV).requires_grad_(True)
+    (H.odeint_ensemble(members, zg, t, **kw) * W).sum().backward()
+    ref_w = [m.ml_net[0].weight.grad.clone() for m in members]
+    ref_k = [m.k_dexa.grad.clone() for m in members]
+    before = [{k: v.clone() for k, v in m.state_dict().items()} for m in members]
+    ens = H.EnsembleParams(members)
+    for m, sd in zip(members, before):  # re-homing keeps every value and key
+        assert all(torch.equal(v, sd[k]) for k, v in m.state_dict().items())
+    z2 = y0.clone().to(DEV).requires_grad_(True)
+    out = H.odeint_ensemble(ens, z2, t, **kw)
+    (out * W).sum().backward()
+    assert ens.flat.grad.shape == (M, ens.flat.shape[1])
+    assert torch.equal(z2.grad, zg.grad)  # same kernels, same parameter bytes
+    for i in range(M):
+        g = ens.member_grad(i)
+        assert relerr(g[13], ref_w[i]) < 1e-6  # 13 expert scalars first, then ml_net weight (include/hode.h)
+        assert abs(g[4].item() - ref_k[i].item()) <= 1e-5 * max(1.0, abs(ref_k[i].item()))  # k_dexa is expert #4
+    with torch.no_grad():
+        ens.flat.add_(ens.flat.grad, alpha=-1e-3)
+    assert torch.equal(members[1].ml_net[0].weight.reshape(-1), ens.flat[1, 13:13 + (D - 4) * D])
+    members[2].load_state_dict(before[2])  # loading a member's checkpoint writes through to the flat tensor
+    assert torch.equal(ens.flat[2, 13:13 + (D - 4) * D], before[2]["ml_net.0.weight"].reshape(-1))
+
+
 def test_multi_warp_group_matches_oracle():
     D, B = 6, 200  # 7 warps in one CTA: exercises the shared-memory stage of the group reduction
     o, m = build_pair(D)
