@@ -794,17 +794,19 @@ def c5_extras(dev, fma_peak):
     on a synthetic ICU-shaped cohort, forward + backward through the public API."""
     import hybrid_ode_neurips_2021_b200 as H
 
-    def timed(fwd, n=3):
-        for _ in range(2):
+    def timed(fwd, n=5):
+        """Median over n iterations of the forward and backward device times (a caching-allocator refill in one iteration
+        must not masquerade as kernel time)."""
+        for _ in range(3):
             fwd().backward()
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        tf = tb = 0.0
+        tf, tb = [], []
         for _ in range(n):
             torch.cuda.synchronize()
             ev[0].record(); loss = fwd(); ev[1].record(); loss.backward(); ev[2].record()
             torch.cuda.synchronize()
-            tf += ev[0].elapsed_time(ev[1]) / n; tb += ev[1].elapsed_time(ev[2]) / n
-        return tf, tb
+            tf.append(ev[0].elapsed_time(ev[1])); tb.append(ev[1].elapsed_time(ev[2]))
+        return sorted(tf)[n // 2], sorted(tb)[n // 2]
 
     out = {}
     g = torch.Generator(device=dev).manual_seed(11)

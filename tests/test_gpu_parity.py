@@ -330,15 +330,16 @@ def test_ensemble_params_flat_leaf_equals_member_lists():
     """EnsembleParams: all members' parameters as one [M, P] leaf -- same values, same gradients (now rows of flat.grad),
     members still read / load their own tensors, and an in-place optimizer step on the flat tensor reaches the members."""
     D, B, M = 8, 12, 3
-    members = [build_pair(D, seed=40 + i)[1] for i in range(M)]
-    y0, a = smooth_cohort(B * M, D, seed=19)
+    members = [build_pair(D, seed=30 + i)[1] for i in range(M)]
+    y0, a = smooth_cohort(B * M, D, seed=17)
     t = torch.arange(0, 15.0).to(DEV)
     W = torch.randn(15, B * M, D, generator=torch.Generator().manual_seed(5)).to(DEV)
     for i, m in enumerate(members):
         m.zero_grad(); m.set_action(a[:, i * B:(i + 1) * B].to(DEV))
     kw = dict(method="rk4", options={"step_size": 0.125})
     zg = y0.clone().to(DEV).requires_grad_(True)
-    (H.odeint_ensemble(members, zg, t, **kw) * W).sum().backward()
+    out0 = H.odeint_ensemble(members, zg, t, **kw)
+    (out0 * W).sum().backward()
     ref_w = [m.ml_net[0].weight.grad.clone() for m in members]
     ref_k = [m.k_dexa.grad.clone() for m in members]
     before = [{k: v.clone() for k, v in m.state_dict().items()} for m in members]
@@ -349,7 +350,8 @@ def test_ensemble_params_flat_leaf_equals_member_lists():
     out = H.odeint_ensemble(ens, z2, t, **kw)
     (out * W).sum().backward()
     assert ens.flat.grad.shape == (M, ens.flat.shape[1])
-    assert torch.equal(z2.grad, zg.grad)  # same kernels, same parameter bytes
+    assert bool(torch.isfinite(out0).all())
+    assert torch.equal(out, out0) and torch.equal(z2.grad, zg.grad)  # same kernels, same parameter bytes
     for i in range(M):
         g = ens.member_grad(i)
         assert relerr(g[13], ref_w[i]) < 1e-6  # 13 expert scalars first, then ml_net weight (include/hode.h)
