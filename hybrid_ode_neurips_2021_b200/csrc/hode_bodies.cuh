@@ -442,11 +442,21 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds
 
     // One trip = one attempt of _adaptive_step inside _advance(t[j]).  Returns false when this controller has finished
     // (all outputs emitted, or a failure status).
-    auto attempt = [&]() -> bool {
-        if (poisoned) { status = HODE_SOLVE_NONFINITE; return false; }
-        if (n_steps >= max_steps || attempts >= attempt_cap) { status = HODE_SOLVE_MAX_STEPS; return false; }
-        if (!(t0 + dt > t0)) { status = HODE_SOLVE_DT_UNDERFLOW; return false; }
-        if (y0_bad) { status = HODE_SOLVE_NONFINITE; return false; }
+    // Lock-step groups (Comm::kLockstep: several controllers in one CTA meet at one barrier per attempt): a controller that has
+    // finished (`idle`) or fails here still walks the stages and the reduction, with every side effect suppressed.
+    auto attempt = [&](bool idle) -> bool {
+        if (!idle) {
+            int fail = HODE_SOLVE_OK;
+            if (poisoned) fail = HODE_SOLVE_NONFINITE;
+            else if (n_steps >= max_steps || attempts >= attempt_cap) fail = HODE_SOLVE_MAX_STEPS;
+            else if (!(t0 + dt > t0)) fail = HODE_SOLVE_DT_UNDERFLOW;
+            else if (y0_bad) fail = HODE_SOLVE_NONFINITE;
+            if (fail != HODE_SOLVE_OK) {
+                status = fail;
+                if constexpr (!Comm::kLockstep) return false;
+                idle = true;
+            }
+        }
         const double t1 = t0 + dt;
         const float t0f = (float)t0, dtf = (float)dt, t1f = (float)t1;
         // ---- the 6 new stages (row 0 holds f0: FSAL); the error estimate k @ (dt c_error) is accumulated on the fly,
@@ -481,7 +491,12 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds
             ss = fmaf(q, q, ss);
         }
         if (!valid) ss = 0.0f;
-        cm.sum1(ss);
+        if constexpr (Comm::kLockstep) {
+            cm.sum1_vote(ss, idle);
+            if (idle) return false;
+        } else {
+            cm.sum1(ss);
+        }
         const float ratio = fast_sqrt(ss * inv_count);
         const bool accept = ratio <= 1.0f;
         ++attempts; ++n_steps;
@@ -551,8 +566,16 @@ HODE_HD void dopri5_fwd_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds
     // Controllers that share a warp (lane segments) are re-converged before every attempt, so that they walk the stage loop
     // in lock-step and share its instruction issue; a finished controller idles until the last one of its warp is done.
     bool done = !(j < a.n_t);
-    while (!cm.all_done(done)) {
-        if (!done) done = !attempt();
+    if constexpr (Comm::kLockstep) {
+        if (!valid) done = true;  // padding threads of a packed CTA belong to no controller
+        do {  // the vote inside the attempt's barrier tells whether ANY thread of the CTA still had work in it
+            const bool r = attempt(done);
+            if (!done) done = !r;
+        } while (!cm.all_done(done));
+    } else {
+        while (!cm.all_done(done)) {
+            if (!done) done = !attempt(false);
+        }
     }
     if (leader) {
         hode_stats st;

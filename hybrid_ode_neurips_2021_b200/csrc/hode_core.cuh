@@ -48,8 +48,27 @@ HODE_HD float div_rn(float a, float b) { volatile float r = a / b; return r; }
 #endif
 
 // tde _nextafter(t, t+1) / _nextafter(t, t-1)
+#if HODE_DEVICE_BUILD && defined(__CUDA_ARCH__)
+// libm's nextafterf is ~25 instructions with three branches, paid twice per dopri5 attempt (the two stages at t0 + dt) and
+// once per perturbed fixed-grid step (ncu: 8 % of the dopri5 forward kernel's instructions at D = 6).  Same function on the
+// bit pattern: toward a larger value the magnitude grows for t > 0 and shrinks for t < 0; t + 1 == t (|t| >= 2^24, inf)
+// returns t like nextafter(x, x); NaN propagates through t + 1.
+HODE_D float t_next(float t) {
+    const float y = t + 1.0f;
+    if (!(y > t)) return y;
+    const int b = __float_as_int(t);
+    return __int_as_float(t > 0.0f ? b + 1 : (t < 0.0f ? b - 1 : 0x00000001));
+}
+HODE_D float t_prev(float t) {
+    const float y = t - 1.0f;
+    if (!(y < t)) return y;
+    const int b = __float_as_int(t);
+    return __int_as_float(t > 0.0f ? b - 1 : (t < 0.0f ? b + 1 : (int)0x80000001u));
+}
+#else
 HODE_HD float t_next(float t) { return nextafterf(t, t + 1.0f); }
 HODE_HD float t_prev(float t) { return nextafterf(t, t - 1.0f); }
+#endif
 
 // ---- transcendental primitives ----------------------------------------------------------------------------------
 // HODE_FAST_MATH=1 (device default): MUFU-based forms with ~1e-7 absolute error (DESIGN.md "math"): the kernels are

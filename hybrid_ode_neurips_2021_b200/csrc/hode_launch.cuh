@@ -39,12 +39,14 @@ __host__ __device__ constexpr int round4(int n) { return (n + 3) / 4 * 4; }
 // ---- group operations of the dopri5 controller: a sum over the controller group (batch-coupled: the CTA or a lane
 //      segment; per-trajectory: nothing) that is bit-identical in every thread of the group, and any() -------------------
 struct CommNone {
+    static constexpr bool kLockstep = false;
     __device__ __forceinline__ void sum1(float&) {}
     __device__ __forceinline__ void sum2(float&, float&) {}
     __device__ __forceinline__ bool any(bool p) { return p; }
     __device__ __forceinline__ bool all_done(bool done) { return done; }
 };
 struct CommCta {
+    static constexpr bool kLockstep = false;
     float* red;  // 2 buffers x (2 * 32) floats of shared memory, used alternately: ONE barrier per reduction
     int nwarps;
     int phase = 0;
@@ -158,6 +160,10 @@ inline bool const_params_enabled() {
     static const bool on = getenv("HODE_NO_CONST_PARAMS") == nullptr;
     return on;
 }
+inline bool pack_enabled() {  // HODE_NO_PACK=1: one group per CTA for mid-size groups (A/B measurements, tests of both paths)
+    static const bool on = getenv("HODE_NO_PACK") == nullptr;
+    return on;
+}
 template <class F>
 inline bool use_const_params(const SolveArgs& a) { return F::kConstBank && a.pset == nullptr && const_params_enabled(); }
 
@@ -168,6 +174,7 @@ inline bool use_const_params(const SolveArgs& a) { return F::kConstBank && a.pse
 // (Per-lane __shfl_sync with a run-time mask cost a MATCH + REDUX + VOTE + WARPSYNC sequence per shuffle: ~120
 // instructions per reduction of a 10-lane group.)  Two buffers are used alternately, so one __syncwarp per reduction.
 struct CommSeg {
+    static constexpr bool kLockstep = false;
     unsigned mask;  // lanes of this segment
     int rel;        // lane index inside the segment
     int nvec;       // round_up4(size) / 4
@@ -192,6 +199,66 @@ struct CommSeg {
     // re-converges every controller of the warp (`part` = the warp's participating lanes) and tells whether all are done
     unsigned part;
     __device__ __forceinline__ bool all_done(bool done) { return __all_sync(part, done) != 0; }
+};
+
+// Mid-size groups PACKED into one CTA: floor(256 / batch) groups of `batch` consecutive threads each, group boundaries
+// anywhere inside a warp.  (One group per CTA leaves 14 of 64 lanes idle at the reference's batch of 50,
+// run_simulation.py:30; 5 groups in 256 threads use 250.)  Group sum in two levels: per warp, one masked butterfly per group
+// that overlaps the warp (at most 3 for batch >= 17) -> lane 0 stores the partial in the group's slot of that warp -> ONE CTA
+// barrier -> every thread adds its group's partials in warp order (bit-identical across the group).  All threads of the CTA
+// walk the attempts in LOCK-STEP -- a finished or failed group keeps executing (results discarded) so that every thread meets
+// every barrier -- and the barrier doubles as the vote that ends the loop: sum1_vote(.., idle) returns in `all_idle` whether
+// no thread of the CTA had work in this attempt.
+struct CommPack {
+    static constexpr bool kLockstep = true;
+    static constexpr int kThreads = 256, kW = 8, kG = 16;  // largest CTA; warps per CTA (>= warps a group can span); groups per CTA (batch >= 17 -> <= 15)
+    // CTA size for groups of `batch`: the smallest multiple of 32 (<= 256) that fills >= 93 % of its lanes with whole groups --
+    // small CTAs keep the lock-step barrier cheap and the wait for a CTA's slowest group short -- else the best-filled one.
+    static int threads_for(int batch) {
+        static const int forced = getenv("HODE_PACK_THREADS") ? atoi(getenv("HODE_PACK_THREADS")) : 0;  // A/B measurements
+        if (forced >= 32 && forced <= kThreads && forced % 32 == 0 && forced >= batch) return forced;
+        int best = 0;
+        double best_u = 0.0;
+        for (int t = 32; t <= kThreads; t += 32) {
+            const double u = (double)(t / batch * batch) / t;
+            if (u >= 0.93) return t;
+            if (u > best_u) { best_u = u; best = t; }
+        }
+        return best;
+    }
+    static constexpr int kFloats = 2 * kG * kW;
+    float* red;        // [2 phases][kG][kW]
+    int batch;
+    int g;             // this thread's group inside the CTA; kG - 1 .. for padding threads: a group nobody reduces into
+    int g_lo, g_hi;    // groups overlapping this warp (warp-uniform; g_lo > g_hi: none)
+    int nw;            // warps my group spans (0 for padding threads)
+    int phase = 0;
+    bool all_idle = false;
+    __device__ __forceinline__ void reduce(float& a, bool idle) {
+        float* r = red + phase * (kG * kW);
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int gk = g_lo + k;
+            if (gk <= g_hi) {  // warp-uniform
+                float v = (g == gk) ? a : 0.0f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) r[gk * kW + (wid - ((gk * batch) >> 5))] = v;
+            }
+        }
+        all_idle = __syncthreads_and(idle ? 1 : 0) != 0;
+        float s = 0.0f;
+        const float* mine = r + g * kW;
+        for (int i = 0; i < nw; ++i) s += mine[i];
+        phase ^= 1;  // the next reduction writes the other buffer; the one after is separated from these reads by its barrier
+        a = s;
+    }
+    __device__ __forceinline__ void sum1(float& a) { reduce(a, false); }
+    __device__ __forceinline__ void sum1_vote(float& a, bool idle) { reduce(a, idle); }
+    __device__ __forceinline__ void sum2(float& a, float& b) { reduce(a, false); reduce(b, false); }
+    __device__ __forceinline__ bool any(bool p) { float f = p ? 1.0f : 0.0f; reduce(f, false); return f > 0.0f; }
+    __device__ __forceinline__ bool all_done(bool) { return all_idle; }
 };
 
 template <class F>
@@ -588,6 +655,35 @@ __global__ void __launch_bounds__(128, D5Store<F>::kFwdMinBlocks) dopri5_fwd_seg
     });
 }
 
+// Batch-coupled controller for MID-SIZE groups (17 <= batch <= 128, one parameter set) whose size wastes lanes as one CTA
+// per group: floor(256 / batch) groups per 256-thread CTA (CommPack).
+template <class F, int ND, bool CP>
+__global__ void __launch_bounds__(CommPack::kThreads, D5Store<F>::kSmem || F::D <= 6 ? 2 : 1) dopri5_fwd_pack_kernel(const SolveArgs a, int gpc) {
+    extern __shared__ __align__(16) float smem[];
+    float* red = smem + (CP ? 0 : round4(F::SP));
+    float* rows = red + CommPack::kFloats;
+    if constexpr (!CP) stage_params<F>(a, 0, smem);
+    const int tid = threadIdx.x, size = (int)a.batch;
+    const int gl = tid / size;  // group inside the CTA
+    const int64_t group = (int64_t)blockIdx.x * gpc + gl;
+    const bool valid = gl < gpc && group < a.n_groups;
+    const int rel = tid - gl * size;
+    CommPack cm;
+    cm.red = red;
+    cm.batch = size;
+    cm.g = valid ? gl : CommPack::kG - 1;  // gpc <= 15: slot kG - 1 is never written
+    const int w0 = (tid >> 5) << 5;
+    cm.g_lo = w0 / size;
+    cm.g_hi = min((w0 + 31) / size, gpc - 1);
+    cm.nw = valid ? (((gl * size + size - 1) >> 5) - ((gl * size) >> 5) + 1) : 0;
+    const int64_t idx = valid ? group * a.batch + rel : 0;
+    const float count = (float)(a.batch * F::D);
+    with_rows<F, 7, 0>(rows, [&](auto& k) {
+        if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F, D5Store<F>::kFwdRolled>(a, cm, ParamConst(), ds, k, idx, valid, valid ? group : 0, valid && rel == 0, count))); }
+        else { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F, D5Store<F>::kFwdRolled>(a, cm, (const float*)smem, ds, k, idx, valid, valid ? group : 0, valid && rel == 0, count))); }
+    });
+}
+
 template <class F, bool EG, int ND, bool CP>
 __global__ void __launch_bounds__(128, D5Store<F>::kBwdMinBlocks) dopri5_bwd_kernel(const SolveArgs a, int tiles_per_group) {
     extern __shared__ __align__(16) float smem[];
@@ -893,6 +989,32 @@ int launch_dopri5_fwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t s
 #undef HODE_DS
         HODE_LAUNCH_CHECK();
         return 0;
+    }
+    if (!a_in.per_traj && a_in.pset == nullptr && a_in.batch >= 17 && a_in.batch <= 128 && pack_enabled()) {
+        // mid-size groups: pack floor(256 / batch) of them into one CTA when that fills clearly more lanes than one group per CTA
+        const SolveArgs& a = a_in;
+        const int pthreads = CommPack::threads_for((int)a.batch);
+        const int gpc = pthreads / (int)a.batch;
+        const double util_pack = (double)(gpc * a.batch) / pthreads, util_cta = (double)a.batch / round_up32(a.batch);
+        // measured (B200, 8 192 groups): batch 20 at D = 12 1.85 x faster packed (60 of 64 lanes instead of 20 of 32), batch 50 at
+        // D = 6 10 % SLOWER packed (150 of 160 lanes instead of 50 of 64: the lock-step barrier over 5 warps and the wait for the
+        // slowest of 3 groups cost more than the lanes gain) -> pack only for a clear gain in filled lanes
+        if (gpc >= 2 && a.n_groups >= gpc && util_pack >= 1.4 * util_cta) {
+            const int64_t nblk = (a.n_groups + gpc - 1) / gpc;
+#define HODE_DP(ND, CP)                                                                                                        \
+    do {                                                                                                                       \
+        const size_t sh_ = ((CP ? 0 : round4(F::SP)) + CommPack::kFloats + D5Store<F>::fwd_floats(pthreads)) * sizeof(float); \
+        int e_ = set_smem(dopri5_fwd_pack_kernel<F, ND, CP>, sh_);                                                             \
+        if (e_ != 0) return e_;                                                                                                \
+        dopri5_fwd_pack_kernel<F, ND, CP><<<(unsigned)nblk, pthreads, sh_, st>>>(a, gpc);                                      \
+    } while (0)
+#define HODE_DP_CP(CP) do { if (nd1) HODE_DP(1, CP); else HODE_DP(0, CP); } while (0)
+            HODE_DISPATCH_CP(F, a, st, HODE_DP_CP);
+#undef HODE_DP_CP
+#undef HODE_DP
+            HODE_LAUNCH_CHECK();
+            return 0;
+        }
     }
     const SolveArgs a = a_in.per_traj ? flatten(a_in) : a_in;
     const int threads = a.per_traj ? (a.batch >= 128 ? 128 : round_up32(a.batch)) : round_up32(a.batch);

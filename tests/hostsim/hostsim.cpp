@@ -22,12 +22,14 @@ using namespace hode;
 
 namespace {
 struct CommNone {
+    static constexpr bool kLockstep = false;
     void sum1(float&) {}
     void sum2(float&, float&) {}
     bool any(bool p) { return p; }
     bool all_done(bool done) { return done; }
 };
 struct CommThreads {
+    static constexpr bool kLockstep = false;
     std::barrier<>* bar;
     float* buf;
     int n, tid;
@@ -43,6 +45,33 @@ struct CommThreads {
     void sum1(float& a) { float z = 0.f; sum2(a, z); }
     bool any(bool p) { float v = p ? 1.f : 0.f, z = 0.f; sum2(v, z); return v > 0.f; }
     bool all_done(bool done) { return done; }
+};
+// Emulation of the device's CommPack (several controller groups in one CTA, all threads in lock-step, the reduction's barrier
+// doubling as the "did anybody still have work" vote): `n` threads = `groups` x `batch` + padding threads that belong to no group.
+struct CommPackThreads {
+    static constexpr bool kLockstep = true;
+    std::barrier<>* bar;
+    float* buf;   // [n] values
+    int* idle;    // [n] votes
+    int n, tid, first, count;  // my group's threads: first .. first + count - 1 (count = 0: padding thread)
+    bool all_idle = false;
+    void reduce(float& a, bool idl) {
+        buf[tid] = a;
+        idle[tid] = idl ? 1 : 0;
+        bar->arrive_and_wait();
+        float s = 0.f;
+        for (int i = 0; i < count; ++i) s += buf[first + i];
+        bool all = true;
+        for (int i = 0; i < n; ++i) all = all && idle[i] != 0;
+        bar->arrive_and_wait();
+        all_idle = all;
+        a = s;
+    }
+    void sum1(float& a) { reduce(a, false); }
+    void sum1_vote(float& a, bool idl) { reduce(a, idl); }
+    void sum2(float& a, float& b) { reduce(a, false); reduce(b, false); }
+    bool any(bool p) { float v = p ? 1.f : 0.f; reduce(v, false); return v > 0.f; }
+    bool all_done(bool) { return all_idle; }
 };
 // Row storage of the dopri5 bodies: the device keeps the rows of the D = 12 kernels in shared memory with ROLLED stage
 // loops (RowsMem) and in registers with unrolled loops otherwise (RowsReg).  The emulation follows the same policy;
@@ -164,6 +193,30 @@ void dopri5_fwd(const SolveArgs& a) {
         }
     }
 }
+// the device's packed launch shape (dopri5_fwd_pack_kernel): `gpc` groups per emulated CTA plus two padding threads, lock-step
+template <class F>
+void dopri5_fwd_packed(const SolveArgs& a, int gpc) {
+    auto sp = stage<F>(a, 0);
+    const int bsz = (int)a.batch;
+    for (int64_t g0 = 0; g0 < a.n_groups; g0 += gpc) {
+        const int n = gpc * bsz + 2;  // a last CTA with fewer groups has more padding threads, like on the device
+        std::barrier<> bar(n);
+        std::vector<float> buf(n);
+        std::vector<int> idle(n);
+        std::vector<std::thread> th;
+        for (int t = 0; t < n; ++t)
+            th.emplace_back([&, t]() {
+                const int gl = t / bsz;
+                const int64_t g = g0 + gl;
+                const bool valid = gl < gpc && g < a.n_groups;
+                const int rel = t - gl * bsz;
+                const int64_t idx = valid ? g * a.batch + rel : 0;
+                CommPackThreads cm{&bar, buf.data(), idle.data(), n, t, gl * bsz, valid ? bsz : 0};
+                with_rows<F, 7>([&](auto& k, auto rolled) { dopri5_fwd_traj<F, decltype(rolled)::value>(a, cm, sp.data(), dose(a, idx), k, idx, valid, valid ? g : 0, valid && rel == 0, (float)(a.batch * F::D)); });
+            });
+        for (auto& t : th) t.join();
+    }
+}
 template <class F>
 void dopri5_bwd(const SolveArgs& a, bool eg) {
     for (int64_t g = 0; g < a.n_groups; ++g) {
@@ -252,7 +305,12 @@ int run(Op op, const hode_cfg& cfg, const SolveArgs& a) {
             else if (cfg.method == HODE_MIDPOINT) fixed_fwd_sse<F, M_MIDPOINT>(a);
             else fixed_fwd_sse<F, M_RK4_38>(a);
             return 0;
-        case DF: dopri5_fwd<F>(a); return 0;
+        case DF: {
+            const char* pk = getenv("HODE_HOSTSIM_PACK");  // test switch: emulate the packed launch shape with this many groups per CTA
+            if (pk != nullptr && !a.per_traj && a.pset == nullptr && atoi(pk) > 0) dopri5_fwd_packed<F>(a, atoi(pk));
+            else dopri5_fwd<F>(a);
+            return 0;
+        }
         case DB: dopri5_bwd<F>(a, eg); return 0;
         case DA: dopri5_adj<F>(a, eg); return 0;
     }

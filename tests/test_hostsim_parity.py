@@ -111,6 +111,37 @@ def test_dopri5_forward_and_reverse_sweep(lib, D, ctrl, hill2):
         assert relerr(gp[0][13:], grads_vec(o, False)[13:]) < 5e-5
 
 
+@pytest.mark.parametrize("D", [6, 12])
+def test_dopri5_packed_groups_in_lock_step_equal_one_group_per_cta(lib, D, monkeypatch):
+    """The device packs mid-size groups (17..128 trajectories) several to a CTA and walks all of them in lock-step -- one
+    barrier per attempt, finished / failed / padding threads keep attending it (dopri5_fwd_pack_kernel, CommPack).  The host
+    emulation of that launch shape must reproduce the one-group-per-CTA run bit for bit: outputs, tapes, per-group step counts
+    and statuses -- including groups that fail (attempt cap) while their neighbours carry on, and a last CTA with fewer groups."""
+    G, B = 5, 3
+    o = oracle_roche(D, 2, True)
+    y0, a, _, _ = make_cohort(G * B, D, seed=50 + D)
+    o.set_action(a)
+    t = torch.arange(0, 15.0).double()
+    # the five groups need 131 .. 169 attempts (D = 6) / 123 .. 152 (D = 12): the cap stops some of them mid-way
+    cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.DOPRI5, n_dose=1, rtol=1e-4, atol=1e-5, attempt_cap=140 if D == 6 else 133)
+    pb = problem(o, cfg, G * B, n_groups=G)
+    monkeypatch.delenv("HODE_HOSTSIM_PACK", raising=False)
+    h0, st0, tape0 = ops.dopri5_fwd(lib, pb, y0, t, 1024)
+    assert (st0[:, 3] != 0).any() and (st0[:, 3] == 0).any()  # at least one failed group and one finished group
+    assert len(set(int(v) for v in (st0[:, 0] + st0[:, 1]))) > 1  # groups need different numbers of attempts
+    for gpc in (2, 5):
+        monkeypatch.setenv("HODE_HOSTSIM_PACK", str(gpc))
+        h1, st1, tape1 = ops.dopri5_fwd(lib, pb, y0, t, 1024)
+        assert torch.equal(st0, st1)
+        ok = st0[:, 3] == 0
+        hv0, hv1 = h0.reshape(15, G, B, D)[:, ok], h1.reshape(15, G, B, D)[:, ok]
+        assert torch.equal(hv0, hv1)
+        for g in range(G):
+            n = int(st0[g, 0])
+            assert torch.equal(tape0[0][g, :n], tape1[0][g, :n])  # (t0, dt) of every accepted step
+            assert torch.equal(tape0[1][:n].reshape(n, G, B, D)[:, g], tape1[1][:n].reshape(n, G, B, D)[:, g])
+
+
 def test_dopri5_first_attempt_is_exactly_the_oracle_attempt(lib):
     D, B, h = 6, 4, 0.25
     o = oracle_roche(D, 3, True)
