@@ -84,7 +84,8 @@ static int dispatch(Op op, const hode_cfg& cfg, const SolveArgs& a, cudaStream_t
         return fail(HODE_ERR_UNSUPPORTED, "field %s%lld is not compiled in", "", cfg.field);
     }
     if (rc == 0) return HODE_OK;
-    if (rc == -2) return fail(HODE_ERR_UNSUPPORTED, "batch-coupled dopri5 group larger than %s%lld trajectories", "", hode_dopri5_max_batch(&cfg));
+    if (rc == -2) return fail(HODE_ERR_UNSUPPORTED, "batch-coupled dopri5 group larger than %s%lld trajectories", "",
+                              op == OP_DOPRI5_ADJ ? (long long)512 : (long long)hode_dopri5_max_batch(&cfg));
     if (rc == -3) return fail(HODE_ERR_UNSUPPORTED, "the adaptive adjoint of the NeuralODE field is built for the batch-coupled controller only%s%lld", "", 0);
     if (rc == -1 && op == OP_FIXED_FWD_SSE)
         return fail(HODE_ERR_UNSUPPORTED, "no fused solve + read-out kernel for this field / method / obs / n_dose / parameter-set "
@@ -118,7 +119,7 @@ int32_t hode_supported(const hode_cfg* cfg) {
 
 int64_t hode_dopri5_max_batch(const hode_cfg* cfg) {
     (void)cfg;
-    return 512;
+    return 4096;  // forward / reverse sweep: one CTA up to 512 trajectories, a cluster of up to 8 CTAs beyond (hode_launch.cuh)
 }
 
 size_t hode_fixed_tape_bytes(const hode_cfg* cfg, int64_t n_traj, int32_t n_grid) {

@@ -5,6 +5,7 @@
 // written with 16/8-byte vector stores, D*4 contiguous bytes per lane (full 32 B sectors).  A CTA never spans two
 // groups, so a CTA has exactly one parameter set and (dopri5, batch-coupled) one controller.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdlib.h>
 
@@ -199,6 +200,35 @@ struct CommSeg {
     // re-converges every controller of the warp (`part` = the warp's participating lanes) and tells whether all are done
     unsigned part;
     __device__ __forceinline__ bool all_done(bool done) { return __all_sync(part, done) != 0; }
+};
+
+// A group LARGER than one CTA (batch > 512; torchdiffeq's norm is over the whole [B, D] tensor at any B, model.py:1116): the
+// group's CTAs form a thread-block CLUSTER (<= 8 CTAs = 4 096 trajectories).  Per reduction: CTA-level sum as above, then the
+// first `nrank` threads of every CTA store that sum into slot [own rank] of EVERY CTA's shared memory (distributed shared
+// memory), one cluster barrier, and every thread adds the slots in rank order -- bit-identical across the whole group, so the
+// accept / reject decisions (and the loop trip count, hence the barrier count) are cluster-uniform by construction.
+struct CommCluster {
+    static constexpr bool kLockstep = false;
+    static constexpr int kMaxCtas = 8, kFloats = 2 * kMaxCtas;
+    CommCta cta;
+    float* slots;  // [2 phases][kMaxCtas] in this CTA's shared memory
+    unsigned rank, nrank;
+    int phase = 0;
+    __device__ __forceinline__ void sum1(float& a) {
+        cta.sum1(a);
+        namespace cg = cooperative_groups;
+        cg::cluster_group cl = cg::this_cluster();
+        float* mine = slots + phase * kMaxCtas;
+        if (threadIdx.x < nrank) cl.map_shared_rank(mine, threadIdx.x)[rank] = a;
+        cl.sync();  // release / acquire: the remote stores are visible after it
+        float s = 0.0f;
+        for (unsigned i = 0; i < nrank; ++i) s += mine[i];
+        phase ^= 1;  // as in CommCta: the buffer written two reductions from now is separated from these reads by the next barrier
+        a = s;
+    }
+    __device__ __forceinline__ void sum2(float& a, float& b) { sum1(a); sum1(b); }
+    __device__ __forceinline__ bool any(bool p) { float f = p ? 1.0f : 0.0f; sum1(f); return f > 0.0f; }
+    __device__ __forceinline__ bool all_done(bool done) { return done; }  // cluster-uniform by construction
 };
 
 // Mid-size groups PACKED into one CTA: floor(256 / batch) groups of `batch` consecutive threads each, group boundaries
@@ -684,6 +714,30 @@ __global__ void __launch_bounds__(CommPack::kThreads, D5Store<F>::kSmem || F::D 
     });
 }
 
+// Batch-coupled controller for a group of more than 512 trajectories: `nrank` CTAs of one cluster per group (CommCluster).
+template <class F, int ND, bool CP>
+__global__ void __launch_bounds__(HODE_DOPRI5_MAX_THREADS, 1) dopri5_fwd_cluster_kernel(const SolveArgs a) {
+    extern __shared__ __align__(16) float smem[];
+    float* red = smem + (CP ? 0 : round4(F::SP));
+    float* slots = red + 128;
+    float* rows = slots + CommCluster::kFloats;
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    const unsigned nrank = cl.num_blocks(), rank = cl.block_rank();
+    const int64_t group = blockIdx.x / nrank;
+    if constexpr (!CP) stage_params<F>(a, group, smem);
+    const int64_t b0 = (int64_t)rank * blockDim.x + threadIdx.x;
+    const bool valid = b0 < a.batch;
+    const int64_t idx = group * a.batch + (valid ? b0 : a.batch - 1);
+    const float count = (float)(a.batch * F::D);
+    CommCluster cm{CommCta{red, (int)(blockDim.x >> 5), 0}, slots, rank, nrank, 0};
+    with_rows<F, 7, 0>(rows, [&](auto& k) {
+        if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F, D5Store<F>::kFwdRolled>(a, cm, ParamConst(), ds, k, idx, valid, group, rank == 0 && threadIdx.x == 0, count))); }
+        else { HODE_WITH_DOSE(ND, a, idx, (dopri5_fwd_traj<F, D5Store<F>::kFwdRolled>(a, cm, (const float*)smem, ds, k, idx, valid, group, rank == 0 && threadIdx.x == 0, count))); }
+    });
+    cl.sync();  // no CTA leaves while a sibling could still address its shared memory
+}
+
 template <class F, bool EG, int ND, bool CP>
 __global__ void __launch_bounds__(128, D5Store<F>::kBwdMinBlocks) dopri5_bwd_kernel(const SolveArgs a, int tiles_per_group) {
     extern __shared__ __align__(16) float smem[];
@@ -968,7 +1022,36 @@ int launch_fixed_adj(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st
 template <class F>
 int launch_dopri5_fwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st) {
     const bool nd1 = cfg.n_dose == 1;
-    if (!a_in.per_traj && a_in.batch > HODE_DOPRI5_MAX_THREADS) return -2;
+    if (!a_in.per_traj && a_in.batch > (int64_t)HODE_DOPRI5_MAX_THREADS * CommCluster::kMaxCtas) return -2;
+    if (!a_in.per_traj && a_in.batch > HODE_DOPRI5_MAX_THREADS) {
+        // one cluster of CTAs per group
+        const SolveArgs& a = a_in;
+        const int nrank = (int)((a.batch + HODE_DOPRI5_MAX_THREADS - 1) / HODE_DOPRI5_MAX_THREADS);
+        const int threads = round_up32((int)((a.batch + nrank - 1) / nrank));
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)(a.n_groups * nrank), 1, 1);
+        lc.blockDim = dim3((unsigned)threads, 1, 1);
+        lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)nrank; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+#define HODE_DC(ND, CP)                                                                                                   \
+    do {                                                                                                                  \
+        const size_t sh_ = ((CP ? 0 : round4(F::SP)) + 128 + CommCluster::kFloats + D5Store<F>::fwd_floats(threads)) * sizeof(float); \
+        int e_ = set_smem(dopri5_fwd_cluster_kernel<F, ND, CP>, sh_);                                                     \
+        if (e_ != 0) return e_;                                                                                           \
+        lc.dynamicSmemBytes = sh_;                                                                                        \
+        cudaError_t le_ = cudaLaunchKernelEx(&lc, dopri5_fwd_cluster_kernel<F, ND, CP>, a);                               \
+        if (le_ != cudaSuccess) return (int)le_;                                                                          \
+    } while (0)
+#define HODE_DC_CP(CP) do { if (nd1) HODE_DC(1, CP); else HODE_DC(0, CP); } while (0)
+        HODE_DISPATCH_CP(F, a, st, HODE_DC_CP);
+#undef HODE_DC_CP
+#undef HODE_DC
+        HODE_LAUNCH_CHECK();
+        return 0;
+    }
     if (!a_in.per_traj && a_in.pset == nullptr && a_in.batch <= 16 && a_in.batch >= 4) {
         // small batch-coupled groups: several groups per warp
         const SolveArgs& a = a_in;

@@ -717,12 +717,15 @@ def _odeint_impl(funcs, y0, t, rtol, atol, method, options, event_fn, adjoint=No
         mb = int(L.get_lib().hode_dopri5_max_batch(cfg))
         if batch > mb:
             raise NotImplementedError(
-                "batch-coupled dopri5 integrates one group per CTA (<= {} trajectories); got {}. Use "
+                "batch-coupled dopri5 integrates one group per CTA or cluster of CTAs (<= {} trajectories); got {}. Use "
                 "options={{'n_groups': g}} or options={{'controller': 'trajectory'}}.".format(mb, batch)
             )
     t_dev, _ = _times_for(t, None, y0.device, False)
     holder = []
     if adjoint is not None and need_grad:
+        if ctrl_name == "batch" and batch > 512:
+            raise NotImplementedError("the adaptive adjoint integrates one group per CTA (<= 512 trajectories); got {}. Use "
+                                      "options={{'n_groups': g}} or options={{'controller': 'trajectory'}}.".format(batch))
         aopt = adjoint["options"]
         acfg = L.HodeCfg.from_buffer_copy(cfg)
         acfg.rtol, acfg.atol = float(adjoint["rtol"]), float(adjoint["atol"])

@@ -176,7 +176,9 @@ int32_t hode_fixed_adjoint(const hode_cfg* cfg, int64_t n_groups, int64_t batch,
 
 /* ---- dopri5: torchdiffeq Dopri5Solver (RKAdaptiveStepsizeODESolver.integrate), model.py:1116 ------------------
  * t_eval is float64 (torchdiffeq casts `t` to float64).  controller BATCH: one controller per group
- * (batch <= hode_dopri5_max_batch()); TRAJ: one per trajectory.  n_ctrl = n_groups (BATCH) or n_traj (TRAJ).
+ * (batch <= hode_dopri5_max_batch() = 4096: one CTA up to 512 trajectories, a thread-block cluster of up to 8 CTAs with the
+ * group sum exchanged through distributed shared memory beyond); TRAJ: one per trajectory.
+ * n_ctrl = n_groups (BATCH) or n_traj (TRAJ).
  * tape (NULL for forward-only): accepted steps, capacity tape_capacity per controller:
  *     tape_t  [n_ctrl, tape_capacity, 2] float64 (t0, dt);  tape_y [tape_capacity, n_traj, D] float32.
  * stats [n_ctrl].                                                                                            */
@@ -195,7 +197,7 @@ int32_t hode_dopri5_bwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, co
  * reference keeps commented out at model.py:9; dopri5 is its default method, sim_config.py:50).  For i = n_t-1 .. 1 the
  * augmented state (y = h[i], a, g_params) is integrated by the dopri5 controller from t[i] back to t[i-1] (negated time),
  * interpolated to t[i-1] by the quartic dense output; then a += grad_h[i-1], y = h[i-1].  No tape.
- * cfg: rtol / atol = the ADJOINT tolerances; controller BATCH (one controller per group, batch <= hode_dopri5_max_batch())
+ * cfg: rtol / atol = the ADJOINT tolerances; controller BATCH (one controller per group, batch <= 512)
  * or TRAJ; flags must contain HODE_FLAG_ADJ_SEMINORM.  h [n_t, n_traj, D]: the forward solution (hode_dopri5_fwd without a
  * tape).  stats [n_ctrl]: accepted / rejected attempts summed over the intervals, status as in hode_dopri5_fwd. */
 int32_t hode_dopri5_adjoint(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,

@@ -438,6 +438,36 @@ def test_multi_warp_group_matches_oracle():
     assert relerr(out, ref) < 5e-5 and relerr(gout, gref) < 2e-4
 
 
+@pytest.mark.parametrize("D,B", [(6, 1300), (12, 600), (8, 4096)])
+def test_group_larger_than_one_cta_runs_as_a_cluster(D, B):
+    """One odeint call of more than 512 patients (torchdiffeq's error norm is over the whole batch, model.py:1116): the
+    group's CTAs form a thread-block cluster and exchange the norm through distributed shared memory
+    (dopri5_fwd_cluster_kernel): 3 CTAs with a partly filled last one, 2 CTAs with shared-memory stage rows, and the
+    8-CTA maximum.  Same accept / reject sequence as the oracle on a smooth cohort, values and gradients at the gates of the
+    one-CTA test above; one patient more than the maximum is refused."""
+    o, m = build_pair(D)
+    t = torch.arange(0, 15.0)
+    W = torch.ones(15, B, D)
+    y0, a = smooth_cohort(B, D, seed=8)
+    ref, gref, out, gout, tr = run_both(o, m, y0, a, t, W, method="dopri5", rtol=1e-4, atol=1e-5)
+    info = H.last_solve_info()
+    assert info.stats.shape[0] == 1 and int(info.stats[0, 3]) == 0
+    n_ref, n_out = tr.accepted + tr.rejected, int(info.accepted[0] + info.rejected[0])
+    assert abs(n_out - n_ref) <= 2, (n_out, n_ref)
+    check("cluster group D={} B={} h".format(D, B), relerr(out, ref), 1e-4)  # rtol 1e-4; measured 1e-5 .. 5e-5
+    check("cluster group D={} B={} dL/dy0".format(D, B), relerr(gout, gref), 2e-4)
+    check_param_grads(o, m, 5e-4)
+    if B == 4096:
+        y1, a1 = smooth_cohort(B + 1, D, seed=8)
+        m.set_action(a1.to(DEV))
+        with pytest.raises(NotImplementedError, match="4096"):
+            H.odeint(m, y1.to(DEV), t.to(DEV), method="dopri5")
+        m.set_action(a1[:, :600].to(DEV))
+        with pytest.raises(NotImplementedError, match="512"):
+            H.odeint_adjoint(m, y1[:600].to(DEV).requires_grad_(True), t.to(DEV), method="dopri5",
+                             adjoint_options={"norm": "seminorm"})
+
+
 def test_two_doses_per_patient():
     D, B = 6, 9
     o, m = build_pair(D)
