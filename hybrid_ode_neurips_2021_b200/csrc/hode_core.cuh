@@ -512,21 +512,29 @@ struct Roche {
 template <int D_>
 struct NeuralCoop {
     static constexpr int H = 10 * D_, IN = D_ + 1, NJ = (H + 31) / 32;
-    static constexpr int kStageFloats = (IN + D_) * 32 + 2 * 32 * 33;  // per warp
-    float* stage;          // warp-private: S_in [IN][32], S_u [D][32], S_del [32][33], S_a [32][33]
+    static constexpr int SI = (D_ + 2 + 3) / 4 * 4;  // staged input row: in[0..D], 1 (the bias "input"), zero padding
+    static constexpr int SU = (D_ + 3) / 4 * 4;      // staged output-adjoint row
+    static constexpr int SDA = 66;                   // (delta, a) pairs of one unit over the 32 lanes, +2 floats: conflict-free LDS.64
+    static constexpr int kStageFloats = (SI + SU) * 32 + 32 * SDA;  // per warp
+    float* stage;          // warp-private: S_in [32][SI], S_u [32][SU], S_da [32 units][SDA]
     int lane;
-    float w1[NJ][IN + 1];  // rows of dW1 (IN) and db1 (1) of the owned units
-    float w2[NJ][D_];      // columns of dW2 of the owned units
+    float w1[NJ][SI];      // rows of dW1 (IN) and db1 (1) of the owned units (+ padding that stays zero)
+    float w2[NJ][SU];      // columns of dW2 of the owned units
     float b2[D_];          // this lane's own contribution to db2 (reduced over the warp at the end)
     bool mute;             // true: the call only needs J^T l (zero-weight stage of the continuous adjoint)
 };
 
+// The two mat-vecs are written on packed pairs (FFMA2, see above): layer 1 as a dot product over input pairs
+// (w1[2q], w1[2q+1]) . (in[2q], in[2q+1]) with the bias riding along as the weight of a constant-one input, layer 2 as
+// (out[2q], out[2q+1]) += a_j (W2[2q][j], W2[2q+1][j]).  13 -> 8 math issue slots per hidden unit at D = 6.  Both layers'
+// staged weights carry the factor 2 log2(e) of the tanh (HODE_FOLD_TANH), which the VJP folds back into its cotangents.
 template <int D_>
 struct Neural {
     static constexpr int D = D_;
     static constexpr int H = 10 * D_;
     static constexpr int IN = D_ + 1;
     static constexpr int P = 1 + H * IN + H + D_ * H + D_;
+    static constexpr int NP1 = (D_ + 2) / 2;              // input pairs of layer 1: in[0..D], 1
     static constexpr int R = ((2 * D_ + 2 + 3) / 4) * 4;  // record length
     static constexpr int SP = H * R + ((D_ + 3) / 4) * 4;
     static constexpr int OFF_W1 = 1;
@@ -535,7 +543,9 @@ struct Neural {
     static constexpr int OFF_B2 = OFF_W2 + D_ * H;
     static constexpr bool kAccInRegs = false;  // P is 846..3132: accumulators live in local memory
     static constexpr bool kConstBank = false;
+    static_assert(D_ % 2 == 0, "packed pairs assume an even state dimension");
 
+    // staged record of hidden unit j: {W1[j][0..D], b1[j], W2[0..D-1][j], pad} * kTanhPre, then b2 * kTanhPre
     HODE_HD static void stage(const float* __restrict__ src, float* sp, int tid, int nthr) {
         for (int e = tid; e < H * R; e += nthr) {
             const int j = e / R, c = e % R;
@@ -543,45 +553,61 @@ struct Neural {
             if (c < IN) v = src[OFF_W1 + j * IN + c];
             else if (c == IN) v = src[OFF_B1 + j];
             else if (c < IN + 1 + D_) v = src[OFF_W2 + (c - IN - 1) * H + j];
-            sp[e] = v;
+            sp[e] = v * kTanhPre;
         }
-        for (int d = tid; d < D_; d += nthr) sp[H * R + d] = src[OFF_B2 + d];
+        for (int d = tid; d < D_; d += nthr) sp[H * R + d] = src[OFF_B2 + d] * kTanhPre;
     }
     HODE_HD static void prepare(float*) {}
 
     template <class PS>
     HODE_HD static bool params_ok(PS) { return true; }
 
+    HODE_HD static float act(float pre) {  // tanh of a pre-activation that already carries kTanhPre
+#if HODE_FOLD_TANH
+        return tanh_pre(pre);
+#else
+        return tanh_f(pre);
+#endif
+    }
+    // (in[0..D], 1): the layer-1 input with the bias input appended
     template <class Dose>
-    HODE_HD static void eval(const float* __restrict__ sp, float t, const Dose& ds, const float (&y)[D_],
-                             float (&dy)[D_]) {
-        float in[IN], out[D_];
+    HODE_HD static void inputs(float t, const Dose& ds, const float (&y)[D_], float (&in)[2 * NP1]) {
 #pragma unroll
         for (int i = 0; i < D_; ++i) in[i] = y[i];
         in[D_] = neural_dose(ds, t);
+        in[D_ + 1] = 1.0f;
+    }
+    // hidden activation of one unit from its record
+    HODE_HD static float hidden(const float* rec, const float (&in)[2 * NP1]) {
+        float p0 = 0.0f, p1 = 0.0f;
+#pragma unroll
+        for (int q = 0; q < NP1; ++q) fma2(rec[2 * q], rec[2 * q + 1], in[2 * q], in[2 * q + 1], p0, p1, p0, p1);
+        return act(p0 + p1);
+    }
+
+    template <class Dose>
+    HODE_HD static void eval(const float* __restrict__ sp, float t, const Dose& ds, const float (&y)[D_],
+                             float (&dy)[D_]) {
+        float in[2 * NP1], out[D_];
+        inputs(t, ds, y, in);
 #pragma unroll
         for (int d = 0; d < D_; ++d) out[d] = sp[H * R + d];
 #pragma unroll 2
         for (int j = 0; j < H; ++j) {
             const float* rec = sp + j * R;
-            float a = rec[IN];
+            const float a = hidden(rec, in);
 #pragma unroll
-            for (int i = 0; i < IN; ++i) a = fmaf(rec[i], in[i], a);
-            a = tanh_f(a);
-#pragma unroll
-            for (int d = 0; d < D_; ++d) out[d] = fmaf(rec[IN + 1 + d], a, out[d]);
+            for (int d = 0; d < D_; d += 2) fma2s(a, rec[IN + 1 + d], rec[IN + 2 + d], out[d], out[d + 1], out[d], out[d + 1]);
         }
 #pragma unroll
-        for (int d = 0; d < D_; ++d) dy[d] = tanh_f(out[d]);
+        for (int d = 0; d < D_; ++d) dy[d] = act(out[d]);
     }
 
-    template <bool EG, class Dose>
-    HODE_HD static void vjp(const float* __restrict__ sp, float t, const Dose& ds, const float (&y)[D_],
-                            const float* k, const float (&l)[D_], float (&gy)[D_], float* acc) {
-        float in[IN], u[D_];
-#pragma unroll
-        for (int i = 0; i < D_; ++i) in[i] = y[i];
-        in[D_] = neural_dose(ds, t);
+    // u = l (1 - s^2): cotangent of the output pre-activation; `us` additionally carries kTanhPre so that it can be
+    // contracted with the STAGED second-layer weights
+    template <class Dose>
+    HODE_HD static void out_cotangent(const float* __restrict__ sp, float t, const Dose& ds, const float (&y)[D_],
+                                      const float* k, const float (&l)[D_], float (&u)[D_]) {
         if (k != nullptr) {
 #pragma unroll
             for (int d = 0; d < D_; ++d) u[d] = l[d] * (1.0f - k[d] * k[d]);
@@ -591,28 +617,41 @@ struct Neural {
 #pragma unroll
             for (int d = 0; d < D_; ++d) u[d] = l[d] * (1.0f - s2[d] * s2[d]);
         }
+    }
+    // one hidden unit of the VJP: activation a, delta = (W2[:, j] . u) (1 - a^2), gy += W1[j][0..D-1] delta
+    HODE_HD static void unit_vjp(const float* rec, const float (&in)[2 * NP1], const float (&us)[D_], float (&gy)[D_],
+                                 float& a, float& del) {
+        a = hidden(rec, in);
+        float c0 = 0.0f, c1 = 0.0f;
 #pragma unroll
-        for (int d = 0; d < D_; ++d) { acc[OFF_B2 + d] += u[d]; gy[d] = 0.0f; }
+        for (int d = 0; d < D_; d += 2) fma2(rec[IN + 1 + d], rec[IN + 2 + d], us[d], us[d + 1], c0, c1, c0, c1);
+        del = (c0 + c1) * (1.0f - a * a);
+        // gy is accumulated against the STAGED first-layer weights (W1 * kTanhPre); the callers rescale it once at the end
+#pragma unroll
+        for (int i = 0; i < D_; i += 2) fma2s(del, rec[i], rec[i + 1], gy[i], gy[i + 1], gy[i], gy[i + 1]);
+    }
+
+    template <bool EG, class Dose>
+    HODE_HD static void vjp(const float* __restrict__ sp, float t, const Dose& ds, const float (&y)[D_],
+                            const float* k, const float (&l)[D_], float (&gy)[D_], float* acc) {
+        float in[2 * NP1], u[D_], us[D_];
+        inputs(t, ds, y, in);
+        out_cotangent(sp, t, ds, y, k, l, u);
+#pragma unroll
+        for (int d = 0; d < D_; ++d) { acc[OFF_B2 + d] += u[d]; gy[d] = 0.0f; us[d] = u[d] * kTanhPreInv; }
 #pragma unroll 1
         for (int j = 0; j < H; ++j) {
             const float* rec = sp + j * R;
-            float a = rec[IN];
+            float a, del;
+            unit_vjp(rec, in, us, gy, a, del);
 #pragma unroll
-            for (int i = 0; i < IN; ++i) a = fmaf(rec[i], in[i], a);
-            a = tanh_f(a);
-            float c = 0.0f;
-#pragma unroll
-            for (int d = 0; d < D_; ++d) {
-                c = fmaf(rec[IN + 1 + d], u[d], c);
-                acc[OFF_W2 + d * H + j] = fmaf(u[d], a, acc[OFF_W2 + d * H + j]);
-            }
-            const float del = c * (1.0f - a * a);
-#pragma unroll
-            for (int i = 0; i < D_; ++i) gy[i] = fmaf(rec[i], del, gy[i]);
+            for (int d = 0; d < D_; ++d) acc[OFF_W2 + d * H + j] = fmaf(u[d], a, acc[OFF_W2 + d * H + j]);
 #pragma unroll
             for (int i = 0; i < IN; ++i) acc[OFF_W1 + j * IN + i] = fmaf(del, in[i], acc[OFF_W1 + j * IN + i]);
             acc[OFF_B1 + j] += del;
         }
+#pragma unroll
+        for (int i = 0; i < D_; ++i) gy[i] *= kTanhPreInv;
     }
 
 #if HODE_DEVICE_BUILD && defined(__CUDA_ARCH__)
@@ -620,66 +659,64 @@ struct Neural {
     template <bool EG, class Dose>
     HODE_D static void vjp(const float* __restrict__ sp, float t, const Dose& ds, const float (&y)[D_], const float* k,
                            const float (&l)[D_], float (&gy)[D_], NeuralCoop<D_>* cp) {
-        float in[IN], u[D_];
-#pragma unroll
-        for (int i = 0; i < D_; ++i) in[i] = y[i];
-        in[D_] = neural_dose(ds, t);
-        if (k != nullptr) {
-#pragma unroll
-            for (int d = 0; d < D_; ++d) u[d] = l[d] * (1.0f - k[d] * k[d]);
-        } else {
-            float s2[D_];
-            eval(sp, t, ds, y, s2);
-#pragma unroll
-            for (int d = 0; d < D_; ++d) u[d] = l[d] * (1.0f - s2[d] * s2[d]);
-        }
+        using C = NeuralCoop<D_>;
+        float in[2 * NP1], u[D_], us[D_];
+        inputs(t, ds, y, in);
+        out_cotangent(sp, t, ds, y, k, l, u);
         float* S_in = cp->stage;
-        float* S_u = S_in + IN * 32;
-        float* S_del = S_u + D_ * 32;
-        float* S_a = S_del + 32 * 33;
+        float* S_u = S_in + C::SI * 32;
+        float* S_da = S_u + C::SU * 32;
         const int lane = cp->lane;
         __syncwarp();  // the previous call's owner phase has finished reading the staging area
+        // this lane's rows of the staging area: the layer-1 input (with the constant-one bias input) and u, zero padded
+        {
+            float row[C::SI];
 #pragma unroll
-        for (int i = 0; i < IN; ++i) S_in[i * 32 + lane] = in[i];
+            for (int i = 0; i < C::SI; ++i) row[i] = i < 2 * NP1 ? in[i] : 0.0f;
 #pragma unroll
-        for (int d = 0; d < D_; ++d) { S_u[d * 32 + lane] = u[d]; cp->b2[d] += cp->mute ? 0.0f : u[d]; gy[d] = 0.0f; }
+            for (int i = 0; i < C::SI; i += 4) *reinterpret_cast<float4*>(S_in + lane * C::SI + i) = make_float4(row[i], row[i + 1], row[i + 2], row[i + 3]);
+            float ru[C::SU];
 #pragma unroll
-        for (int c = 0; c < NeuralCoop<D_>::NJ; ++c) {
+            for (int d = 0; d < C::SU; ++d) ru[d] = d < D_ ? u[d] : 0.0f;
+#pragma unroll
+            for (int d = 0; d < C::SU; d += 4) *reinterpret_cast<float4*>(S_u + lane * C::SU + d) = make_float4(ru[d], ru[d + 1], ru[d + 2], ru[d + 3]);
+        }
+#pragma unroll
+        for (int d = 0; d < D_; ++d) { cp->b2[d] += cp->mute ? 0.0f : u[d]; gy[d] = 0.0f; us[d] = u[d] * kTanhPreInv; }
+#pragma unroll
+        for (int c = 0; c < C::NJ; ++c) {
             // producer phase: this lane's trajectory, hidden units 32 c .. 32 c + 31
 #pragma unroll 1
             for (int jj = 0; jj < 32; ++jj) {
                 const int j = c * 32 + jj;
                 float del = 0.0f, a = 0.0f;
-                if (j < H) {
-                    const float* rec = sp + j * R;
-                    a = rec[IN];
-#pragma unroll
-                    for (int i = 0; i < IN; ++i) a = fmaf(rec[i], in[i], a);
-                    a = tanh_f(a);
-                    float cc = 0.0f;
-#pragma unroll
-                    for (int d = 0; d < D_; ++d) cc = fmaf(rec[IN + 1 + d], u[d], cc);
-                    del = cc * (1.0f - a * a);
-#pragma unroll
-                    for (int i = 0; i < D_; ++i) gy[i] = fmaf(rec[i], del, gy[i]);
-                }
-                S_del[jj * 33 + lane] = del;
-                S_a[jj * 33 + lane] = a;
+                if (j < H) unit_vjp(sp + j * R, in, us, gy, a, del);
+                *reinterpret_cast<float2*>(S_da + jj * C::SDA + 2 * lane) = make_float2(del, a);
             }
             __syncwarp();
             if (cp->mute) { __syncwarp(); continue; }  // warp-uniform
-            // owner phase: unit j = 32 c + lane, all 32 trajectories of the warp
+            // owner phase: unit j = 32 c + lane, all 32 trajectories of the warp: dW1[j][:] += delta in, db1[j] += delta (the
+            // constant-one input), dW2[:, j] += a u -- vector loads of the staged rows (broadcast), packed FMAs
 #pragma unroll 4
             for (int tt = 0; tt < 32; ++tt) {
-                const float del = S_del[lane * 33 + tt], a = S_a[lane * 33 + tt];
+                const float2 da = *reinterpret_cast<const float2*>(S_da + lane * C::SDA + 2 * tt);
 #pragma unroll
-                for (int i = 0; i < IN; ++i) cp->w1[c][i] = fmaf(del, S_in[i * 32 + tt], cp->w1[c][i]);
-                cp->w1[c][IN] += del;
+                for (int i = 0; i < C::SI; i += 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(S_in + tt * C::SI + i);
+                    fma2s(da.x, v.x, v.y, cp->w1[c][i], cp->w1[c][i + 1], cp->w1[c][i], cp->w1[c][i + 1]);
+                    fma2s(da.x, v.z, v.w, cp->w1[c][i + 2], cp->w1[c][i + 3], cp->w1[c][i + 2], cp->w1[c][i + 3]);
+                }
 #pragma unroll
-                for (int d = 0; d < D_; ++d) cp->w2[c][d] = fmaf(S_u[d * 32 + tt], a, cp->w2[c][d]);
+                for (int d = 0; d < C::SU; d += 4) {
+                    const float4 v = *reinterpret_cast<const float4*>(S_u + tt * C::SU + d);
+                    fma2s(da.y, v.x, v.y, cp->w2[c][d], cp->w2[c][d + 1], cp->w2[c][d], cp->w2[c][d + 1]);
+                    fma2s(da.y, v.z, v.w, cp->w2[c][d + 2], cp->w2[c][d + 3], cp->w2[c][d + 2], cp->w2[c][d + 3]);
+                }
             }
             __syncwarp();
         }
+#pragma unroll
+        for (int i = 0; i < D_; ++i) gy[i] *= kTanhPreInv;
     }
 #endif
 };

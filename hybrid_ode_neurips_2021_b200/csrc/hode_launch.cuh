@@ -449,9 +449,9 @@ __device__ __forceinline__ void coop_init(NeuralCoop<D>& cp, float* stage_base) 
 #pragma unroll
     for (int c = 0; c < NeuralCoop<D>::NJ; ++c) {
 #pragma unroll
-        for (int i = 0; i <= NeuralCoop<D>::IN; ++i) cp.w1[c][i] = 0.0f;
+        for (int i = 0; i < NeuralCoop<D>::SI; ++i) cp.w1[c][i] = 0.0f;
 #pragma unroll
-        for (int d = 0; d < D; ++d) cp.w2[c][d] = 0.0f;
+        for (int d = 0; d < NeuralCoop<D>::SU; ++d) cp.w2[c][d] = 0.0f;
     }
 #pragma unroll
     for (int d = 0; d < D; ++d) cp.b2[d] = 0.0f;

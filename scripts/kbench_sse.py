@@ -16,9 +16,10 @@ ap.add_argument("--D", type=int, default=8)
 ap.add_argument("--obs", type=int, default=40)
 ap.add_argument("--h", type=float, default=0.0625)
 ap.add_argument("--reps", type=int, default=5)
+ap.add_argument("--lib", default=None, help="alternative build of libhode_b200.so (A/B measurements)")
 args = ap.parse_args()
 dev = "cuda:0"
-lib = L.get_lib()
+lib = L.HodeLib(args.lib) if args.lib else L.get_lib()
 B, D, obs = args.patients, args.D, args.obs
 torch.manual_seed(0)
 m = H.RocheODE(D, 1, 14, 1, device=dev)
