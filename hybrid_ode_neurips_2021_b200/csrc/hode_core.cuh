@@ -592,7 +592,7 @@ struct Neural {
         inputs(t, ds, y, in);
 #pragma unroll
         for (int d = 0; d < D_; ++d) out[d] = sp[H * R + d];
-#pragma unroll 2
+#pragma unroll 4
         for (int j = 0; j < H; ++j) {
             const float* rec = sp + j * R;
             const float a = hidden(rec, in);

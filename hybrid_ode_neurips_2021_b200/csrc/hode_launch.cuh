@@ -532,22 +532,31 @@ __device__ __forceinline__ void coop_flush(const SolveArgs& a, int64_t group, Ro
     for (int i = threadIdx.x; i < F::P; i += blockDim.x) atomicAdd(&dst[i], sred[i]);
 }
 
+// CTAs of 128 threads per SM that the reverse sweeps' register budget must allow.  Left alone, ptxas takes 215 registers for
+// the NeuralODE sweep at D = 6 (2 CTAs per SM, issue-active 41 %, `wait` 2.0 per issue); capped at 128 registers it spills
+// 24 bytes and runs 1.29 x faster (34.7 -> 26.9 ms at 131 072 patients).
+template <class F> struct BwdBlocks { static constexpr int value = HODE_BWD_MINBLOCKS; };
+template <int D> struct BwdBlocks<Neural<D>> { static constexpr int value = D <= 6 ? 4 : (D <= 8 ? 3 : HODE_BWD_MINBLOCKS); };
+
 template <class F, int METHOD, bool EG, int ND, bool CP>
-__global__ void __launch_bounds__(128, HODE_BWD_MINBLOCKS) fixed_bwd_kernel(const SolveArgs a, int tiles_per_group) {
-    extern __shared__ float smem[];
+__global__ void __launch_bounds__(128, BwdBlocks<F>::value) fixed_bwd_kernel(const SolveArgs a, int tiles_per_group) {
+    extern __shared__ __align__(16) float smem[];
     float* sp = smem;
-    float* sred = smem + (CP ? 0 : F::SP);
+    float* sred = smem + (CP ? 0 : round4(F::SP));
     const Tile tl = tile_of(a, tiles_per_group);
     if constexpr (!CP) stage_params<F>(a, tl.group, sp);
-    if constexpr (CoopOf<F>::value) {
-        // every lane of every warp runs the sweep (padding lanes on a clamped trajectory with zero gradients): the
-        // parameter-gradient accumulation is a warp-wide cooperation
-        NeuralCoop<F::D> cp;
-        coop_init(cp, sred + F::P);
+    if constexpr (CoopD5<F>::value) {
+        // NeuralODE, and RocheODE at D = 12 (104 ml_net accumulators: 255 registers + spills when kept per thread): every lane
+        // of every warp runs the sweep (padding lanes on a clamped trajectory with zero gradients) -- the parameter-gradient
+        // accumulation is a warp-wide cooperation
+        typename CoopD5<F>::type cp;
+        coop_init(cp, sred + round4(F::P));
         const bool valid = tl.b < a.batch;
         const int64_t idx = tl.group * a.batch + (valid ? tl.b : a.batch - 1);
-        HODE_WITH_DOSE(ND, a, idx, (fixed_bwd_traj<F, METHOD, EG>(a, (const float*)sp, ds, idx, &cp, valid)));
-        coop_flush(a, tl.group, cp, sred);
+        if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (fixed_bwd_traj<F, METHOD, EG>(a, ParamConst(), ds, idx, &cp, valid))); }
+        else { HODE_WITH_DOSE(ND, a, idx, (fixed_bwd_traj<F, METHOD, EG>(a, (const float*)sp, ds, idx, &cp, valid))); }
+        if constexpr (CoopOf<F>::value) coop_flush(a, tl.group, cp, sred);
+        else coop_flush<F, EG>(a, tl.group, cp, sred);
     } else {
         float acc[F::P];
         zero_acc<F>(acc);
@@ -562,19 +571,24 @@ __global__ void __launch_bounds__(128, HODE_BWD_MINBLOCKS) fixed_bwd_kernel(cons
 
 // continuous adjoint of a fixed-grid solve: same shape as the reverse sweep, no tape (fixed_adj_traj)
 template <class F, int METHOD, bool EG, int ND, bool CP>
-__global__ void __launch_bounds__(128, HODE_BWD_MINBLOCKS) fixed_adj_kernel(const SolveArgs a, int tiles_per_group) {
-    extern __shared__ float smem[];
+__global__ void __launch_bounds__(128, BwdBlocks<F>::value) fixed_adj_kernel(const SolveArgs a, int tiles_per_group) {
+    extern __shared__ __align__(16) float smem[];
     float* sp = smem;
-    float* sred = smem + (CP ? 0 : F::SP);
+    float* sred = smem + (CP ? 0 : round4(F::SP));
     const Tile tl = tile_of(a, tiles_per_group);
     if constexpr (!CP) stage_params<F>(a, tl.group, sp);
-    if constexpr (CoopOf<F>::value) {
-        NeuralCoop<F::D> cp;
-        coop_init(cp, sred + F::P);
+    if constexpr (CoopD5<F>::value) {
+        // NeuralODE, and RocheODE at D = 12 (104 ml_net accumulators: 255 registers + spills when kept per thread): every lane
+        // of every warp runs the sweep (padding lanes on a clamped trajectory with zero gradients) -- the parameter-gradient
+        // accumulation is a warp-wide cooperation
+        typename CoopD5<F>::type cp;
+        coop_init(cp, sred + round4(F::P));
         const bool valid = tl.b < a.batch;
         const int64_t idx = tl.group * a.batch + (valid ? tl.b : a.batch - 1);
-        HODE_WITH_DOSE(ND, a, idx, (fixed_adj_traj<F, METHOD, EG>(a, (const float*)sp, ds, idx, &cp, valid)));
-        coop_flush(a, tl.group, cp, sred);
+        if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (fixed_adj_traj<F, METHOD, EG>(a, ParamConst(), ds, idx, &cp, valid))); }
+        else { HODE_WITH_DOSE(ND, a, idx, (fixed_adj_traj<F, METHOD, EG>(a, (const float*)sp, ds, idx, &cp, valid))); }
+        if constexpr (CoopOf<F>::value) coop_flush(a, tl.group, cp, sred);
+        else coop_flush<F, EG>(a, tl.group, cp, sred);
     } else {
         float acc[F::P];
         zero_acc<F>(acc);
@@ -860,7 +874,7 @@ inline int set_smem(K kernel, size_t bytes) {
 
 template <class F>
 constexpr size_t coop_stage_floats() {
-    if constexpr (CoopOf<F>::value) return NeuralCoop<F::D>::kStageFloats;
+    if constexpr (CoopD5<F>::value) return CoopD5<F>::type::kStageFloats;
     else return 0;
 }
 
@@ -959,7 +973,7 @@ int launch_fixed_bwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st
     const bool eg = cfg.expert_grads != 0;
 #define HODE_FB(M, EG, ND, CP)                                                                                        \
     do {                                                                                                           \
-        const size_t sh_ = ((CP ? 0 : F::SP) + F::P + coop_stage_floats<F>() * (size_t)(threads / 32)) * sizeof(float); \
+        const size_t sh_ = ((CP ? 0 : round4(F::SP)) + round4(F::P) + coop_stage_floats<F>() * (size_t)(threads / 32)) * sizeof(float); \
         if (sh_ > 48 * 1024)                                                                                       \
             cudaFuncSetAttribute(fixed_bwd_kernel<F, M, EG, ND, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_); \
         fixed_bwd_kernel<F, M, EG, ND, CP><<<(unsigned)nblk, threads, sh_, st>>>(a, tiles);                        \
@@ -994,7 +1008,7 @@ int launch_fixed_adj(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st
     const bool eg = cfg.expert_grads != 0;
 #define HODE_FA(M, EG, ND, CP)                                                                                        \
     do {                                                                                                           \
-        const size_t sh_ = ((CP ? 0 : F::SP) + F::P + coop_stage_floats<F>() * (size_t)(threads / 32)) * sizeof(float); \
+        const size_t sh_ = ((CP ? 0 : round4(F::SP)) + round4(F::P) + coop_stage_floats<F>() * (size_t)(threads / 32)) * sizeof(float); \
         if (sh_ > 48 * 1024)                                                                                       \
             cudaFuncSetAttribute(fixed_adj_kernel<F, M, EG, ND, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh_); \
         fixed_adj_kernel<F, M, EG, ND, CP><<<(unsigned)nblk, threads, sh_, st>>>(a, tiles);                        \
