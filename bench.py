@@ -393,16 +393,21 @@ def run_ours(args):
         and the packed gradients are read back."""
         fg.zero_()
         main = torch.cuda.current_stream(dev)
-        keep = []
-        for (y0_c, a_c, x_c, m_c) in chunks:
-            with torch.cuda.stream(copy_stream):
+        # all copies are queued on the copy stream first (one event per mini-batch): set_action's host read of the dose count
+        # would otherwise hold back the NEXT mini-batch's copies until the current one has landed, leaving the copy engine idle
+        # between mini-batches
+        staged = []
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_stream(main)
+            for (y0_c, a_c, x_c, m_c) in chunks:
                 dev_c = [t.to(dev, non_blocking=True) for t in (y0_c, a_c, x_c, m_c)]
                 ready = torch.cuda.Event()
                 ready.record(copy_stream)
+                staged.append((dev_c, ready))
+        for dev_c, ready in staged:
             main.wait_event(ready)
             for t in dev_c:
                 t.record_stream(main)
-            keep.append(dev_c)
             z = dev_c[0].requires_grad_(True)
             loss = dec.loss(z, dev_c[1], dev_c[2], dev_c[3], n_norm=B_global)
             loss.backward()
