@@ -8,7 +8,13 @@ Semantics kept from torchdiffeq 0.2.2: ``odeint(func, y0, t, *, rtol=1e-7, atol=
 event_fn=None) -> Tensor[len(t), *y0.shape]``; default method ``dopri5``; fixed-grid options ``step_size`` /
 ``perturb``; adaptive options ``first_step, safety, ifactor, dfactor, max_num_steps``; unknown option keys warn;
 solver failures raise ``AssertionError`` with torchdiffeq's messages.  Gradients are the discrete backprop through
-the accepted steps (what autograd gives through torchdiffeq's ``odeint``), with constant step sizes.
+the accepted steps (what autograd gives through torchdiffeq's ``odeint``), with constant step sizes.  One known
+difference: torchdiffeq computes dopri5's FIRST step size from ``y0`` and ``f(t0, y0)`` inside the
+graph, so its autograd gradient carries a term through that step size; the kernels treat every step size -- the first
+included -- as a constant.  Measured against the oracle with the differentiable first step: 2e-6 .. 4e-5 norm-wise on
+``dL/dy0`` / the encoder gradients at rtol 1e-7 (``tests/test_training_fixture.py``), bounded at 5e-3 by
+``test_first_step_gradient_term_is_small`` for loose tolerances; pass ``options={'first_step': h}`` to remove the term
+on both sides.
 
 There is no generic path: ``func`` must be one of the hybrid-ODE vector fields (``TypeError`` otherwise) and ``y0``
 must live on a CUDA device (``RuntimeError`` otherwise).  Extensions (all optional, in ``options``):

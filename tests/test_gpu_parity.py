@@ -468,6 +468,34 @@ def test_group_larger_than_one_cta_runs_as_a_cluster(D, B):
                              adjoint_options={"norm": "seminorm"})
 
 
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_model_on_a_gpu_that_is_not_the_current_device():
+    """The reference's default device is cuda:1 (global_config.py:7) and nothing calls torch.cuda.set_device: every C-ABI call
+    must run under a device guard for the tensors' device (stream, constant-bank lease and launches on THAT device)."""
+    assert torch.cuda.current_device() == 0
+    dev1 = "cuda:1"
+    D, B, obs = 8, 64, 40
+    o = oracle_roche(D, 0, True)
+    y0, a, x, mask = make_cohort(B, D, obs=obs, seed=31)
+    outs, sd = [], None
+    for dev in (DEV, dev1):
+        dec = H.RocheExpertDecoder(obs, D, 1, 14, 1, method="rk4", device=dev, solver_options={"step_size": 0.125})
+        dec.ode.load_state_dict(o.state_dict())
+        if sd is None:
+            sd = {k: v.cpu() for k, v in dec.state_dict().items()}
+        dec.load_state_dict(sd)  # same read-out weights on both devices
+        z = y0.clone().to(dev).requires_grad_(True)
+        loss = dec.loss(z, a.to(dev), x.to(dev), mask.to(dev))
+        loss.backward()
+        with torch.no_grad():
+            h5 = H.odeint(dec.ode, y0.to(dev), torch.arange(0, 15.0, device=dev), rtol=1e-5, atol=1e-6, method="dopri5")
+        assert z.grad.device == torch.device(dev) and h5.device == torch.device(dev)
+        outs.append((loss.item(), z.grad.cpu(), dec.ode.ml_net[0].weight.grad.cpu(), h5.cpu()))
+    assert torch.cuda.current_device() == 0  # the guard restores the caller's device
+    assert outs[0][0] == outs[1][0] and torch.equal(outs[0][1], outs[1][1]) and torch.equal(outs[0][3], outs[1][3])
+    assert relerr(outs[1][2], outs[0][2]) < 1e-5  # atomics: order of the CTA partial sums
+
+
 def test_two_doses_per_patient():
     D, B = 6, 9
     o, m = build_pair(D)
