@@ -7,7 +7,7 @@ generator that feeds the path.
 Importing this package does not load CUDA; the shared library is loaded on first solver call and its absence is a
 hard error (there is no CPU fallback).
 """
-from .solver import odeint, odeint_adjoint, odeint_ensemble, odeint_sse, EnsembleParams, last_solve_info, fixed_grid_points  # noqa: F401
+from .solver import odeint, odeint_adjoint, odeint_ensemble, odeint_sse, EnsembleParams, last_solve_info, last_adjoint_solve_info, fixed_grid_points  # noqa: F401
 from .model import RocheODE, NeuralODE, RocheExpertDecoder, RochConfig  # noqa: F401
 from .real import RocheODEReal, NeuralODEReal, NeuralODEReal2nd, DecoderReal  # noqa: F401
 from .loss import masked_sse, decode_sse_loss  # noqa: F401

@@ -86,6 +86,8 @@ static int dispatch(Op op, const hode_cfg& cfg, const SolveArgs& a, cudaStream_t
     if (rc == 0) return HODE_OK;
     if (rc == -2) return fail(HODE_ERR_UNSUPPORTED, "batch-coupled dopri5 group larger than %s%lld trajectories", "",
                               op == OP_DOPRI5_ADJ ? (long long)512 : (long long)hode_dopri5_max_batch(&cfg));
+    if (rc == -4) return fail(HODE_ERR_UNSUPPORTED, "the adaptive adjoint with torchdiffeq's default mixed norm is built for the batch-coupled controller and "
+                                                    "the RocheODE field up to latent_dim 8; pass adjoint_options={'norm': 'seminorm'} (HODE_FLAG_ADJ_SEMINORM)%s%lld", "", 0);
     if (rc == -3) return fail(HODE_ERR_UNSUPPORTED, "the adaptive adjoint of the NeuralODE field is built for the batch-coupled controller only%s%lld", "", 0);
     if (rc == -1 && op == OP_FIXED_FWD_SSE)
         return fail(HODE_ERR_UNSUPPORTED, "no fused solve + read-out kernel for this field / method / obs / n_dose / parameter-set "
@@ -268,9 +270,6 @@ int32_t hode_dopri5_adjoint(const hode_cfg* cfg, int64_t n_groups, int64_t batch
     int rc = check_common(cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, n_t);
     if (rc) return rc;
     if (cfg->method != HODE_DOPRI5) return fail(HODE_ERR_ARG, "hode_dopri5_adjoint called with a fixed-grid method (use hode_fixed_adjoint)");
-    if (!(cfg->flags & HODE_FLAG_ADJ_SEMINORM))
-        return fail(HODE_ERR_UNSUPPORTED, "the adaptive adjoint is built for torchdiffeq's 'seminorm' (adjoint_options={'norm': 'seminorm'}, "
-                                          "HODE_FLAG_ADJ_SEMINORM): the default mixed norm also controls the step size by the parameter adjoints");
     if (!t_eval || !stats || n_param_sets < 1 || !grad_params) return fail(HODE_ERR_ARG, "NULL / bad t_eval, stats or grad_params");
     const int64_t P = hode_param_count(cfg);
     cudaError_t e = cudaMemsetAsync(grad_params, 0, sizeof(float) * (size_t)P * (size_t)n_param_sets, (cudaStream_t)stream);
@@ -282,6 +281,7 @@ int32_t hode_dopri5_adjoint(const hode_cfg* cfg, int64_t n_groups, int64_t batch
     a.n_param_sets = n_param_sets;
     a.t_eval_d = t_eval; a.n_t = n_t; a.h_out = const_cast<float*>(h); a.grad_h = grad_h;
     a.stats = stats; a.grad_y0 = grad_y0; a.grad_params = grad_params;
+    a.adj_mixed = (cfg->flags & HODE_FLAG_ADJ_SEMINORM) ? 0 : 1;  // torchdiffeq's default is the mixed norm
     return dispatch(OP_DOPRI5_ADJ, *cfg, a, (cudaStream_t)stream);
 }
 

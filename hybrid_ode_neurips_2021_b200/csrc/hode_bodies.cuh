@@ -51,6 +51,7 @@ struct SolveArgs {
     float* sse_grad_h;
     float* sse_grad_w;
     float* sse_grad_b;
+    int adj_mixed = 0;  // adaptive adjoint: 1 = torchdiffeq's default mixed norm (the parameter adjoints take part in the error control)
     // continuous adjoint: `grid` holds the n_t - 1 reversed-time interval grids back to back (n_grid points in total),
     // adj_cnt[iv] = number of grid points of interval iv (iv = 0 is the LAST output interval)
     const int32_t* adj_cnt;
@@ -992,6 +993,329 @@ HODE_HD void dopri5_adj_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds
             } else {
                 ++nrej;
             }
+            dt = optimal_step(dt, ratio, safety, ifactor, dfactor);
+        }
+    }
+    if (leader) {
+        hode_stats st;
+        st.accepted = nacc; st.rejected = nrej; st.nfe = 0; st.status = status;
+        a.stats[ctrl] = st;
+    }
+    if (!valid) return;
+    float g0[D];
+    load_vec<D>(a.grad_h + idx * D, g0);
+#pragma unroll
+    for (int d = 0; d < D; ++d) lam[d] += g0[d];
+    if (poisoned) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) lam[d] = nanf("");
+    }
+    store_vec<D>(a.grad_y0 + idx * D, lam);
+}
+
+
+// ==============================================================================================================
+// Adaptive continuous adjoint with torchdiffeq's DEFAULT (mixed) adjoint norm -- batch-coupled controller, fields with
+// per-thread parameter accumulators (RocheODE, D <= 8).
+// The solver state of OdeintAdjointMethod.backward is the tuple (vjp_t, y, adj_y, *adj_params) and the step-size controller
+// sees  max(|vjp_t| = 0, rms(y-part), rms(adj_y-part), rms(part of parameter tensor k) for every k)  of the scaled error --
+// so every ATTEMPT needs, for every parameter, the group-summed error estimate  E = ds sum_m c_err[m] P_m  and the group-summed
+// increment  S = ds sum_m c_sol[m] P_m  (P_m = (df/dtheta(Y_m))^T A_m summed over the group's trajectories), and the tolerance
+// uses the accumulated parameter adjoint g of the GROUP (it carries over from interval to interval):
+//   per stage: the full VJP into a scratch vector, folded into E and S with the stage's weights;
+//   per attempt: one vector reduction over the group (Comm::sum_vec) -> thread `leader` forms the per-tensor norms;
+//   accepted step inside an interval: g += S;  last step of an interval: g += ds sum_m w_m(x) P_m from a second pass with
+//   the dense-output weights (exactly how tde interpolates the parameter components back to the output time);
+//   _select_initial_step of every interval includes the parameter parts of d0, d1, d2 as well.
+// `pc`: group-level state in memory every thread of the group can read: g [P], q [2 P] (reduction results), r [4] (scalars).
+// ==============================================================================================================
+struct ParamCtl {
+    float* g;
+    float* q;
+    float* r;
+};
+
+// max over the parameter TENSORS of rms(v[tensor] ) where v[k] = num[k] / (atol + rtol * max(|ga[k]|, |gb[k]|)):
+// the 13 expert scalars (and theta_1 / theta_2) are tensors of one element, ml_net.weight and ml_net.bias are the other two
+template <class F, bool EG>
+HODE_HD float param_tensor_norm(const float* num, const float* ga, const float* gb, float scale_num, float rtol, float atol) {
+    float worst = 0.0f;
+    auto term = [&](int k) {
+        const float tol = fmaf(rtol, nan_maxf(fabsf(ga[k]), fabsf(gb[k])), atol);
+        const float v = (num[k] * scale_num) / tol;
+        return v * v;
+    };
+    if (EG) {
+        for (int k = 0; k < R_NSCALAR; ++k) worst = nan_maxf(worst, sqrtf(term(k)));
+        if (F::ABLATE) {
+            worst = nan_maxf(worst, sqrtf(term(F::OFF_TH)));
+            worst = nan_maxf(worst, sqrtf(term(F::OFF_TH + 1)));
+        }
+    }
+    if (F::ML > 0) {
+        float sw = 0.0f, sb = 0.0f;
+        for (int k = 0; k < F::ML * F::D; ++k) sw += term(F::OFF_W + k);
+        for (int k = 0; k < F::ML; ++k) sb += term(F::OFF_B + k);
+        worst = nan_maxf(worst, sqrtf(sw / (float)(F::ML * F::D)));
+        worst = nan_maxf(worst, sqrtf(sb / (float)F::ML));
+    }
+    return worst;
+}
+
+template <class F, bool EG, class PS, class Dose, class Comm, class KS>
+HODE_HD void dopri5_adj_mixed_traj(const SolveArgs& a, Comm& cm, PS sp, const Dose& ds, KS& R, int64_t idx, bool valid,
+                                   int64_t ctrl, bool leader, float count, ParamCtl pc, int tid, int nthreads) {
+    constexpr int D = F::D, P = F::P;
+    constexpr bool UNROLL = false;
+    static_assert(KS::kDynamic, "rolled stage loops need rows that can be indexed at run time");
+    const int64_t n_traj = a.n_groups * a.batch;
+    const float rtol = a.rtol_f, atol = a.atol_f;
+    const float inv_count = 1.0f / count;
+    const float safety = (float)a.safety, ifactor = (float)a.ifactor, dfactor = (float)a.dfactor;
+    const int max_steps = (int)(a.max_num_steps < 0x7fffffffLL ? a.max_num_steps : 0x7fffffffLL);
+    const int attempt_cap = (int)(a.attempt_cap < 0x7fffffffLL ? a.attempt_cap : 0x7fffffffLL);
+    int nacc = 0, nrej = 0, status = HODE_SOLVE_OK, attempts = 0;
+    float lam[D], y[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) lam[d] = 0.0f;
+    const bool poisoned = !F::params_ok(sp);
+    for (int k = tid; k < P; k += nthreads) pc.g[k] = 0.0f;
+    cm.sync();
+
+    float ES[2 * P], pm[P];  // E = ES[0 .. P), S = ES[P .. 2 P)
+    auto zero_pm = [&]() {
+#pragma unroll 1
+        for (int k = 0; k < P; ++k) pm[k] = 0.0f;
+    };
+    auto fold = [&](float we, float ws) {  // E += we pm, S += ws pm
+#pragma unroll 1
+        for (int k = 0; k < P; ++k) { ES[k] = fmaf(we, pm[k], ES[k]); ES[P + k] = fmaf(ws, pm[k], ES[P + k]); }
+    };
+    auto zero_es = [&]() {
+#pragma unroll 1
+        for (int k = 0; k < 2 * P; ++k) ES[k] = 0.0f;
+    };
+
+    for (int iv = 0; iv + 1 < a.n_t && status == HODE_SOLVE_OK; ++iv) {
+        const int i = a.n_t - 1 - iv;
+        {
+            float g[D];
+            load_vec<D>(a.grad_h + ((int64_t)i * n_traj + idx) * D, g);
+            load_vec<D>(a.h_out + ((int64_t)i * n_traj + idx) * D, y);
+#pragma unroll
+            for (int d = 0; d < D; ++d) lam[d] += valid ? g[d] : 0.0f;
+        }
+        double s0 = -a.t_eval_d[i];
+        const double s_end = -a.t_eval_d[i - 1];
+        float flast[D], glast[D];
+        F::eval(sp, -(float)s0, ds, y, flast);
+        zero_pm();
+        F::template vjp<EG>(sp, -(float)s0, ds, y, (const float*)flast, lam, glast, (float*)pm);
+        R.store(0, flast);
+        R.store(7, glast);
+        // ---- _select_initial_step on the augmented state with the mixed norm ------------------------------------------
+        double dt;
+        if (a.first_step > 0.0) {
+            dt = a.first_step;
+        } else {
+            float sy[D], sa[D], q0 = 0.0f, q1 = 0.0f, r0 = 0.0f, r1 = 0.0f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                sy[d] = atol + fabsf(y[d]) * rtol;
+                sa[d] = atol + fabsf(lam[d]) * rtol;
+                const float u0 = y[d] / sy[d], u1 = flast[d] / sy[d], v0 = lam[d] / sa[d], v1 = glast[d] / sa[d];
+                q0 += u0 * u0; q1 += u1 * u1; r0 += v0 * v0; r1 += v1 * v1;
+            }
+            if (!valid) { q0 = q1 = r0 = r1 = 0.0f; }
+            cm.sum2(q0, q1);
+            cm.sum2(r0, r1);
+            // parameter parts: d0 <- g / scale, d1 <- P(s0) / scale with scale = atol + rtol |g|
+            zero_es();
+            if (valid) fold(1.0f, 0.0f);
+            cm.template sum_vec<2 * P>(ES, pc.q);  // q[0 .. P) = P(s0) summed over the group
+            if (leader) {
+                pc.r[0] = param_tensor_norm<F, EG>(pc.g, pc.g, pc.g, 1.0f, rtol, atol);
+                pc.r[1] = param_tensor_norm<F, EG>(pc.q, pc.g, pc.g, 1.0f, rtol, atol);
+            }
+            cm.sync();
+            const float d0 = nan_maxf(nan_maxf(sqrtf(q0 / count), sqrtf(r0 / count)), pc.r[0]);
+            const float d1 = nan_maxf(nan_maxf(sqrtf(q1 / count), sqrtf(r1 / count)), pc.r[1]);
+            float h0;
+            if (d0 < 1e-5f || d1 < 1e-5f) h0 = 1e-6f;
+            else h0 = (0.01f * d0) / d1;
+            float y1[D], a1[D], f1[D], g1[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) { y1[d] = y[d] - h0 * flast[d]; a1[d] = lam[d] + h0 * glast[d]; }
+            const float th = -add_rn((float)s0, h0);
+            F::eval(sp, th, ds, y1, f1);
+            // P at the probe point minus P(s0): fold with weights (+1 probe, -1 start) into E
+            zero_es();
+            if (valid) fold(-1.0f, 0.0f);
+            zero_pm();
+            F::template vjp<EG>(sp, th, ds, y1, (const float*)f1, a1, g1, (float*)pm);
+            if (valid) fold(1.0f, 0.0f);
+            float q2 = 0.0f, r2 = 0.0f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const float u = (f1[d] - flast[d]) / sy[d], v = (g1[d] - glast[d]) / sa[d];
+                q2 += u * u; r2 += v * v;
+            }
+            if (!valid) { q2 = r2 = 0.0f; }
+            cm.sum2(q2, r2);
+            cm.sync();  // r[0 .. 1] have been read by every thread
+            cm.template sum_vec<2 * P>(ES, pc.q);
+            if (leader) pc.r[2] = param_tensor_norm<F, EG>(pc.q, pc.g, pc.g, 1.0f, rtol, atol);
+            cm.sync();
+            const float d2 = nan_maxf(nan_maxf(sqrtf(q2 / count), sqrtf(r2 / count)), pc.r[2]) / h0;
+            float h1;
+            if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
+            else h1 = powf(0.01f / ((d2 > d1) ? d2 : d1), 0.2f);
+            dt = (double)nan_minf(100.0f * h0, h1);
+        }
+        int n_steps = 0;
+        bool first = true;
+        bool done = false;
+        while (!done) {
+            if (poisoned) { status = HODE_SOLVE_NONFINITE; break; }
+            if (n_steps >= max_steps || attempts >= attempt_cap) { status = HODE_SOLVE_MAX_STEPS; break; }
+            if (!(s0 + dt > s0)) { status = HODE_SOLVE_DT_UNDERFLOW; break; }
+            const double s1 = s0 + dt;
+            const float s0f = (float)s0, dsf = (float)dt, s1f = (float)s1;
+            float y1[D], a1[D], ey[D], ea[D];
+#pragma unroll
+            for (int d = 0; d < D; ++d) { ey[d] = 0.0f; ea[d] = 0.0f; }
+            R.load(0, flast);
+            R.load(7, glast);
+            // parameter part of stage 0 (k_1 of the step: the FSAL evaluation, recomputed for its parameter VJP)
+            zero_es();
+            {
+                float gdead[D];
+                zero_pm();
+                F::template vjp<EG>(sp, -(first ? s0f : t_prev(s0f)), ds, y, (const float*)flast, lam, gdead, (float*)pm);
+                fold(mul_rn(dsf, d5_cerr(0)), mul_rn(dsf, d5_beta(5, 0)));
+            }
+            stage_up<UNROLL, 0, 6>([&](auto il) {
+                float ts, we, ws;
+                stage_switch<true, 6>(il, [&](auto ic) {
+                    const int m = ic;
+                    d5_stage_input<D, true>(R, m, -dsf, y, flast, y1, 0);
+                    d5_stage_input<D, true>(R, m, dsf, lam, glast, a1, 7);
+                    const float ce = mul_rn(dsf, d5_cerr(m));
+                    v_axpy<D>(ey, ce, flast, ey);
+                    v_axpy<D>(ea, ce, glast, ea);
+                    ts = d5_stage_time(m, s0f, dsf, s1f);
+                    we = mul_rn(dsf, d5_cerr(m + 1));
+                    ws = (m + 1 < 6) ? mul_rn(dsf, d5_beta(5, m + 1)) : 0.0f;
+                });
+                F::eval(sp, -ts, ds, y1, flast);
+                zero_pm();
+                F::template vjp<EG>(sp, -ts, ds, y1, (const float*)flast, a1, glast, (float*)pm);
+                fold(we, ws);
+                R.store((int)il + 1, flast);
+                R.store((int)il + 8, glast);
+            });
+            {
+                const float ce = mul_rn(dsf, d5_cerr(6));
+                v_axpy<D>(ey, ce, flast, ey);
+                v_axpy<D>(ea, ce, glast, ea);
+            }
+            float ssy = 0.0f, ssa = 0.0f;
+#pragma unroll
+            for (int d = 0; d < D; ++d) {
+                const float qy = div_tol(ey[d], fmaf(rtol, nan_maxf(fabsf(y[d]), fabsf(y1[d])), atol));
+                const float qa = div_tol(ea[d], fmaf(rtol, nan_maxf(fabsf(lam[d]), fabsf(a1[d])), atol));
+                ssy = fmaf(qy, qy, ssy);
+                ssa = fmaf(qa, qa, ssa);
+            }
+            if (!valid) { ssy = 0.0f; ssa = 0.0f; zero_es(); }
+            cm.sum2(ssy, ssa);
+            cm.template sum_vec<2 * P>(ES, pc.q);  // q[0 .. P) = E, q[P .. 2 P) = S, summed over the group
+            if (leader) {
+                // tolerance of parameter k: atol + rtol max(|g_k|, |g_k + S_k|); r[3] doubles as scratch-free: g + S is formed on the fly
+                float worst = 0.0f;
+                {
+                    // reuse q[P .. 2P) in place as g + S for the tolerance, restore nothing: S is re-derived as (g + S) - g below
+                    for (int k = 0; k < P; ++k) pc.q[P + k] = pc.g[k] + pc.q[P + k];
+                    worst = param_tensor_norm<F, EG>(pc.q, pc.g, pc.q + P, 1.0f, rtol, atol);
+                }
+                pc.r[3] = worst;
+            }
+            cm.sync();
+            const float ratio = nan_maxf(nan_maxf(fast_sqrt(ssy * inv_count), fast_sqrt(ssa * inv_count)), pc.r[3]);
+            const bool accept = ratio <= 1.0f;
+#if !HODE_DEVICE_BUILD
+            if (leader && getenv("HODE_TRACE")) printf("[mixed] s0 %.9g dt %.9g ratio_y %.6g ratio_a %.6g ratio_p %.6g acc %d\n", s0, dt, (double)sqrtf(ssy * inv_count), (double)sqrtf(ssa * inv_count), (double)pc.r[3], (int)accept);
+#endif
+            ++attempts; ++n_steps;
+            if (accept) {
+                ++nacc;
+                const bool last = s_end <= s1;
+                const float x = last ? (float)((s_end - s0) / (s1 - s0)) : 1.0f;
+                if (!last) {
+                    for (int k = tid; k < P; k += nthreads) pc.g[k] = pc.q[P + k];  // g <- g + S
+                    R.store(0, flast);  // FSAL
+                    R.store(7, glast);
+#pragma unroll
+                    for (int d = 0; d < D; ++d) { y[d] = y1[d]; lam[d] = a1[d]; }
+                    s0 = s1;
+                    first = false;
+                } else {
+                    // parameter components interpolated to s_end through the dense-output weights: second pass over the stages
+                    zero_es();
+                    stage_up<UNROLL, 0, 7>([&](auto il) {
+                        float Ym[D], Am[D], frow[D], gdead[D], ts, w;
+                        stage_switch<true, 7>(il, [&](auto ic) {
+                            const int m = ic;
+                            w = d5_dense_weight(m, x);
+                            if (m == 0) {
+#pragma unroll
+                                for (int d = 0; d < D; ++d) { Ym[d] = y[d]; Am[d] = lam[d]; }
+                                ts = first ? s0f : t_prev(s0f);
+                            } else {
+                                d5_stage_input_rows<D, true>(R, m - 1, -dsf, y, Ym, 0);
+                                d5_stage_input_rows<D, true>(R, m - 1, dsf, lam, Am, 7);
+                                ts = d5_stage_time(m - 1, s0f, dsf, s1f);
+                            }
+                        });
+                        R.load((int)il, frow);
+                        zero_pm();
+                        F::template vjp<EG>(sp, -ts, ds, Ym, (const float*)frow, Am, gdead, (float*)pm);
+                        fold(mul_rn(w, dsf), 0.0f);
+                    });
+                    if (!valid) zero_es();
+                    cm.template sum_vec<2 * P>(ES, pc.q);
+                    for (int k = tid; k < P; k += nthreads) pc.g[k] += pc.q[k];
+                    // dense output of the state adjoint at s_end
+                    float m_[D], g0[D];
+#pragma unroll
+                    for (int d = 0; d < D; ++d) m_[d] = 0.0f;
+                    range_up<UNROLL, 7>(0, 7, [&](int mm) {
+                        float row[D];
+                        R.load(7 + mm, row);
+                        const float c = mul_rn(dsf, d5_cmid(mm));
+#pragma unroll
+                        for (int d = 0; d < D; ++d) m_[d] = fmaf(row[d], c, m_[d]);
+                    });
+                    R.load(7, g0);
+                    const float x2 = x * x, x3 = x2 * x, x4 = x3 * x;
+#pragma unroll
+                    for (int d = 0; d < D; ++d) {
+                        const float amid = lam[d] + m_[d], f0 = g0[d], f1 = glast[d];
+                        const float ca = 2.0f * dsf * (f1 - f0) - 8.0f * (a1[d] + lam[d]) + 16.0f * amid;
+                        const float cb = dsf * (5.0f * f0 - 3.0f * f1) + 18.0f * lam[d] + 14.0f * a1[d] - 32.0f * amid;
+                        const float cc = dsf * (f1 - 4.0f * f0) - 11.0f * lam[d] - 5.0f * a1[d] + 16.0f * amid;
+                        float tot = lam[d] + x * (dsf * f0);
+                        tot = tot + x2 * cc;
+                        tot = tot + x3 * cb;
+                        tot = tot + x4 * ca;
+                        lam[d] = tot;
+                    }
+                    done = true;
+                }
+            } else {
+                ++nrej;
+            }
+            cm.sync();  // g (and q) settled before the next attempt reads / overwrites them
             dt = optimal_step(dt, ratio, safety, ifactor, dfactor);
         }
     }

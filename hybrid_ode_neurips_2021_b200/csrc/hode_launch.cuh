@@ -89,6 +89,27 @@ struct CommCta {
         return __any_sync(0xffffffffu, p) != 0;
     }
     __device__ __forceinline__ bool all_done(bool done) { return done; }  // CTA-uniform by construction
+    // vector reduction for the mixed adjoint norm: out[k] = sum over the CTA of v[k], visible to every thread on return
+    float* vbuf = nullptr;  // [nwarps][N]
+    template <int N>
+    __device__ __forceinline__ void sum_vec(const float (&v)[N], float* out) {
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll 1
+        for (int k = 0; k < N; ++k) {
+            float x = v[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if (lane == 0) vbuf[wid * N + k] = x;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < N; k += blockDim.x) {
+            float t = 0.0f;
+            for (int w = 0; w < nwarps; ++w) t += vbuf[w * N + k];
+            out[k] = t;
+        }
+        __syncthreads();
+    }
+    __device__ __forceinline__ void sync() { __syncthreads(); }
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -797,6 +818,13 @@ __global__ void __launch_bounds__(128, D5Store<F>::kBwdMinBlocks) dopri5_bwd_ker
 // trajectory (flat launch).  14 rows per thread always live in shared memory (7 field values + 7 adjoint derivatives).
 // Parameter gradients: warp-cooperative accumulators where the field has them and the warp is converged (batch-coupled
 // groups: accept / reject is CTA-uniform); per-thread accumulators otherwise.
+// fields for which the mixed-norm adaptive adjoint is built: per-thread parameter accumulators (RocheODE up to D = 8)
+template <class F> struct MixedOk { static constexpr bool value = F::kAccInRegs && !CoopD5<F>::value; };
+template <class F>
+constexpr size_t mixed_floats(int threads) {
+    return (size_t)round4(F::P) + round4(2 * F::P) + 4 + (size_t)(threads / 32) * 2 * F::P;
+}
+
 template <class F, bool PER_TRAJ, bool EG, int ND, int MAXT, bool CP>
 __global__ void __launch_bounds__(MAXT, MAXT <= 128 ? 2 : 1) dopri5_adj_kernel(const SolveArgs a, int tiles_per_group) {
     extern __shared__ __align__(16) float smem[];
@@ -819,6 +847,20 @@ __global__ void __launch_bounds__(MAXT, MAXT <= 128 ? 2 : 1) dopri5_adj_kernel(c
         if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_adj_traj<F, EG, true>(a, cm, ParamConst(), ds, R, idx, valid, ctrl, leader, count, accp))); }
         else { HODE_WITH_DOSE(ND, a, idx, (dopri5_adj_traj<F, EG, true>(a, cm, (const float*)sp, ds, R, idx, valid, ctrl, leader, count, accp))); }
     };
+    if constexpr (MixedOk<F>::value && !PER_TRAJ) {
+        if (a.adj_mixed) {  // torchdiffeq's default adjoint norm: the group's parameter adjoint lives in shared memory
+            float* pg = coop_stage;  // [P] g, [2 P] reduction results, [4] scalars, then the per-warp partials of sum_vec
+            ParamCtl pc{pg, pg + round4(F::P), pg + round4(F::P) + round4(2 * F::P)};
+            CommCta cm{red, (int)(blockDim.x >> 5), 0};
+            cm.vbuf = pc.r + 4;
+            if constexpr (CP) { HODE_WITH_DOSE(ND, a, idx, (dopri5_adj_mixed_traj<F, EG>(a, cm, ParamConst(), ds, R, idx, valid, ctrl, leader, count, pc, (int)threadIdx.x, (int)blockDim.x))); }
+            else { HODE_WITH_DOSE(ND, a, idx, (dopri5_adj_mixed_traj<F, EG>(a, cm, (const float*)sp, ds, R, idx, valid, ctrl, leader, count, pc, (int)threadIdx.x, (int)blockDim.x))); }
+            __syncthreads();
+            const int set = a.pset ? a.pset[tl.group] : 0;
+            for (int k = threadIdx.x; k < F::P; k += blockDim.x) atomicAdd(a.grad_params + (int64_t)set * F::P + k, pc.g[k]);
+            return;
+        }
+    }
     if constexpr (!PER_TRAJ && CoopD5<F>::value) {
         typename CoopD5<F>::type cp;
         coop_init(cp, coop_stage);
@@ -1172,12 +1214,14 @@ int launch_dopri5_adj(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t s
     const bool eg = cfg.expert_grads != 0;
     if (!a_in.per_traj && a_in.batch > HODE_DOPRI5_MAX_THREADS) return -2;
     if (a_in.per_traj && CoopOf<F>::value) return -3;  // NeuralODE: cooperative accumulators need converged warps
+    if (a_in.adj_mixed && (a_in.per_traj || !MixedOk<F>::value)) return -4;  // mixed norm: batch-coupled RocheODE, D <= 8
     const SolveArgs a = a_in.per_traj ? flatten(a_in) : a_in;
     const int threads = a.per_traj ? (a.batch >= 128 ? 128 : round_up32(a.batch)) : round_up32(a.batch);
     const int tiles = a.per_traj ? (int)((a.batch + threads - 1) / threads) : 1;
     const int64_t nblk = a.n_groups * tiles;
     size_t coop_floats = 0;
     if constexpr (CoopD5<F>::value) coop_floats = (size_t)CoopD5<F>::type::kStageFloats * (size_t)(threads / 32);
+    if constexpr (MixedOk<F>::value) { if (a.adj_mixed) coop_floats = mixed_floats<F>(threads); }
     const size_t sh_base = (size_t)128 + round4(F::P) + (size_t)14 * F::D * threads + coop_floats;
 #define HODE_DA(PT, EG, ND, MAXT, CP)                                                                              \
     do {                                                                                                           \

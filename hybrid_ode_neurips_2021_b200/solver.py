@@ -33,7 +33,7 @@ from . import _lib as L
 from . import ops
 
 __all__ = ["odeint", "odeint_adjoint", "odeint_ensemble", "odeint_sse", "EnsembleParams", "SolveInfo", "last_solve_info",
-           "fixed_grid_points"]
+           "last_adjoint_solve_info", "fixed_grid_points"]
 
 EXPERT_NAMES = (
     "HillCure", "HillPatho", "ec50_patho", "emax_patho", "k_dexa", "k_discure_immunereact", "k_discure_immunity",
@@ -394,7 +394,7 @@ class _Dopri5Solve(torch.autograd.Function):
 class _Dopri5AdjointSolve(torch.autograd.Function):
     """torchdiffeq's ``OdeintAdjointMethod`` with the adaptive solver: forward = the dopri5 solve without a tape, backward = ONE
     launch integrating the augmented system backwards over every output interval with the dopri5 controller
-    (``hode_dopri5_adjoint``; 'seminorm' error control)."""
+    (``hode_dopri5_adjoint``; error control by torchdiffeq's mixed norm or by 'seminorm')."""
 
     @staticmethod
     def forward(ctx, y0, packed, pb, adj_pb, t_eval, holder):
@@ -412,9 +412,21 @@ class _Dopri5AdjointSolve(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_h):
         (h,) = ctx.saved_tensors
+        global _last_adjoint_info
         gy0, gp, stats = ops.dopri5_adjoint(L.get_lib(), ctx.adj_pb, ctx.t_eval, h, grad_h)
-        _raise_on_failure(stats.cpu())
+        st = stats.cpu()
+        _last_adjoint_info = SolveInfo(st)
+        _raise_on_failure(st)
         return gy0, gp.reshape(-1), None, None, None, None
+
+
+_last_adjoint_info = None
+
+
+def last_adjoint_solve_info():
+    """Counters of the most recent ADAPTIVE ADJOINT solve (``odeint_adjoint(method='dopri5')`` backward pass): accepted /
+    rejected attempts per controller summed over the output intervals, status."""
+    return _last_adjoint_info
 
 
 def _raise_on_failure(st: torch.Tensor):
@@ -462,8 +474,9 @@ def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=No
     """torchdiffeq's ``odeint_adjoint`` (the import the reference keeps commented out at ``model.py:9``): same forward
     result as :func:`odeint`, but the backward pass is the CONTINUOUS adjoint -- no tape, O(1) memory in the number of
     solver steps.  Fixed-grid methods (``euler`` / ``midpoint`` / ``rk4``) and ``dopri5`` (the reference's default method;
-    the adaptive adjoint solve needs ``adjoint_options={'norm': 'seminorm'}``, tolerances ``adjoint_rtol`` / ``adjoint_atol``
-    defaulting to the forward ones); the adjoint solve uses the forward method and options unless ``adjoint_method`` /
+    error control of the adaptive adjoint solve by torchdiffeq's default mixed norm -- RocheODE up to latent_dim 8, batch-coupled
+    controller -- or by ``adjoint_options={'norm': 'seminorm'}`` -- every field and controller; tolerances ``adjoint_rtol`` /
+    ``adjoint_atol`` defaulting to the forward ones); the adjoint solve uses the forward method and options unless ``adjoint_method`` /
     ``adjoint_options`` say otherwise (torchdiffeq's defaults).
     ``adjoint_params`` must be the vector field's own parameters (the default): gradients are produced for the packed
     parameter vector as a whole.  Gradients differ from :func:`odeint`'s discrete backprop by the method's
@@ -487,10 +500,22 @@ def odeint_adjoint(func, y0, t, *, rtol=1e-7, atol=1e-9, method=None, options=No
         unused = {k: v for k, v in adjoint_options.items() if k not in known}
         if unused:
             warnings.warn("{}: Unexpected arguments {}".format(_NAMES[adjoint_method], unused))
-    if adjoint_method == "dopri5" and adjoint_options.get("norm") != "seminorm":
-        raise NotImplementedError(
-            "odeint_adjoint(method='dopri5') is built for adjoint_options={'norm': 'seminorm'} (error control by the state and "
-            "the state adjoint); torchdiffeq's default mixed norm additionally lets every parameter adjoint veto a step")
+    if adjoint_method == "dopri5":
+        norm = adjoint_options.get("norm")
+        if norm is not None and norm != "seminorm":
+            raise NotImplementedError("adjoint_options['norm'] must be absent (torchdiffeq's mixed norm) or 'seminorm'")
+        if norm is None:
+            # torchdiffeq's default: the MIXED norm -- every parameter tensor's adjoint takes part in the error control
+            # (hode_dopri5_adjoint without HODE_FLAG_ADJ_SEMINORM: batch-coupled controller, RocheODE up to latent_dim 8)
+            from .real import real_field_kind
+            opts = options or {}
+            ctrl = adjoint_options.get("controller", opts.get("controller", "batch"))
+            if (real_field_kind(func) is not None or field_kind(func) != L.FIELD_ROCHE or int(func.latent_dim) > 8
+                    or ctrl != "batch"):
+                raise NotImplementedError(
+                    "odeint_adjoint(method='dopri5') with torchdiffeq's default mixed norm (every parameter adjoint can veto a "
+                    "step) is built for the RocheODE field up to latent_dim 8 with the batch-coupled controller; pass "
+                    "adjoint_options={'norm': 'seminorm'} (error control by the state and the state adjoint) otherwise")
     adjoint = {"method": adjoint_method, "options": adjoint_options,
                "rtol": rtol if adjoint_rtol is None else adjoint_rtol, "atol": atol if adjoint_atol is None else adjoint_atol}
     return _odeint_impl([func], y0, t, rtol, atol, method, options, event_fn, adjoint=adjoint)
@@ -735,7 +760,8 @@ def _odeint_impl(funcs, y0, t, rtol, atol, method, options, event_fn, adjoint=No
         aopt = adjoint["options"]
         acfg = L.HodeCfg.from_buffer_copy(cfg)
         acfg.rtol, acfg.atol = float(adjoint["rtol"]), float(adjoint["atol"])
-        acfg.flags |= L.FLAG_ADJ_SEMINORM
+        if aopt.get("norm") == "seminorm":
+            acfg.flags |= L.FLAG_ADJ_SEMINORM
         for key, attr in (("safety", "safety"), ("ifactor", "ifactor"), ("dfactor", "dfactor")):
             if key in aopt:
                 setattr(acfg, attr, float(aopt[key]))

@@ -45,6 +45,20 @@ struct CommThreads {
     void sum1(float& a) { float z = 0.f; sum2(a, z); }
     bool any(bool p) { float v = p ? 1.f : 0.f, z = 0.f; sum2(v, z); return v > 0.f; }
     bool all_done(bool done) { return done; }
+    // vector reduction of the mixed adjoint norm: out[k] = sum over the group's threads of v[k]
+    float* vbuf = nullptr;  // [n][N]
+    template <int N>
+    void sum_vec(const float (&v)[N], float* out) {
+        for (int k = 0; k < N; ++k) vbuf[(size_t)tid * N + k] = v[k];
+        bar->arrive_and_wait();
+        for (int k = tid; k < N; k += n) {
+            float t = 0.f;
+            for (int i = 0; i < n; ++i) t += vbuf[(size_t)i * N + k];
+            out[k] = t;
+        }
+        bar->arrive_and_wait();
+    }
+    void sync() { bar->arrive_and_wait(); }
 };
 // Emulation of the device's CommPack (several controller groups in one CTA, all threads in lock-step, the reduction's barrier
 // doubling as the "did anybody still have work" vote): `n` threads = `groups` x `batch` + padding threads that belong to no group.
@@ -254,6 +268,29 @@ void dopri5_adj(const SolveArgs& a, bool eg) {
             if (eg) dopri5_adj_traj<F, true, true>(a, cm, sp.data(), dose(a, idx), R, idx, true, ctrl, leader, count, accp);
             else dopri5_adj_traj<F, false, true>(a, cm, sp.data(), dose(a, idx), R, idx, true, ctrl, leader, count, accp);
         };
+        if constexpr (F::kAccInRegs && F::D <= 8) {
+            if (a.adj_mixed && !a.per_traj) {  // torchdiffeq's default mixed norm (dopri5_adj_mixed_traj)
+                const int n = (int)a.batch;
+                std::barrier<> bar(n);
+                std::vector<float> buf(2 * n), vbuf((size_t)n * 2 * F::P), pg(F::P, 0.f), pq(2 * F::P, 0.f), pr(4, 0.f);
+                std::vector<std::thread> th;
+                for (int b = 0; b < n; ++b)
+                    th.emplace_back([&, b]() {
+                        CommThreads cm{&bar, buf.data(), n, b};
+                        cm.vbuf = vbuf.data();
+                        ParamCtl pc{pg.data(), pq.data(), pr.data()};
+                        std::vector<float> rb(RM::kFloatsPerThread);
+                        RM R{rb.data(), RM::VEC};
+                        const int64_t idx = g * a.batch + b;
+                        if (eg) dopri5_adj_mixed_traj<F, true>(a, cm, sp.data(), dose(a, idx), R, idx, true, g, b == 0, (float)(a.batch * F::D), pc, b, n);
+                        else dopri5_adj_mixed_traj<F, false>(a, cm, sp.data(), dose(a, idx), R, idx, true, g, b == 0, (float)(a.batch * F::D), pc, b, n);
+                    });
+                for (auto& t : th) t.join();
+                const int set = a.pset ? a.pset[g] : 0;
+                for (int i = 0; i < F::P; ++i) a.grad_params[(int64_t)set * F::P + i] += pg[i];
+                continue;
+            }
+        }
         if (a.per_traj) {
             for (int64_t b = 0; b < a.batch; ++b) {
                 const int64_t idx = g * a.batch + b;
@@ -435,10 +472,12 @@ int32_t hode_dopri5_adjoint(const hode_cfg* cfg, int64_t n_groups, int64_t batch
                             const float* dose_t, int64_t dose_t_stride, const float* params, const int32_t* pset,
                             int32_t n_param_sets, const double* t_eval, int32_t n_t, const float* h, const float* grad_h,
                             float* grad_y0, float* grad_params, hode_stats* stats, void*) {
-    if (!(cfg->flags & HODE_FLAG_ADJ_SEMINORM)) return HODE_ERR_UNSUPPORTED;
+    const bool mixed = !(cfg->flags & HODE_FLAG_ADJ_SEMINORM);
+    if (mixed && (cfg->controller != HODE_CTRL_BATCH || cfg->field != HODE_FIELD_ROCHE || cfg->latent_dim > 8)) return HODE_ERR_UNSUPPORTED;
     SolveArgs a; fill(a, cfg, n_groups, batch, dose_amt, dose_t, dose_t_stride, params, pset);
     a.n_param_sets = n_param_sets; a.t_eval_d = t_eval; a.n_t = n_t; a.h_out = const_cast<float*>(h); a.grad_h = grad_h;
     a.stats = stats; a.grad_y0 = grad_y0; a.grad_params = grad_params;
+    a.adj_mixed = mixed ? 1 : 0;
     memset(grad_params, 0, sizeof(float) * pcount(cfg) * n_param_sets);
     return dispatch(DA, *cfg, a);
 }

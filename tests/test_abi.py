@@ -134,15 +134,19 @@ def test_fixed_grid_points_equal_the_oracle():
 
 
 def test_adjoint_surface_and_reversed_time_grids():
-    """odeint_adjoint: torchdiffeq's signature, dopri5 with the seminorm only, no CPU fallback; the adjoint's per-interval grids
+    """odeint_adjoint: torchdiffeq's signature, dopri5 with the mixed norm (where built) or the seminorm, no CPU fallback; the adjoint's per-interval grids
     are torchdiffeq's fixed grid of the negated interval (what the oracle's reverse-time odeint constructs)."""
     m = H.RocheODE(6, 1, 14, 1, device="cpu")
     a = torch.zeros(15, 2, 1)
     a[3, :, 0] = 1.0
     m.set_action(a)
     t = torch.arange(0, 15.0)
-    with pytest.raises(NotImplementedError, match="seminorm"):
-        H.odeint_adjoint(m, torch.zeros(2, 6), t)  # default method dopri5 with torchdiffeq's default mixed norm: not built
+    with pytest.raises(NotImplementedError, match="seminorm"):  # the default mixed norm needs the batch-coupled controller ...
+        H.odeint_adjoint(m, torch.zeros(2, 6), t, options={"controller": "trajectory"})
+    with pytest.raises(NotImplementedError, match="seminorm"):  # ... and RocheODE up to latent_dim 8
+        H.odeint_adjoint(H.NeuralODE(6, 1, 14, 1, device="cpu"), torch.zeros(2, 6), t)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):  # default method dopri5, default (mixed) adjoint norm
+        H.odeint_adjoint(m, torch.zeros(2, 6), t)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         H.odeint_adjoint(m, torch.zeros(2, 6), t, adjoint_options={"norm": "seminorm"})
     with pytest.raises(RuntimeError, match="no CPU fallback"):

@@ -572,8 +572,63 @@ def test_dopri5_continuous_adjoint_seminorm(lib_dadj, D, ctrl):
     assert relerr(gy0, gy0_d) < 5e-4
 
 
-def test_dopri5_adjoint_requires_the_seminorm_flag(lib_dadj):
-    D, B = 6, 2
+@pytest.mark.parametrize("D,experts", [(6, False), (8, False), (6, True), (4, False)])
+def test_dopri5_continuous_adjoint_mixed_norm(lib_dadj, D, experts):
+    """torchdiffeq's DEFAULT adjoint norm (no HODE_FLAG_ADJ_SEMINORM): every parameter tensor's adjoint takes part in the error
+    control, also in every interval's first-step selection.  Loose tolerances put the error estimates far above float32
+    noise, so the ATTEMPT SEQUENCE of the kernel body must be the oracle's: same accepted / rejected counts, and gradients at
+    solver tolerance.  `experts`: the 13 expert scalars are adjoint
+    parameters too (each its own one-element tensor in the norm), else only ml_net (expert_grads=False / requires_grad False)."""
+    lib = lib_dadj
+    B = 4
+    o = oracle_roche(D, 9, True)
+    y0, a, _, _ = make_cohort(B, D, seed=50 + D)
+    if experts:
+        # With the Hill exponents among the adjoint parameters a single NaN in d f / d Hill (a state that an attempt pushes
+        # below zero) makes the error ratio NaN and torchdiffeq -- and the oracle, and the kernel -- stop with 'underflow in
+        # dt nan'; the smooth loose-tolerance problem below does exactly that.  This cohort at 1e-6 stays clear of it, but its
+        # error estimates sit at float32 noise level, so the counts are compared within a band.
+        rtol, atol, T, exact = 1e-6, 1e-7, 6, False
+    else:
+        rtol, atol, T, exact = 1e-3, 1e-4, 4, True
+        a = torch.zeros_like(a); a[0] = 3.0  # smooth: every dose at day 0
+        for n in EXPERT_NAMES:
+            getattr(o, n).requires_grad_(False)
+    o.set_action(a)
+    t = torch.arange(0, float(T))
+    W = torch.randn(T, B, D, generator=torch.Generator().manual_seed(3))
+    counts = {}
+    for name, ao in (("mixed", {}), ("seminorm", {"norm": "seminorm"})):
+        o.zero_grad()
+        z = y0.clone().requires_grad_(True)
+        tr = OI.SolveTrace()
+        ref = OI.odeint_adjoint(o, z, t, rtol=rtol, atol=atol, method="dopri5", adjoint_options=dict(ao, trace=tr))
+        (ref * W).sum().backward()
+        counts[name] = (tr.accepted, tr.rejected)
+        gref = grads_vec(o, False) if experts else torch.cat([torch.zeros(13)] + ([o.ml_net[0].weight.grad.reshape(-1),
+                                                                                   o.ml_net[0].bias.grad.reshape(-1)] if D > 4 else []))
+        cfg = ops.make_cfg(L.FIELD_ROCHE, D, L.DOPRI5, n_dose=1, rtol=rtol, atol=atol, adj_seminorm=name == "seminorm",
+                           expert_grads=experts)
+        pb = problem(o, cfg, B)
+        gy0, gp, st = ops.dopri5_adjoint(lib, pb, t.double(), ref.detach().contiguous(), W)
+        assert int(st[0, 3]) == 0
+        if exact:
+            assert (int(st[0, 0]), int(st[0, 1])) == counts[name], (name, st.tolist(), counts[name])
+        else:
+            n_ref, n_out = sum(counts[name]), int(st[0, 0] + st[0, 1])
+            assert abs(n_out - n_ref) <= 0.15 * n_ref, (name, st.tolist(), counts[name])
+        assert relerr(gy0, z.grad) < 2e-4
+        ok = ~torch.isnan(gref)
+        lo = 2 if experts else 13  # the Hill exponents' gradients are dominated by cancellation
+        if gref[ok][lo:].numel():
+            assert relerr(gp[0][ok][lo:], gref[ok][lo:]) < 5e-4, name
+    # (on this problem the parameter tensors dominate d1 / d2 of every interval's first-step selection -- 5015 and 6520 against
+    # 2539 for the state adjoint at D = 6 -- so equal counts also pin the parameter part of _select_initial_step)
+
+
+def test_dopri5_adjoint_mixed_norm_support(lib_dadj):
+    """The mixed norm is built for the batch-coupled controller and RocheODE up to latent_dim 8; elsewhere the entry refuses."""
+    D, B = 12, 2
     o = oracle_roche(D, 1, False)
     y0, a, _, _ = make_cohort(B, D, seed=1)
     o.set_action(a)
@@ -583,3 +638,11 @@ def test_dopri5_adjoint_requires_the_seminorm_flag(lib_dadj):
     h, _, _ = ops.dopri5_fwd(lib_dadj, pb, y0, t.double(), 0)
     with pytest.raises(NotImplementedError):
         ops.dopri5_adjoint(lib_dadj, pb, t.double(), h, torch.ones_like(h))
+    cfg6 = ops.make_cfg(L.FIELD_ROCHE, 6, L.DOPRI5, n_dose=1, rtol=1e-5, atol=1e-6, controller=L.CTRL_TRAJ)
+    o6 = oracle_roche(6, 1, False)
+    y6, a6, _, _ = make_cohort(B, 6, seed=1)
+    o6.set_action(a6)
+    pb6 = problem(o6, cfg6, B)
+    h6, _, _ = ops.dopri5_fwd(lib_dadj, pb6, y6, t.double(), 0)
+    with pytest.raises(NotImplementedError):
+        ops.dopri5_adjoint(lib_dadj, pb6, t.double(), h6, torch.ones_like(h6))
