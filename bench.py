@@ -746,6 +746,16 @@ def dopri5_extras(lib, dev, fma_peak):
                 "adjoint_accepted_per_call": float(sta[:, 0].float().mean()), "adjoint_rejected_per_call": float(sta[:, 1].float().mean()),
                 "value": int((st0.cpu()[:, 0] + st0.cpu()[:, 1]).sum()) * batch / ((t_f0 + t_a) * 1e-3), "unit": UNIT,
                 "note": "odeint_adjoint(method='dopri5', adjoint_options={'norm': 'seminorm'}): no tape is allocated"}
+            if Dd <= 8:  # torchdiffeq's default mixed norm (built for RocheODE up to latent_dim 8, batch-coupled controller)
+                mcfg = ops.make_cfg(L.FIELD_ROCHE, Dd, L.DOPRI5, n_dose=1, expert_grads=False, hill2=True, rtol=1e-7, atol=1e-8)
+                mpb = ops.Problem(mcfg, ga, batch, m.dosage[:ga * batch], m._dose_t_f32[:ga * batch], pb.params, None)
+                t_m, (_, _, stm) = ev(lambda: ops.dopri5_adjoint(lib, mpb, tt, h0, gh0))
+                stm = stm.cpu()
+                out[name]["adjoint_path"]["mixed_norm"] = {
+                    "adjoint_ms": t_m, "status_ok": bool(int(stm[:, 3].max()) == 0),
+                    "adjoint_accepted_per_call": float(stm[:, 0].float().mean()),
+                    "adjoint_rejected_per_call": float(stm[:, 1].float().mean()),
+                    "note": "torchdiffeq's default adjoint norm: the parameter adjoints take part in the error control"}
             del h0, gh0
         except Exception as e:
             out[name]["adjoint_path"] = {"error": repr(e)}

@@ -89,7 +89,10 @@ typedef struct hode_stats {
  * dx = (ImmuneReact, -Disease theta_1, Dose2, -Immunity theta_2); the packed parameters gain theta_1, theta_2 at the END
  * (after ml_net's bias); the dose schedule is unused.
  * HODE_FLAG_ADJ_SEMINORM (hode_dopri5_adjoint): the adjoint solve is controlled by torchdiffeq's 'seminorm' (state and state
- * adjoint; the parameter adjoints are integrated but take no part in the step-size decisions). */
+ * adjoint; the parameter adjoints are integrated but take no part in the step-size decisions).  Without the flag the solve is
+ * controlled by torchdiffeq's DEFAULT mixed norm: max over (rms of the state part, rms of the state-adjoint part, rms of every
+ * parameter TENSOR's adjoint part -- each expert scalar, ml_net.weight, ml_net.bias) of the scaled error, the parameter
+ * adjoints being those of the whole group (batch-coupled controller, RocheODE up to latent_dim 8; HODE_ERR_UNSUPPORTED else). */
 typedef enum hode_flags { HODE_FLAG_HILL2 = 1, HODE_FLAG_ABLATE = 2, HODE_FLAG_ADJ_SEMINORM = 4 } hode_flags;
 
 typedef struct hode_cfg {
@@ -198,7 +201,7 @@ int32_t hode_dopri5_bwd(const hode_cfg* cfg, int64_t n_groups, int64_t batch, co
  * augmented state (y = h[i], a, g_params) is integrated by the dopri5 controller from t[i] back to t[i-1] (negated time),
  * interpolated to t[i-1] by the quartic dense output; then a += grad_h[i-1], y = h[i-1].  No tape.
  * cfg: rtol / atol = the ADJOINT tolerances; controller BATCH (one controller per group, batch <= 512)
- * or TRAJ; flags must contain HODE_FLAG_ADJ_SEMINORM.  h [n_t, n_traj, D]: the forward solution (hode_dopri5_fwd without a
+ * or TRAJ; flags: HODE_FLAG_ADJ_SEMINORM or none (= mixed norm, see hode_flags).  h [n_t, n_traj, D]: the forward solution (hode_dopri5_fwd without a
  * tape).  stats [n_ctrl]: accepted / rejected attempts summed over the intervals, status as in hode_dopri5_fwd. */
 int32_t hode_dopri5_adjoint(const hode_cfg* cfg, int64_t n_groups, int64_t batch, const float* dose_amt,
                             const float* dose_t, int64_t dose_t_stride, const float* params,
