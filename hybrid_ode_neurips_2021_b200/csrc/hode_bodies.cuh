@@ -1083,17 +1083,35 @@ HODE_HD void dopri5_adj_mixed_traj(const SolveArgs& a, Comm& cm, PS sp, const Do
     cm.sync();
 
     float ES[2 * P], pm[P];  // E = ES[0 .. P), S = ES[P .. 2 P)
+    // up to D = 6 (P = 27) the three vectors stay in registers (fully unrolled loops); above, they are indexed at run time and
+    // live in local memory
+    constexpr bool kVecRegs = P <= 32;
     auto zero_pm = [&]() {
+        if constexpr (kVecRegs) {
+#pragma unroll
+            for (int k = 0; k < P; ++k) pm[k] = 0.0f;
+        } else {
 #pragma unroll 1
-        for (int k = 0; k < P; ++k) pm[k] = 0.0f;
+            for (int k = 0; k < P; ++k) pm[k] = 0.0f;
+        }
     };
     auto fold = [&](float we, float ws) {  // E += we pm, S += ws pm
+        if constexpr (kVecRegs) {
+#pragma unroll
+            for (int k = 0; k < P; ++k) { ES[k] = fmaf(we, pm[k], ES[k]); ES[P + k] = fmaf(ws, pm[k], ES[P + k]); }
+        } else {
 #pragma unroll 1
-        for (int k = 0; k < P; ++k) { ES[k] = fmaf(we, pm[k], ES[k]); ES[P + k] = fmaf(ws, pm[k], ES[P + k]); }
+            for (int k = 0; k < P; ++k) { ES[k] = fmaf(we, pm[k], ES[k]); ES[P + k] = fmaf(ws, pm[k], ES[P + k]); }
+        }
     };
     auto zero_es = [&]() {
+        if constexpr (kVecRegs) {
+#pragma unroll
+            for (int k = 0; k < 2 * P; ++k) ES[k] = 0.0f;
+        } else {
 #pragma unroll 1
-        for (int k = 0; k < 2 * P; ++k) ES[k] = 0.0f;
+            for (int k = 0; k < 2 * P; ++k) ES[k] = 0.0f;
+        }
     };
 
     for (int iv = 0; iv + 1 < a.n_t && status == HODE_SOLVE_OK; ++iv) {

@@ -94,12 +94,18 @@ struct CommCta {
     template <int N>
     __device__ __forceinline__ void sum_vec(const float (&v)[N], float* out) {
         const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll 1
-        for (int k = 0; k < N; ++k) {
+        auto one = [&](int k) {
             float x = v[k];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
             if (lane == 0) vbuf[wid * N + k] = x;
+        };
+        if constexpr (N <= 64) {  // compile-time indices: `v` can stay in registers
+#pragma unroll
+            for (int k = 0; k < N; ++k) one(k);
+        } else {
+#pragma unroll 1
+            for (int k = 0; k < N; ++k) one(k);
         }
         __syncthreads();
         for (int k = threadIdx.x; k < N; k += blockDim.x) {
