@@ -294,7 +294,9 @@ struct Roche {
     static constexpr int SP = OFF_WT + ML * D_;
     static_assert(ML % 2 == 0 && D_ % 2 == 0, "packed loops assume even D and ML");
     static constexpr bool kAccInRegs = true;  // per-thread gradient accumulators fit in registers
-    static constexpr bool kConstBank = true;  // staged parameters may be read from the constant bank (hode_launch.cuh)
+    // staged parameters may be read from the constant bank (hode_launch.cuh); the rarely used generic-Hill / ablation variants keep
+    // them in shared memory only (half the kernels to build)
+    static constexpr bool kConstBank = HILL2_ && !ABLATE_;
 
     // cooperative copy of one packed parameter set into the staged layout (thread `tid` of `nthr`).
     // With HODE_FOLD_TANH the ml_net weights and biases are pre-multiplied by 2 log2(e): W y + b is then directly the

@@ -905,6 +905,22 @@ inline int set_smem(K kernel, size_t bytes) {
         if (e_ != cudaSuccess) return (int)e_;                \
     } while (0)
 
+// The n_dose == 1 specialisation (dose schedule in registers) doubles the number of kernels of a field.  It is compiled for
+// the variants every reference call site uses (Hill exponents of 2, the NeuralODE field); the generic-Hill-exponent and ablation
+// variants of RocheODE -- taken only when somebody trains the Hill exponents / runs the ablation study -- use the general
+// dose path and shared-memory parameters (Roche::kConstBank), which quarters their share of the build.
+template <class F> struct NdSpecial { static constexpr bool value = true; };
+template <int D, bool A> struct NdSpecial<Roche<D, false, A>> { static constexpr bool value = false; };
+template <int D> struct NdSpecial<Roche<D, true, true>> { static constexpr bool value = false; };
+#define HODE_ND(A, B)                                 \
+    do {                                              \
+        if constexpr (NdSpecial<F>::value) {          \
+            if (nd1) { A; } else { B; }               \
+        } else {                                      \
+            B;                                        \
+        }                                             \
+    } while (0)
+
 // Runs `LAUNCH(CPFLAG)` with CPFLAG = true behind a constant-bank lease when the launch qualifies, else CPFLAG = false.
 #define HODE_DISPATCH_CP(F, a, st, LAUNCH)                               \
     do {                                                                 \
@@ -948,9 +964,9 @@ int launch_fixed_fwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st
 #define HODE_FF(M, ND, CP) fixed_fwd_kernel<F, M, ND, CP><<<(unsigned)nblk, threads, (CP ? 0 : F::SP) * sizeof(float), st>>>(a, tiles)
 #define HODE_FF_CP(CP)                                                                                   \
     switch (cfg.method) {                                                                                \
-        case HODE_EULER: if (nd1) HODE_FF(M_EULER, 1, CP); else HODE_FF(M_EULER, 0, CP); break;          \
-        case HODE_MIDPOINT: if (nd1) HODE_FF(M_MIDPOINT, 1, CP); else HODE_FF(M_MIDPOINT, 0, CP); break; \
-        case HODE_RK4_38: if (nd1) HODE_FF(M_RK4_38, 1, CP); else HODE_FF(M_RK4_38, 0, CP); break;       \
+        case HODE_EULER: HODE_ND(HODE_FF(M_EULER, 1, CP), HODE_FF(M_EULER, 0, CP)); break;          \
+        case HODE_MIDPOINT: HODE_ND(HODE_FF(M_MIDPOINT, 1, CP), HODE_FF(M_MIDPOINT, 0, CP)); break; \
+        case HODE_RK4_38: HODE_ND(HODE_FF(M_RK4_38, 1, CP), HODE_FF(M_RK4_38, 0, CP)); break;       \
         default: return -1;                                                                              \
     }
     HODE_DISPATCH_CP(F, a, st, HODE_FF_CP);
@@ -1028,8 +1044,8 @@ int launch_fixed_bwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st
     } while (0)
 #define HODE_FB_M(M, CP)                                                           \
     do {                                                                           \
-        if (eg) { if (nd1) HODE_FB(M, true, 1, CP); else HODE_FB(M, true, 0, CP); } \
-        else    { if (nd1) HODE_FB(M, false, 1, CP); else HODE_FB(M, false, 0, CP); } \
+        if (eg) { HODE_ND(HODE_FB(M, true, 1, CP), HODE_FB(M, true, 0, CP)); } \
+        else    { HODE_ND(HODE_FB(M, false, 1, CP), HODE_FB(M, false, 0, CP)); } \
     } while (0)
 #define HODE_FB_CP(CP)                                      \
     switch (cfg.method) {                                   \
@@ -1063,8 +1079,8 @@ int launch_fixed_adj(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t st
     } while (0)
 #define HODE_FA_M(M, CP)                                                           \
     do {                                                                           \
-        if (eg) { if (nd1) HODE_FA(M, true, 1, CP); else HODE_FA(M, true, 0, CP); } \
-        else    { if (nd1) HODE_FA(M, false, 1, CP); else HODE_FA(M, false, 0, CP); } \
+        if (eg) { HODE_ND(HODE_FA(M, true, 1, CP), HODE_FA(M, true, 0, CP)); } \
+        else    { HODE_ND(HODE_FA(M, false, 1, CP), HODE_FA(M, false, 0, CP)); } \
     } while (0)
 #define HODE_FA_CP(CP)                                      \
     switch (cfg.method) {                                   \
@@ -1107,7 +1123,7 @@ int launch_dopri5_fwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t s
         cudaError_t le_ = cudaLaunchKernelEx(&lc, dopri5_fwd_cluster_kernel<F, ND, CP>, a);                               \
         if (le_ != cudaSuccess) return (int)le_;                                                                          \
     } while (0)
-#define HODE_DC_CP(CP) do { if (nd1) HODE_DC(1, CP); else HODE_DC(0, CP); } while (0)
+#define HODE_DC_CP(CP) do { HODE_ND(HODE_DC(1, CP), HODE_DC(0, CP)); } while (0)
         HODE_DISPATCH_CP(F, a, st, HODE_DC_CP);
 #undef HODE_DC_CP
 #undef HODE_DC
@@ -1128,7 +1144,7 @@ int launch_dopri5_fwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t s
         if (e_ != 0) return e_;                                                                                                  \
         dopri5_fwd_seg_kernel<F, ND, CP><<<(unsigned)nblk, threads, sh_, st>>>(a);                                               \
     } while (0)
-#define HODE_DS_CP(CP) do { if (nd1) HODE_DS(1, CP); else HODE_DS(0, CP); } while (0)
+#define HODE_DS_CP(CP) do { HODE_ND(HODE_DS(1, CP), HODE_DS(0, CP)); } while (0)
         HODE_DISPATCH_CP(F, a, st, HODE_DS_CP);
 #undef HODE_DS_CP
 #undef HODE_DS
@@ -1153,7 +1169,7 @@ int launch_dopri5_fwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t s
         if (e_ != 0) return e_;                                                                                                \
         dopri5_fwd_pack_kernel<F, ND, CP><<<(unsigned)nblk, pthreads, sh_, st>>>(a, gpc);                                      \
     } while (0)
-#define HODE_DP_CP(CP) do { if (nd1) HODE_DP(1, CP); else HODE_DP(0, CP); } while (0)
+#define HODE_DP_CP(CP) do { HODE_ND(HODE_DP(1, CP), HODE_DP(0, CP)); } while (0)
             HODE_DISPATCH_CP(F, a, st, HODE_DP_CP);
 #undef HODE_DP_CP
 #undef HODE_DP
@@ -1174,9 +1190,9 @@ int launch_dopri5_fwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t s
     } while (0)
 #define HODE_DF_CP(CP)                                                                                       \
     do {                                                                                                     \
-        if (a.per_traj) { if (nd1) HODE_DF(true, 1, 128, CP); else HODE_DF(true, 0, 128, CP); }              \
-        else if (threads <= 128) { if (nd1) HODE_DF(false, 1, 128, CP); else HODE_DF(false, 0, 128, CP); }   \
-        else { if (nd1) HODE_DF(false, 1, HODE_DOPRI5_MAX_THREADS, CP); else HODE_DF(false, 0, HODE_DOPRI5_MAX_THREADS, CP); } \
+        if (a.per_traj) { HODE_ND(HODE_DF(true, 1, 128, CP), HODE_DF(true, 0, 128, CP)); }              \
+        else if (threads <= 128) { HODE_ND(HODE_DF(false, 1, 128, CP), HODE_DF(false, 0, 128, CP)); }   \
+        else { HODE_ND(HODE_DF(false, 1, HODE_DOPRI5_MAX_THREADS, CP), HODE_DF(false, 0, HODE_DOPRI5_MAX_THREADS, CP)); } \
     } while (0)
     HODE_DISPATCH_CP(F, a, st, HODE_DF_CP);
 #undef HODE_DF_CP
@@ -1204,8 +1220,8 @@ int launch_dopri5_bwd(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t s
     } while (0)
 #define HODE_DB_CP(CP)                                                         \
     do {                                                                       \
-        if (eg) { if (nd1) HODE_DB(true, 1, CP); else HODE_DB(true, 0, CP); }  \
-        else    { if (nd1) HODE_DB(false, 1, CP); else HODE_DB(false, 0, CP); } \
+        if (eg) { HODE_ND(HODE_DB(true, 1, CP), HODE_DB(true, 0, CP)); }  \
+        else    { HODE_ND(HODE_DB(false, 1, CP), HODE_DB(false, 0, CP)); } \
     } while (0)
     HODE_DISPATCH_CP(F, a, st, HODE_DB_CP);
 #undef HODE_DB_CP
@@ -1237,7 +1253,7 @@ int launch_dopri5_adj(const hode_cfg& cfg, const SolveArgs& a_in, cudaStream_t s
         if (e_ != 0) return e_;                                                                                    \
         dopri5_adj_kernel<F, PT, EG, ND, MAXT, CP><<<(unsigned)nblk, threads, sh_, st>>>(a, tiles);                \
     } while (0)
-#define HODE_DA_ND(PT, EG, MAXT, CP) do { if (nd1) HODE_DA(PT, EG, 1, MAXT, CP); else HODE_DA(PT, EG, 0, MAXT, CP); } while (0)
+#define HODE_DA_ND(PT, EG, MAXT, CP) do { HODE_ND(HODE_DA(PT, EG, 1, MAXT, CP), HODE_DA(PT, EG, 0, MAXT, CP)); } while (0)
 #define HODE_DA_EG(PT, MAXT, CP) do { if (eg) HODE_DA_ND(PT, true, MAXT, CP); else HODE_DA_ND(PT, false, MAXT, CP); } while (0)
 #define HODE_DA_CP(CP)                                                              \
     do {                                                                            \
