@@ -316,6 +316,25 @@ def test_mid_size_groups_packed_into_one_cta_match_single_calls(D, B):
     check("packed mid-size groups D={} batch={} vs single calls, dL/dW".format(D, B), relerr(gw, gw_sum), 5e-4)
 
 
+def test_packed_and_cluster_shapes_with_shared_memory_parameters():
+    """The generic-Hill-exponent kernels (options={'hill2_kernels': False}) keep their parameters in shared memory instead of the
+    constant bank: the packed (several groups per CTA) and the cluster (one group over several CTAs) launch shapes must give
+    the constant-bank kernels' results -- same arithmetic except pow(x, 2) for x * x."""
+    t = torch.arange(0, 15.0).to(DEV)
+    for D, B, G in ((6, 20, 7), (6, 700, 1)):
+        o, m = build_pair(D)
+        y0, a = smooth_cohort(B * G, D, seed=33)
+        m.set_action(a.to(DEV))
+        outs = []
+        for h2 in (True, False):
+            with torch.no_grad():
+                outs.append(H.odeint(m, y0.to(DEV), t, rtol=1e-5, atol=1e-6, method="dopri5",
+                                     options={"n_groups": G, "hill2_kernels": h2}))
+            info = H.last_solve_info()
+            assert bool((info.stats[:, 3] == 0).all())
+        check("shared-memory parameters vs constant bank, D={} batch={} x {}".format(D, B, G), relerr(outs[1], outs[0]), 2e-5)
+
+
 def test_small_groups_share_warps_and_flat_launches_match_single_calls():
     """C3 shape (run_dim.sh:41): groups of 10 patients.  Batch-coupled dopri5 packs three groups per warp (lane segments),
     fixed-grid and reverse-sweep kernels enumerate trajectories across groups; both must equal one call per group."""
