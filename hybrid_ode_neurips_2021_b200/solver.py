@@ -416,7 +416,19 @@ class _Dopri5AdjointSolve(torch.autograd.Function):
         gy0, gp, stats = ops.dopri5_adjoint(L.get_lib(), ctx.adj_pb, ctx.t_eval, h, grad_h)
         st = stats.cpu()
         _last_adjoint_info = SolveInfo(st)
-        _raise_on_failure(st)
+        try:
+            _raise_on_failure(st)
+        except AssertionError as e:
+            cfg = ctx.adj_pb.cfg
+            if not (cfg.flags & L.FLAG_ADJ_SEMINORM) and cfg.expert_grads:
+                # torchdiffeq fails the same way ('underflow in dt nan'): under its default mixed norm ONE NaN in a parameter's
+                # error estimate -- d f / d Hill = x**p log x at a state an attempt pushed below zero -- makes the ratio NaN
+                raise AssertionError(
+                    str(e) + " -- adjoint solve under torchdiffeq's default mixed norm with the 13 expert scalars among the "
+                    "adjoint parameters: a NaN in d f / d HillCure / d HillPatho poisons the error norm (torchdiffeq stops the "
+                    "same way).  Pass options={'expert_grads': False} (the reference never trains the expert scalars, "
+                    "run_simulation.py:125-129) or adjoint_options={'norm': 'seminorm'}") from None
+            raise
         return gy0, gp.reshape(-1), None, None, None, None
 
 
